@@ -1,0 +1,213 @@
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Container-only (needs /root/reference):   python tests/golden/make_golden.py
+
+Imports ``/root/reference/code`` through ``oracle/ref_import.py`` (third-party packages
+that are absent offline are stubbed; ``torch_geometric.nn.GATv2Conv`` is the restatement
+in ``oracle/gatv2conv.py``), runs the reference's own ``SceneData`` / ``GraphAttnSfMNet``
+/ ``SetOfSetLayer`` / ``SparseMat`` on small seeded inputs, checks that
+``oracle/gasfm_cpu.py`` reproduces them, and stores inputs, weights and outputs as
+small ``.npz`` files.  The fixtures travel to the GPU box; the reference does not.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import gasfm_cpu, ref_import  # noqa: E402
+
+MODEL_VARIANTS = {
+    # name: (model-conf overrides, scene (m, n, density, seed))
+    "tiny_shipped_like": (dict(), (10, 80, 0.35, 11)),
+    "tiny_global2node_hidden1": (dict(global2view_and_global2scenepoint_enabled=True,
+                                      n_hidden_layers_scenepoint_update=1, n_hidden_layers_view_update=1,
+                                      n_hidden_layers_global_update=1, n_hidden_layers_proj_update=1,
+                                      add_skipconn_from_init_projfeat=False), (9, 70, 0.4, 12)),
+    "tiny_stateless_nonorm": (dict(stateful_global_features=False, use_norm_proj_update=False,
+                                   n_feat_proj=12, n_heads=2), (12, 60, 0.3, 13)),
+    "tiny_projective_depthhead": (dict(depth_head=dict(enabled=True, n_feat=20, n_hidden_layers=1),
+                                       view_head=dict(enabled=True, n_hidden_layers=1,
+                                                      normalize_output="Differentiable Chirality"),
+                                       _calibrated=False), (8, 64, 0.4, 14)),
+    "tiny_rot6d": (dict(view_head=dict(enabled=True, n_hidden_layers=2, rot_representation="6d"),
+                        num_layers=2), (8, 48, 0.4, 15)),
+}
+
+
+def model_conf(**over):
+    model = dict(type="graph_attn_sfm.GraphAttnSfMNet", n_heads=4, stateful_global_features=True,
+                 global2view_and_global2scenepoint_enabled=False, n_feat_proj=16, n_feat_scenepoint=8,
+                 n_feat_view=32, n_feat_global=64, num_layers=3,
+                 n_hidden_layers_scenepoint_update=0, n_hidden_layers_view_update=0,
+                 n_hidden_layers_global_update=0, n_hidden_layers_proj_update=0,
+                 use_norm_proj_update=True, add_residual_skipconn_proj_update=True,
+                 add_skipconn_from_init_projfeat=True, pos_emb_n_freq=0,
+                 depth_head=dict(enabled=False, n_feat=128, n_hidden_layers=2),
+                 view_head=dict(enabled=True, n_hidden_layers=2, rot_representation="quat"),
+                 scenepoint_head=dict(enabled=True, n_hidden_layers=2))
+    over = dict(over)
+    calibrated = over.pop("_calibrated", True)
+    model.update(over)
+    return dict(dataset=dict(calibrated=calibrated), model=model)
+
+
+def random_dense_scene(m, n, density, seed):
+    """Dense M with deliberate degenerate tracks: an empty column, a single-view column."""
+    g = torch.Generator().manual_seed(seed)
+    mask = torch.rand(m, n, generator=g) < density
+    mask[:, 3] = False                      # unobserved track
+    mask[:, 5] = False
+    mask[2, 5] = True                       # seen once -> dropped by MIN_N_VIEWS_PER_POINT
+    xy = torch.randn(m, 2, n, generator=g) * 300 + 500
+    M = (xy * mask[:, None, :]).reshape(2 * m, n)
+    K = torch.eye(3).repeat(m, 1, 1)
+    K[:, 0, 0] = K[:, 1, 1] = 800 + 50 * torch.rand(m, generator=g)
+    K[:, 0, 2], K[:, 1, 2] = 500.0, 480.0
+    Ns = torch.inverse(K)
+    return M, Ns
+
+
+def to_np(d):
+    return {k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def main():
+    ref = ref_import.import_reference()
+    torch.set_num_threads(4)
+
+    # ---- index build + graphs (bit-exact ints) -------------------------------------------
+    M, Ns = random_dense_scene(7, 50, 0.4, 3)
+    M[2 * 6:, :] = 0
+    M[2 * 6, :5] = 1.0                      # a view with < 8 points: excluded from view2global
+    data = ref.SceneData.SceneData(M, Ns, torch.zeros(7, 3, 4), "golden", calibrated=True)
+    fix = dict(M=M, Ns=Ns, values=data.x.values, indices=data.x.indices,
+               cam_per_pts=data.x.cam_per_pts, pts_per_cam=data.x.pts_per_cam,
+               shape=np.array(data.x.shape))
+    for name, gw in data.graph_wrappers.items():
+        fix[f"{name}.edge_index"] = gw.edge_index
+        fix[f"{name}.valid_indices"] = gw.valid_indices
+        fix[f"{name}.meta"] = np.array([gw.m, gw.n, gw.agg_dim, gw.n_agg_nodes])
+    # the invariant documented (commented out) at SceneData.py:189-230
+    nf = data.graph_wrappers["proj2view"].generate_node_features(data.x.to_torch_hybrid_sparse_coo())
+    norm_M = ref.geo_utils.normalize_M(M, Ns)
+    assert torch.equal(nf[: data.x.indices.shape[1]], norm_M[data.x.indices[0], data.x.indices[1], :])
+    ora = gasfm_cpu.make_scene(M, Ns)
+    assert torch.equal(ora["x"]["indices"], data.x.indices)
+    assert torch.equal(ora["x"]["values"], data.x.values)
+    assert torch.equal(ora["x"]["cam_per_pts"], data.x.cam_per_pts)
+    assert torch.equal(ora["x"]["pts_per_cam"], data.x.pts_per_cam)
+    for name, gw in data.graph_wrappers.items():
+        assert torch.equal(ora["graphs"][name]["edge_index"], gw.edge_index), name
+        assert torch.equal(ora["graphs"][name]["valid_indices"], gw.valid_indices), name
+    np.savez_compressed(os.path.join(HERE, "index_build.npz"), **to_np(fix))
+    print("index_build: E =", data.x.indices.shape[1])
+
+    # ---- SparseMat pooling + DPESFM layer ------------------------------------------------
+    torch.manual_seed(5)
+    feat = torch.randn(data.x.indices.shape[1], 6)
+    sm = ref.sparse_utils.SparseMat(feat, data.x.indices, data.x.cam_per_pts, data.x.pts_per_cam, (7, 50, 6))
+    layer = ref.layers.SetOfSetLayer(6, 10)
+    out = layer(sm)
+    pfix = dict(indices=data.x.indices, feat=feat, shape=np.array([7, 50, 6]), sum0=sm.sum(0), sum1=sm.sum(1),
+                mean0=sm.mean(0), mean1=sm.mean(1), sos_out=out.values)
+    sd = {k: v for k, v in layer.state_dict().items()}
+    pfix.update({f"param.{k}": v for k, v in sd.items()})
+    assert torch.allclose(gasfm_cpu.sparse_sum(feat, data.x.indices, (7, 50, 6), 0), sm.sum(0))
+    o2 = gasfm_cpu.set_of_set_layer(gasfm_cpu._P(sd), feat, data.x.indices, (7, 50, 6))
+    assert torch.allclose(o2, out.values, atol=1e-6), (o2 - out.values).abs().max()
+    np.savez_compressed(os.path.join(HERE, "pooling.npz"), **to_np(pfix))
+    print("pooling ok")
+
+    # ---- full model, three configurations -------------------------------------------------
+    for name, (over, (m, n, dens, seed)) in MODEL_VARIANTS.items():
+        conf_d = model_conf(**over)
+        conf = ref.ConfigTree.from_dict(conf_d)
+        torch.manual_seed(seed)
+        model = ref.graph_attn_sfm.GraphAttnSfMNet(conf)
+        # non-trivial norm parameters / conv biases so that every term is exercised
+        with torch.no_grad():
+            for k, v in model.named_parameters():
+                if k.endswith("graph_conv.bias") or "norm" in k or k.endswith("2global.bias"):
+                    v.add_(0.1 * torch.randn_like(v))
+        M, Ns = random_dense_scene(m, n, dens, seed)
+        data = ref.SceneData.SceneData(M, Ns, torch.zeros(m, 3, 4), name, calibrated=True)
+        fix = dict(M=M, Ns=Ns)
+        sd = model.state_dict()
+        for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+            mdl = model.to(dtype)
+            d2 = ref.SceneData.SceneData(M.to(dtype), Ns.to(dtype), torch.zeros(m, 3, 4, dtype=dtype), name, calibrated=True)
+            # the wrapper hard-codes float32 zeros for stateless queries (dataset_utils.py:571)
+            mdl.zero_grad()
+            if dtype == torch.float64:
+                _patch_zero_query_dtype(ref, dtype)
+            out = mdl(d2)
+            w = torch.linspace(0.5, 1.5, out["Ps_norm"].numel(), dtype=dtype).reshape(out["Ps_norm"].shape)
+            w2 = torch.linspace(-1.0, 1.0, out["pts3D"].numel(), dtype=dtype).reshape(out["pts3D"].shape)
+            loss = (out["Ps_norm"] * w).sum() + (out["pts3D"] * w2).sum()
+            if "depths" in out:
+                loss = loss + (out["depths"].values ** 2).sum()
+                fix[f"out.{tag}.depths"] = out["depths"].values
+            loss.backward()
+            fix[f"out.{tag}.Ps_norm"] = out["Ps_norm"]
+            fix[f"out.{tag}.pts3D"] = out["pts3D"]
+            fix[f"loss.{tag}"] = loss
+            for k, v in mdl.named_parameters():
+                fix[f"grad.{tag}.{k}"] = v.grad
+            # oracle agreement (same dtype)
+            params = {k: v.detach().clone().requires_grad_(True) for k, v in mdl.state_dict().items()}
+            scene = gasfm_cpu.make_scene(M.to(dtype), Ns.to(dtype))
+            mc = conf_d["model"]
+            o = gasfm_cpu.gasfm_forward(params, scene, n_heads=mc["n_heads"], stateful=mc["stateful_global_features"],
+                                        calibrated=conf_d["dataset"]["calibrated"],
+                                        rot_representation=mc["view_head"].get("rot_representation", "quat"),
+                                        normalize_output=mc["view_head"].get("normalize_output"))
+            tol = 1e-5 if dtype == torch.float32 else 1e-12
+            for key in ("Ps_norm", "pts3D"):
+                err = (o[key] - out[key]).abs().max().item()
+                assert err <= tol * max(1.0, out[key].abs().max().item()), (name, tag, key, err)
+            l2 = (o["Ps_norm"] * w).sum() + (o["pts3D"] * w2).sum()
+            if "depths" in o:
+                assert (o["depths"] - out["depths"].values).abs().max().item() <= tol * 10
+                l2 = l2 + (o["depths"] ** 2).sum()
+            l2.backward()
+            # gradients that are analytically zero (softmax shift-invariance) are pure rounding
+            # noise, so errors are scaled by max(|g_param|, 1e-3 * largest gradient in the model)
+            worst = 0.0
+            gscale = 1e-3 * max(v.grad.abs().max().item() for v in mdl.parameters())
+            for k, v in mdl.named_parameters():
+                gerr = (params[k].grad - v.grad).abs().max().item() / max(gscale, v.grad.abs().max().item())
+                worst = max(worst, gerr)
+            assert worst < (2e-3 if dtype == torch.float32 else 1e-9), (name, tag, worst)
+            print(f"{name} [{tag}]: E={scene['x']['indices'].shape[1]} oracle-vs-reference out ok, worst grad rel err {worst:.2e}")
+        model.to(torch.float32)
+        fix.update({f"param.{k}": v for k, v in sd.items()})
+        fix["conf_json"] = np.array(__import__("json").dumps(conf_d))
+        np.savez_compressed(os.path.join(HERE, f"model_{name}.npz"), **to_np(fix))
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+def _patch_zero_query_dtype(ref, dtype):
+    """fp64 ground truth only: AxialAggregationGraphWrapper.generate_node_features creates
+    float32 zeros for absent queries (dataset_utils.py:571); run the fp64 pass with the
+    default dtype switched so that the concat is dtype-consistent."""
+    orig = ref.dataset_utils.AxialAggregationGraphWrapper.generate_node_features
+    if getattr(orig, "_patched", False):
+        return
+
+    def gen(self, M, x_agg=None):
+        if x_agg is None:
+            x_agg = torch.zeros((self.n_agg_nodes, M.shape[2]), dtype=M.dtype, device=self.device)
+        return orig(self, M, x_agg)
+
+    gen._patched = True
+    ref.dataset_utils.AxialAggregationGraphWrapper.generate_node_features = gen
+
+
+if __name__ == "__main__":
+    main()
