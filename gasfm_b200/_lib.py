@@ -1,0 +1,98 @@
+"""ctypes binding of ``libgasfm_b200.so`` (the C ABI declared in ``include/gasfm_b200.h``).
+
+There is deliberately no fallback: if the shared library is missing or an entry point
+fails, a ``RuntimeError`` is raised.  The library is built in-tree by
+``__graft_entry__.build()`` / ``make -C gasfm_b200/csrc``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgasfm_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gasfm_b200.h")
+
+_c = ctypes
+_P = _c.c_void_p
+_I, _L, _F, _SZ = _c.c_int, _c.c_int64, _c.c_float, _c.c_size_t
+
+# name -> (restype, argtypes); mirrors include/gasfm_b200.h one to one
+SIGNATURES = {
+    "gasfm_abi_version": (_I, []),
+    "gasfm_last_error": (_c.c_char_p, []),
+    "gasfm_m2sparse_count": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "gasfm_m2sparse_ws_bytes": (_SZ, [_I, _I]),
+    "gasfm_m2sparse_fill": (_I, [_P, _P, _P, _I, _I, _L, _P, _P, _P, _P]),
+    "gasfm_csr_build": (_I, [_P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "gasfm_plan_chunks": (_I, [_P, _I, _I, _P, _P, _I, _P]),
+    "gasfm_gat_ws_bytes": (_SZ, [_I, _I, _I]),
+    "gasfm_gat_edge_fwd": (_I, [_P, _L, _P, _L, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _F, _I,
+                                _P, _P, _P, _P, _P]),
+    "gasfm_gat_bwd_ws_bytes": (_SZ, [_L, _I, _I, _I, _I]),
+    "gasfm_gat_edge_bwd": (_I, [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _F,
+                                _P, _L, _P, _P, _P, _P]),
+    "gasfm_seg_sum": (_I, [_P, _L, _I, _P, _P, _I, _I, _P, _P, _I, _F, _I, _P, _P, _P]),
+    "gasfm_seg_sum_ws_bytes": (_SZ, [_I, _I]),
+    "gasfm_seg_bcast": (_I, [_P, _I, _P, _P, _L, _F, _I, _P, _P]),
+    "gasfm_ln_relu_fwd": (_I, [_P, _L, _I, _P, _P, _F, _P, _P, _P, _P]),
+    "gasfm_ln_relu_bwd_ws_bytes": (_SZ, [_L, _I]),
+    "gasfm_ln_relu_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _P]),
+    "gasfm_edge_update_fwd": (_I, [_P, _L, _P, _I, _P, _P, _P, _P, _P, _L, _P, _P, _L, _I, _F, _F, _P, _P]),
+    "gasfm_csr_build_host": (_I, [_P, _L, _I, _I, _P, _P, _P]),
+    "gasfm_gat_edge_fwd_host": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P]),
+}
+
+_lib = None
+launch_count = 0  # number of C-ABI compute calls made (bench.py reports kernel launches from this)
+
+
+def load():
+    """Load the shared library (once) and attach the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"gasfm_b200: {LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C gasfm_b200/csrc`. There is no CPU or PyTorch fallback for the CUDA path."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().gasfm_last_error().decode("utf-8", "replace")
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; raise on a non-zero return code."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    launch_count += 1
+    if rc != 0:
+        msg = last_error()
+        if "out of memory" in msg.lower():
+            import torch
+
+            raise torch.cuda.OutOfMemoryError(f"{name}: {msg}")
+        raise RuntimeError(f"{name} failed (code {rc}): {msg}")
+
+
+def size_query(name, *args):
+    return int(getattr(load(), name)(*args))
+
+
+def ptr(t):
+    """Device (or host) address of a tensor, or NULL."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,288 @@
+"""torch.autograd bindings of the C-ABI kernels.
+
+Every function here launches hand-written sm_100a kernels through ``_lib.call``; inputs must be
+CUDA fp32 tensors.  There is no CPU or pure-PyTorch fallback: a CPU tensor raises.
+"""
+import torch
+
+from . import _lib
+from .index import SegmentPlan
+
+LEAKY_SLOPE = 0.2  # GATv2Conv default negative_slope (the reference never overrides it)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gasfm_b200 ops run on CUDA tensors only (no CPU fallback); got a tensor on %s" % t.device)
+        if t is not None and t.dtype != torch.float32:
+            raise RuntimeError("gasfm_b200 ops are fp32; got %s" % t.dtype)
+
+
+def _rows(t):
+    """(tensor, row stride) of a 2-D tensor whose rows are contiguous; copies otherwise."""
+    if t.dim() != 2:
+        raise ValueError("expected a 2-D tensor")
+    if t.stride(1) != 1 and t.shape[1] != 1:
+        t = t.contiguous()
+    if t.shape[1] == 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    return t, t.stride(0) if t.shape[0] > 1 else t.shape[1]
+
+
+# ---------------------------------------------------------------------------------------------
+# fused GATv2 edge attention
+# ---------------------------------------------------------------------------------------------
+class _GatEdge(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, XL, XR, att, bias, plan, heads):
+        _require_cuda(XL, XR, att, bias)
+        XL, ldxl = _rows(XL)
+        hc = XL.shape[1]
+        head_dim = hc // heads
+        T = plan.n_seg
+        bcast = XR.shape[0] == 1 and T != 1
+        XR = XR.contiguous()
+        ldxr = 0 if bcast else hc
+        att_flat = att.reshape(-1).contiguous()
+        dev = XL.device
+        out = torch.empty((T, hc), dtype=torch.float32, device=dev)
+        seg_max = torch.empty((T, heads), dtype=torch.float32, device=dev)
+        seg_sum = torch.empty((T, heads), dtype=torch.float32, device=dev)
+        ws = None
+        if plan.chunk > 0:
+            ws = plan.workspace(_lib.size_query("gasfm_gat_ws_bytes", plan.max_chunks, heads, head_dim), dev)
+        with torch.cuda.device(dev):
+            _lib.call("gasfm_gat_edge_fwd", _lib.ptr(XL), ldxl, _lib.ptr(XR), ldxr, _lib.ptr(att_flat), _lib.ptr(bias),
+                      *plan.abi_args(), heads, head_dim, LEAKY_SLOPE, 1,
+                      _lib.ptr(out), _lib.ptr(seg_max), _lib.ptr(seg_sum), _lib.ptr(ws), _lib.stream_ptr())
+        ctx.save_for_backward(XL, XR, att_flat, bias, out, seg_max, seg_sum)
+        ctx.plan, ctx.heads, ctx.bcast, ctx.att_shape = plan, heads, bcast, att.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        XL, XR, att_flat, bias, out, seg_max, seg_sum = ctx.saved_tensors
+        plan, heads = ctx.plan, ctx.heads
+        hc = XL.shape[1]
+        head_dim = hc // heads
+        dev = XL.device
+        d_out = d_out.contiguous()
+        out_nobias = out if bias is None else out - bias
+        covers_all = plan.perm is None or plan.n_edges == XL.shape[0]
+        dXL = (torch.empty if covers_all else torch.zeros)((XL.shape[0], hc), dtype=torch.float32, device=dev)
+        dXR = torch.empty((plan.n_seg, hc), dtype=torch.float32, device=dev)
+        datt = torch.empty(hc, dtype=torch.float32, device=dev)
+        ws = plan.workspace(_lib.size_query("gasfm_gat_bwd_ws_bytes", XL.shape[0], plan.n_seg, plan.max_chunks,
+                                            heads, head_dim), dev)
+        with torch.cuda.device(dev):
+            _lib.call("gasfm_gat_edge_bwd", _lib.ptr(XL), XL.stride(0) if XL.shape[0] > 1 else hc, _lib.ptr(XR),
+                      0 if ctx.bcast else hc, _lib.ptr(att_flat), _lib.ptr(out_nobias), _lib.ptr(seg_max),
+                      _lib.ptr(seg_sum), _lib.ptr(d_out), *plan.abi_args(), heads, head_dim, LEAKY_SLOPE,
+                      _lib.ptr(dXL), hc, _lib.ptr(dXR), _lib.ptr(datt), _lib.ptr(ws), _lib.stream_ptr())
+        if ctx.bcast:
+            dXR = dXR.sum(dim=0, keepdim=True)
+        d_bias = None if bias is None else d_out.sum(dim=0)
+        return dXL, dXR, datt.view(ctx.att_shape), d_bias, None, None
+
+
+def gat_edge_attention(XL, XR, att, bias, plan: SegmentPlan, heads: int):
+    """out[T,HC] = GATv2 softmax-aggregate of XL rows over ``plan``'s segments (+ bias).
+
+    XL [E,HC] projected sources (rows may be a strided slice), XR [T,HC] projected targets, or
+    [1,HC] to broadcast one query row to every target (stateless first block)."""
+    return _GatEdge.apply(XL, XR, att, bias, plan, heads)
+
+
+def gat_edge_partial(XL, XR, att, plan: SegmentPlan, heads: int):
+    """Un-normalised per-shard result (no autograd): (sum_e exp(s-max)*XL[e], max, sum).
+    Used by the track-sharded multi-GPU path, which merges these across ranks."""
+    _require_cuda(XL, XR, att)
+    XL, ldxl = _rows(XL)
+    hc = XL.shape[1]
+    head_dim = hc // heads
+    T = plan.n_seg
+    bcast = XR.shape[0] == 1 and T != 1
+    XR = XR.contiguous()
+    att_flat = att.reshape(-1).contiguous()
+    dev = XL.device
+    out = torch.empty((T, hc), dtype=torch.float32, device=dev)
+    seg_max = torch.empty((T, heads), dtype=torch.float32, device=dev)
+    seg_sum = torch.empty((T, heads), dtype=torch.float32, device=dev)
+    ws = None
+    if plan.chunk > 0:
+        ws = plan.workspace(_lib.size_query("gasfm_gat_ws_bytes", plan.max_chunks, heads, head_dim), dev)
+    with torch.cuda.device(dev):
+        _lib.call("gasfm_gat_edge_fwd", _lib.ptr(XL), ldxl, _lib.ptr(XR), 0 if bcast else hc, _lib.ptr(att_flat), None,
+                  *plan.abi_args(), heads, head_dim, LEAKY_SLOPE, 0,
+                  _lib.ptr(out), _lib.ptr(seg_max), _lib.ptr(seg_sum), _lib.ptr(ws), _lib.stream_ptr())
+    return out, seg_max, seg_sum
+
+
+def gat_edge_backward_raw(XL, XR, att, out_nobias, seg_max, seg_sum, d_out, plan, heads):
+    """Backward kernel with explicitly supplied (global) softmax statistics; returns
+    (dXL, dXR, datt).  The multi-GPU path calls this with the merged statistics."""
+    XL, ldxl = _rows(XL)
+    hc = XL.shape[1]
+    head_dim = hc // heads
+    dev = XL.device
+    bcast = XR.shape[0] == 1 and plan.n_seg != 1
+    covers_all = plan.perm is None or plan.n_edges == XL.shape[0]
+    dXL = (torch.empty if covers_all else torch.zeros)((XL.shape[0], hc), dtype=torch.float32, device=dev)
+    dXR = torch.empty((plan.n_seg, hc), dtype=torch.float32, device=dev)
+    datt = torch.empty(hc, dtype=torch.float32, device=dev)
+    ws = plan.workspace(_lib.size_query("gasfm_gat_bwd_ws_bytes", XL.shape[0], plan.n_seg, plan.max_chunks,
+                                        heads, head_dim), dev)
+    with torch.cuda.device(dev):
+        _lib.call("gasfm_gat_edge_bwd", _lib.ptr(XL), ldxl, _lib.ptr(XR.contiguous()), 0 if bcast else hc,
+                  _lib.ptr(att.reshape(-1).contiguous()), _lib.ptr(out_nobias.contiguous()),
+                  _lib.ptr(seg_max.contiguous()), _lib.ptr(seg_sum.contiguous()), _lib.ptr(d_out.contiguous()),
+                  *plan.abi_args(), heads, head_dim, LEAKY_SLOPE,
+                  _lib.ptr(dXL), hc, _lib.ptr(dXR), _lib.ptr(datt), _lib.ptr(ws), _lib.stream_ptr())
+    if bcast:
+        dXR = dXR.sum(dim=0, keepdim=True)
+    return dXL, dXR, datt
+
+
+# ---------------------------------------------------------------------------------------------
+# LayerNorm + ReLU on observation features
+# ---------------------------------------------------------------------------------------------
+class _LnRelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        _require_cuda(x, gamma, beta)
+        x = x.contiguous()
+        E, w = x.shape
+        dev = x.device
+        y = torch.empty_like(x)
+        mean = rstd = None
+        if gamma is not None:
+            gamma, beta = gamma.contiguous(), beta.contiguous()
+            mean = torch.empty(E, dtype=torch.float32, device=dev)
+            rstd = torch.empty(E, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("gasfm_ln_relu_fwd", _lib.ptr(x), E, w, _lib.ptr(gamma), _lib.ptr(beta), float(eps),
+                      _lib.ptr(y), _lib.ptr(mean), _lib.ptr(rstd), _lib.stream_ptr())
+        ctx.save_for_backward(x, y, mean, rstd, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, rstd, gamma = ctx.saved_tensors
+        E, w = x.shape
+        dev = x.device
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dgamma = dbeta = ws = None
+        if gamma is not None:
+            dgamma = torch.empty(w, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(w, dtype=torch.float32, device=dev)
+            ws = torch.empty(max(1, _lib.size_query("gasfm_ln_relu_bwd_ws_bytes", E, w) // 4),
+                             dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("gasfm_ln_relu_bwd", _lib.ptr(dy), _lib.ptr(x), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(rstd),
+                      _lib.ptr(gamma), E, w, _lib.ptr(dx), _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(ws),
+                      _lib.stream_ptr())
+        return dx, dgamma, dbeta, None
+
+
+def ln_relu(x, gamma=None, beta=None, eps=1e-5):
+    """relu(layer_norm(x)) over the last dim of an [E,d] matrix; gamma=None -> relu(x)."""
+    return _LnRelu.apply(x, gamma, beta, eps)
+
+
+# ---------------------------------------------------------------------------------------------
+# row / column pooling
+# ---------------------------------------------------------------------------------------------
+def seg_sum_raw(X, plan: SegmentPlan, scale=1.0, mean=False):
+    _require_cuda(X)
+    X, ldx = _rows(X)
+    w = X.shape[1]
+    dev = X.device
+    out = torch.empty((plan.n_seg, w), dtype=torch.float32, device=dev)
+    ws = None
+    if plan.chunk > 0:
+        ws = plan.workspace(_lib.size_query("gasfm_seg_sum_ws_bytes", plan.max_chunks, w), dev)
+    with torch.cuda.device(dev):
+        _lib.call("gasfm_seg_sum", _lib.ptr(X), ldx, w, *plan.abi_args(), float(scale), int(mean),
+                  _lib.ptr(out), _lib.ptr(ws), _lib.stream_ptr())
+    return out
+
+
+class _SegPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, plan, seg_of_edge, scale, mean):
+        ctx.plan, ctx.seg_of_edge, ctx.scale, ctx.mean, ctx.n_rows = plan, seg_of_edge, scale, mean, X.shape[0]
+        return seg_sum_raw(X, plan, scale, mean)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        d_out = d_out.contiguous()
+        w = d_out.shape[1]
+        dev = d_out.device
+        dX = torch.empty((ctx.n_rows, w), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("gasfm_seg_bcast", _lib.ptr(d_out), w, _lib.ptr(ctx.seg_of_edge), _lib.ptr(ctx.plan.seg_ptr),
+                      ctx.n_rows, float(ctx.scale), int(ctx.mean), _lib.ptr(dX), _lib.stream_ptr())
+        return dX, None, None, None, None
+
+
+def seg_pool(X, plan, seg_of_edge, scale=1.0, mean=False):
+    """Differentiable segment sum / mean of the rows of X [E,w] -> [T,w]."""
+    return _SegPool.apply(X, plan, seg_of_edge, scale, mean)
+
+
+# ---------------------------------------------------------------------------------------------
+# per-observation update: out = pscale*P + scale*(x0 @ W0^T + S[col] + V[row] + g) + skip
+# ---------------------------------------------------------------------------------------------
+class _EdgeUpdate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, P, x0, W0, S, V, g, skip, index, pscale, scale):
+        _require_cuda(P, x0, W0, S, V, g, skip)
+        P, ldp = _rows(P)
+        E, w = P.shape
+        dev = P.device
+        d0 = 0
+        if x0 is not None:
+            x0, W0 = x0.contiguous(), W0.contiguous()
+            d0 = x0.shape[1]
+        if skip is not None:
+            skip, ldskip = _rows(skip)
+        else:
+            ldskip = w
+        S = None if S is None else S.contiguous()
+        V = None if V is None else V.contiguous()
+        g = None if g is None else g.contiguous()
+        out = torch.empty((E, w), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("gasfm_edge_update_fwd", _lib.ptr(P), ldp, _lib.ptr(x0), d0, _lib.ptr(W0), _lib.ptr(S), _lib.ptr(V),
+                      _lib.ptr(g), _lib.ptr(skip), ldskip, _lib.ptr(index.row_idx), _lib.ptr(index.col_idx), E, w,
+                      float(pscale), float(scale), _lib.ptr(out), _lib.stream_ptr())
+        ctx.save_for_backward(x0, W0)
+        ctx.index, ctx.pscale, ctx.scale = index, pscale, scale
+        ctx.has = (S is not None, V is not None, g is not None, skip is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x0, W0 = ctx.saved_tensors
+        index, scale = ctx.index, ctx.scale
+        has_S, has_V, has_g, has_skip = ctx.has
+        d_out = d_out.contiguous()
+        dP = d_out if ctx.pscale == 1.0 else d_out * ctx.pscale
+        dS = seg_sum_raw(d_out, index.by_track, scale) if (has_S and ctx.needs_input_grad[3]) else None
+        dV = None
+        if (has_V and ctx.needs_input_grad[4]) or (has_g and ctx.needs_input_grad[5]):
+            dV = seg_sum_raw(d_out, index.by_view, scale)
+        dg = dV.sum(dim=0, keepdim=True) if (has_g and ctx.needs_input_grad[5]) else None
+        dx0 = dW0 = None
+        if x0 is not None:
+            if ctx.needs_input_grad[1]:
+                dx0 = torch.mm(d_out, W0).mul_(scale)
+            if ctx.needs_input_grad[2]:
+                dW0 = torch.mm(d_out.t(), x0).mul_(scale)
+        return (dP, dx0, dW0, dS, dV if has_V else None, dg, d_out if has_skip else None, None, None, None)
+
+
+def edge_update(P, x0, W0, S, V, g, skip, index, pscale=1.0, scale=0.25):
+    return _EdgeUpdate.apply(P, x0, W0, S, V, g, skip, index, pscale, scale)

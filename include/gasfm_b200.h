@@ -1,0 +1,183 @@
+/*
+ * gasfm_b200 -- C ABI of the B200-native GASFM graph-attention path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The Python
+ * host layer (gasfm_b200/_lib.py) binds exactly these symbols with ctypes; any other host
+ * (C++, the reference's own Python through ctypes/cffi) can bind them the same way, see
+ * INTEGRATION.md.  Each entry point names the reference interface it replaces; paths are
+ * relative to the reference's ``code/`` directory.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in ``_host``;
+ *   - ``stream`` is a ``cudaStream_t`` passed as ``void*`` (NULL = legacy default stream);
+ *   - matrices are row-major fp32; ``ld*`` arguments are row strides in ELEMENTS;
+ *   - index arrays produced here are int32; the reference-facing ``indices[2,E]`` stays int64;
+ *   - every function returns 0 on success or a non-zero code; ``gasfm_last_error()`` then
+ *     returns a human-readable message (thread-local).  Nothing here falls back to the CPU.
+ *
+ * Segment plans
+ *   A "plan" describes one aggregation graph (AxialAggregationGraphWrapper,
+ *   utils/dataset_utils.py:464-597) as segments over the E observation rows:
+ *     seg_ptr[T+1]   exclusive prefix of segment lengths (CSR over views, CSC over tracks)
+ *     perm[E]|NULL   edge id of the k-th entry in segment order (NULL = storage order,
+ *                    i.e. the row-major CSR the reference's indices already have)
+ *   Long segments are cut into chunks of ``chunk`` edges so that the work fills 148 SMs:
+ *     chunk_ptr[T+1] exclusive prefix of ceil(len/chunk)
+ *     chunk_seg[max_chunks] segment id of every chunk; max_chunks >= E/chunk + T
+ *   chunk == 0 selects the short-segment schedule (one lane group per segment, no chunks).
+ */
+#ifndef GASFM_B200_H
+#define GASFM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GASFM_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GASFM_API __attribute__((visibility("default")))
+#else
+#define GASFM_API
+#endif
+
+GASFM_API int gasfm_abi_version(void);
+GASFM_API const char* gasfm_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Observation index build  (bit-exact integer work)
+ * ------------------------------------------------------------------------------------- */
+
+/* Replaces get_M_valid_points + the counting half of M2sparse
+ * (utils/dataset_utils.py:86-113, 116-127).
+ * M[2m,n] dense measurements -> valid[m*n] (0/1), cam_per_pts[n], pts_per_cam[m] (int64, the
+ * reference's dtype) and n_obs[1] (int64) = number of valid observations E. */
+GASFM_API int gasfm_m2sparse_count(const float* M, int m, int n, int min_views_per_point,
+                         uint8_t* valid, int64_t* cam_per_pts, int64_t* pts_per_cam,
+                         int64_t* n_obs, void* stream);
+
+/* Replaces the index / value half of M2sparse + geo_utils.normalize_M
+ * (utils/dataset_utils.py:128-156, utils/geo_utils.py:689-703).
+ * Writes indices[2,E] (int64, row-major order == np.nonzero order) and values[E,2] =
+ * (Ns[i] @ [x;y;1])[:2] (Ns may be NULL: raw coordinates).  ``scan_ws`` needs
+ * gasfm_m2sparse_ws_bytes(m,n) bytes. */
+GASFM_API size_t gasfm_m2sparse_ws_bytes(int m, int n);
+GASFM_API int gasfm_m2sparse_fill(const float* M, const float* Ns, const uint8_t* valid, int m, int n,
+                        int64_t n_obs, int64_t* indices, float* values, void* scan_ws,
+                        void* stream);
+
+/* CSR / CSC of the observation graph from the reference's indices[2,E] (int64, row-major
+ * sorted).  Replaces the per-call ``sparse_coo_tensor(...).coalesce()`` sorts
+ * (utils/sparse_utils.py:436-449; models/layers.py:545-549,561-565,823,922) and the edge lists
+ * of AxialAggregationGraphWrapper.create_sparse_axial_aggregation_edges
+ * (utils/dataset_utils.py:511-537): built once per scene, never re-sorted.
+ *   row_idx[E], col_idx[E]  int32 copies of indices
+ *   row_ptr[m+1]            CSR over views (storage order is already CSR order)
+ *   col_ptr[n+1], csc_perm[E]  CSC over tracks; csc_perm is the STABLE sort by column
+ * Returns an error if indices are out of range or not sorted row-major. */
+GASFM_API int gasfm_csr_build(const int64_t* indices, int64_t n_obs, int m, int n,
+                    int32_t* row_idx, int32_t* col_idx, int32_t* row_ptr,
+                    int32_t* col_ptr, int32_t* csc_perm, int32_t* status, void* stream);
+
+/* Chunk tables of a plan (see header comment).  chunk_ptr[T+1], chunk_seg[max_chunks]. */
+GASFM_API int gasfm_plan_chunks(const int32_t* seg_ptr, int n_seg, int chunk, int32_t* chunk_ptr,
+                      int32_t* chunk_seg, int max_chunks, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused GATv2 edge attention  (replaces torch_geometric.nn.GATv2Conv's message passing as
+ * called at models/layers.py:329-335, 426-432, 550-556, 566-572, minus lin_l / lin_r)
+ *
+ *   z = XL[e] + XR[t(e)];  s[e,h] = sum_c att[h,c] * leaky_relu(z, slope)
+ *   alpha = softmax over the segment of s;  out[t] = concat_h sum_e alpha * XL[e] + bias
+ *   empty segment -> out[t] = bias, seg_max = -inf, seg_sum = 0
+ *
+ * XL[E,H*C] (row stride ldxl), XR[T,H*C] (row stride ldxr; ldxr == 0 broadcasts one row,
+ * used for the stateless first block where the query is lin_r.bias), att[H*C], bias[H*C]|NULL.
+ * out[T,H*C], seg_max[T,H], seg_sum[T,H] (softmax statistics, needed by backward and by the
+ * multi-GPU merge).  ``ws`` needs gasfm_gat_ws_bytes(max_chunks, H, C) bytes when chunk > 0.
+ * If ``normalize`` == 0 the un-normalised partial sum (sum_e exp(s-max) * XL[e]) is written
+ * to ``out`` without bias: that is the per-GPU partial for a track-sharded graph.
+ * ------------------------------------------------------------------------------------- */
+GASFM_API size_t gasfm_gat_ws_bytes(int max_chunks, int heads, int head_dim);
+
+GASFM_API int gasfm_gat_edge_fwd(const float* XL, int64_t ldxl, const float* XR, int64_t ldxr,
+                       const float* att, const float* bias,
+                       const int32_t* seg_ptr, const int32_t* perm, int n_seg,
+                       int chunk, const int32_t* chunk_ptr, const int32_t* chunk_seg, int max_chunks,
+                       int heads, int head_dim, float slope, int normalize,
+                       float* out, float* seg_max, float* seg_sum, void* ws, void* stream);
+
+/* Backward.  Given dOut[T,H*C] and the forward's out / statistics:
+ *   dXL[E,H*C] (row stride lddxl), dXR[T,H*C], datt[H*C] (accumulated over all edges).
+ * ``out_nobias`` = out - bias (the aggregated values), row stride H*C.
+ * ``datt_ws`` needs gasfm_gat_bwd_ws_bytes(...) bytes. */
+GASFM_API size_t gasfm_gat_bwd_ws_bytes(int64_t n_obs, int n_seg, int max_chunks, int heads, int head_dim);
+
+GASFM_API int gasfm_gat_edge_bwd(const float* XL, int64_t ldxl, const float* XR, int64_t ldxr,
+                       const float* att, const float* out_nobias, const float* seg_max,
+                       const float* seg_sum, const float* dOut,
+                       const int32_t* seg_ptr, const int32_t* perm, int n_seg,
+                       int chunk, const int32_t* chunk_ptr, const int32_t* chunk_seg, int max_chunks,
+                       int heads, int head_dim, float slope,
+                       float* dXL, int64_t lddxl, float* dXR, float* datt, void* ws, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Row / column pooling  (SparseMat.sum / .mean, utils/sparse_utils.py:406-419; sparse_mean,
+ * utils/sparse_utils.py:91-131; and the segment sums of the backward passes)
+ *   out[t] = scale * sum_{e in segment t} X[e]   (mean_mode: divide by the segment length;
+ *   empty segments give 0)
+ * ------------------------------------------------------------------------------------- */
+GASFM_API int gasfm_seg_sum(const float* X, int64_t ldx, int width,
+                  const int32_t* seg_ptr, const int32_t* perm, int n_seg,
+                  int chunk, const int32_t* chunk_ptr, const int32_t* chunk_seg, int max_chunks,
+                  float scale, int mean_mode, float* out, void* ws, void* stream);
+GASFM_API size_t gasfm_seg_sum_ws_bytes(int max_chunks, int width);
+
+/* Backward of pooling: dX[e] = scale * dOut[seg(e)] (/ len if mean_mode). seg_of_edge[E]. */
+GASFM_API int gasfm_seg_bcast(const float* dOut, int width, const int32_t* seg_of_edge,
+                    const int32_t* seg_ptr, int64_t n_obs, float scale, int mean_mode,
+                    float* dX, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Per-observation feature ops
+ * ------------------------------------------------------------------------------------- */
+
+/* y = relu(layer_norm(x) * gamma + beta)  (normalize_projection_features +
+ * relu_on_projection_features, models/layers.py:232-234, 972-984).  gamma == NULL skips the
+ * normalisation (use_norm_proj_update = false): y = relu(x).  mean/rstd[E] saved for backward. */
+GASFM_API int gasfm_ln_relu_fwd(const float* x, int64_t n_rows, int width, const float* gamma,
+                      const float* beta, float eps, float* y, float* mean, float* rstd,
+                      void* stream);
+GASFM_API size_t gasfm_ln_relu_bwd_ws_bytes(int64_t n_rows, int width);
+GASFM_API int gasfm_ln_relu_bwd(const float* dy, const float* x, const float* y, const float* mean,
+                      const float* rstd, const float* gamma, int64_t n_rows, int width,
+                      float* dx, float* dgamma, float* dbeta, void* ws, void* stream);
+
+/* out[e] = pscale * P[e] + scale * (sum_k x0[e,k] * W0[:,k] + S[col[e]] + V[row[e]] + g) + skip[e]
+ * (GraphAttnSfMProjectionFeatureUpdate.forward + the residual of GraphAttnSfMLayer.forward,
+ * models/layers.py:941-945, 254-261; also SetOfSetProjectionFeatureUpdate, :141-143).
+ * x0 / W0 (width x d0, row-major, d0 <= 4), g and skip may be NULL.  ``pscale`` lets the caller fold
+ * the 1/4 into lin_proj's weights so that dP == dOut in backward (no extra pass over [E,width]). */
+GASFM_API int gasfm_edge_update_fwd(const float* P, int64_t ldp, const float* x0, int d0, const float* W0,
+                          const float* S, const float* V, const float* g, const float* skip,
+                          int64_t ldskip, const int32_t* row_idx, const int32_t* col_idx,
+                          int64_t n_obs, int width, float pscale, float scale, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Host-buffer convenience entry points (inputs and outputs in HOST memory; allocation and the
+ * host<->device copies happen inside the call).  These are what a non-torch host binds.
+ * ------------------------------------------------------------------------------------- */
+GASFM_API int gasfm_csr_build_host(const int64_t* indices_host, int64_t n_obs, int m, int n,
+                         int32_t* row_ptr_host, int32_t* col_ptr_host, int32_t* csc_perm_host);
+
+GASFM_API int gasfm_gat_edge_fwd_host(const float* XL_host, const float* XR_host, const float* att_host,
+                            const float* bias_host, const int64_t* target_host,
+                            int64_t n_obs, int n_seg, int heads, int head_dim, float slope,
+                            float* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GASFM_B200_H */

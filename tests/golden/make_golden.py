@@ -156,7 +156,7 @@ def main():
             fix[f"out.{tag}.pts3D"] = out["pts3D"]
             fix[f"loss.{tag}"] = loss
             for k, v in mdl.named_parameters():
-                fix[f"grad.{tag}.{k}"] = v.grad
+                fix[f"grad.{tag}.{k}"] = v.grad.detach().clone()   # clone: module.to() re-types .grad in place
             # oracle agreement (same dtype)
             params = {k: v.detach().clone().requires_grad_(True) for k, v in mdl.state_dict().items()}
             scene = gasfm_cpu.make_scene(M.to(dtype), Ns.to(dtype))

@@ -1,0 +1,343 @@
+"""Kernel-level parity on the B200: every C-ABI entry point against the CPU oracle on the same
+seeded inputs.  Integer / index outputs must be bit-exact; fp32 outputs must agree with the fp64
+oracle to the tolerance written next to each check."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from gasfm_b200 import _lib, ops
+from gasfm_b200.index import ObservationIndex, SegmentPlan, plan_from_targets, single_segment_chunk
+from gasfm_b200.scene import Scene
+from gasfm_b200.utils import dataset_utils, sparse_utils
+from oracle import gasfm_cpu, gat_edge_c
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+FP32_TOL = 2e-5      # max abs err / max(1, |ref|) for forward outputs (fp32 kernels vs fp64 oracle)
+GRAD_TOL = 1e-4      # same for gradients (longer accumulation chains)
+
+
+def rel_err(got, want):
+    got = got.detach().double().cpu().numpy() if torch.is_tensor(got) else np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    return float(np.abs(got - want).max() / max(1.0, np.abs(want).max())) if want.size else 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# index build
+# ---------------------------------------------------------------------------------------------
+def test_m2sparse_matches_reference_golden_bit_exact():
+    g = load_golden("index_build")
+    x = dataset_utils.M2sparse(torch.from_numpy(g["M"]).to(DEV), normalize=True, Ns=torch.from_numpy(g["Ns"]).to(DEV))
+    assert np.array_equal(x.indices.cpu().numpy(), g["indices"])
+    assert np.array_equal(x.cam_per_pts.cpu().numpy(), g["cam_per_pts"])
+    assert np.array_equal(x.pts_per_cam.cpu().numpy(), g["pts_per_cam"])
+    assert tuple(x.shape) == tuple(g["shape"])
+    np.testing.assert_allclose(x.values.cpu().numpy(), g["values"], rtol=2e-6, atol=1e-7)
+    valid = dataset_utils.get_M_valid_points(torch.from_numpy(g["M"]).to(DEV)).cpu().numpy()
+    assert np.array_equal(valid, gasfm_cpu.valid_observation_mask(g["M"]))
+    # host tensors are accepted too (moved to the GPU for the kernels, result returned on the host)
+    xh = dataset_utils.M2sparse(torch.from_numpy(g["M"]), normalize=False)
+    assert not xh.values.is_cuda and np.array_equal(xh.indices.numpy(), g["indices"])
+    graphs = dataset_utils.create_axial_aggregation_graphs(x)
+    for name, w in graphs.items():
+        assert np.array_equal(w.edge_index.cpu().numpy(), g[f"{name}.edge_index"]), name
+        assert np.array_equal(w.valid_indices.cpu().numpy(), g[f"{name}.valid_indices"]), name
+
+
+@pytest.mark.parametrize("m,n,E,seed", [(20, 2000, 12000, 0), (7, 40, 150, 1), (300, 50000, 500000, 2), (64, 100, 3800, 3)])
+def test_csr_csc_bit_exact(m, n, E, seed):
+    idx_np, _ = gasfm_cpu.synthetic_observations(m, n, E, seed)
+    idx = torch.from_numpy(idx_np).to(DEV)
+    oi = ObservationIndex(idx, m, n)
+    rows, cols = torch.from_numpy(idx_np[0]), torch.from_numpy(idx_np[1])
+    row_ptr = torch.zeros(m + 1, dtype=torch.int64); row_ptr[1:] = torch.bincount(rows, minlength=m).cumsum(0)
+    col_ptr = torch.zeros(n + 1, dtype=torch.int64); col_ptr[1:] = torch.bincount(cols, minlength=n).cumsum(0)
+    perm = torch.argsort(cols, stable=True)
+    assert torch.equal(oi.row_idx.cpu().long(), rows) and torch.equal(oi.col_idx.cpu().long(), cols)
+    assert torch.equal(oi.row_ptr.cpu().long(), row_ptr)
+    assert torch.equal(oi.col_ptr.cpu().long(), col_ptr)
+    assert torch.equal(oi.csc_perm.cpu().long(), perm)
+    # chunk tables of the view plan
+    p = oi.by_view
+    lens = (row_ptr[1:] - row_ptr[:-1])
+    nchunks = (lens + p.chunk - 1) // p.chunk
+    cp = torch.zeros(m + 1, dtype=torch.int64); cp[1:] = nchunks.cumsum(0)
+    assert torch.equal(p.chunk_ptr.cpu().long(), cp)
+    total = int(cp[-1])
+    assert total <= p.max_chunks
+    assert torch.equal(p.chunk_seg.cpu().long()[:total], torch.repeat_interleave(torch.arange(m), nchunks))
+
+
+def test_csr_build_rejects_bad_indices():
+    bad = torch.tensor([[0, 0, 1], [1, 1, 0]], dtype=torch.int64, device=DEV)     # duplicate entry
+    with pytest.raises(ValueError, match="sorted"):
+        ObservationIndex(bad, 2, 2)
+    oob = torch.tensor([[0, 5], [0, 1]], dtype=torch.int64, device=DEV)
+    with pytest.raises(ValueError, match="range"):
+        ObservationIndex(oob, 2, 2)
+
+
+def test_csr_build_host_entry_point():
+    idx_np, _ = gasfm_cpu.synthetic_observations(9, 50, 200, 5)
+    E = idx_np.shape[1]
+    idx = np.ascontiguousarray(idx_np, np.int64)
+    rp, cp, perm = np.zeros(10, np.int32), np.zeros(51, np.int32), np.zeros(E, np.int32)
+    lib = _lib.load()
+    rc = lib.gasfm_csr_build_host(idx.ctypes.data, E, 9, 50, rp.ctypes.data, cp.ctypes.data, perm.ctypes.data)
+    assert rc == 0, _lib.last_error()
+    assert np.array_equal(perm, np.argsort(idx[1], kind="stable"))
+    assert np.array_equal(np.diff(rp), np.bincount(idx[0], minlength=9))
+    assert np.array_equal(np.diff(cp), np.bincount(idx[1], minlength=50))
+
+
+# ---------------------------------------------------------------------------------------------
+# fused GATv2 edge attention
+# ---------------------------------------------------------------------------------------------
+def _gat_case(E, T, H, C, seed, empty_tail=0, bcast=False):
+    rng = np.random.default_rng(seed)
+    target = np.sort(rng.integers(0, max(1, T - empty_tail), size=E))
+    XL = rng.standard_normal((E, H * C)).astype(np.float32)
+    XR = rng.standard_normal((1 if bcast else T, H * C)).astype(np.float32)
+    att = (rng.standard_normal(H * C) * 0.5).astype(np.float32)
+    bias = rng.standard_normal(H * C).astype(np.float32)
+    dOut = rng.standard_normal((T, H * C)).astype(np.float32)
+    return target, XL, XR, att, bias, dOut
+
+
+def _run_gat(plan, XL, XR, att, bias, dOut, H, C):
+    t = lambda a: torch.from_numpy(a).to(DEV).requires_grad_(True)  # noqa: E731
+    xl, xr, a, b = t(XL), t(XR), t(att.reshape(1, H, C)), t(bias)
+    out = ops.gat_edge_attention(xl, xr, a, b, plan, H)
+    out.backward(torch.from_numpy(dOut).to(DEV))
+    torch.cuda.synchronize()
+    return out, xl.grad, xr.grad, a.grad.reshape(-1), b.grad
+
+
+def _check_gat(target, XL, XR, att, bias, dOut, T, H, C, plan, perm_rows=None):
+    """perm_rows: edge e of the oracle corresponds to row perm_rows[e] of XL on the device."""
+    XLo = XL if perm_rows is None else XL[perm_rows]
+    ref_out, _, _ = gat_edge_c.gat_edge_fwd(XLo, XR, att, bias, target, T, H, C)
+    dXL, dXR, datt, dbias = gat_edge_c.gat_edge_bwd(XLo, XR, att, target, dOut, T, H, C)
+    out, gxl, gxr, gatt, gb = _run_gat(plan, XL, XR, att, bias, dOut, H, C)
+    assert rel_err(out, ref_out) < FP32_TOL
+    g = gxl.cpu().numpy()
+    if perm_rows is not None:
+        full = np.zeros_like(g, dtype=np.float64); full[perm_rows] = dXL; dXL = full
+    assert rel_err(g, dXL) < GRAD_TOL
+    assert rel_err(gxr, dXR) < GRAD_TOL
+    assert rel_err(gatt, datt) < GRAD_TOL * 5
+    assert rel_err(gb, dbias) < GRAD_TOL
+    return out
+
+
+HEAD_SHAPES = [(4, 8), (4, 64), (4, 1), (4, 2), (4, 4), (4, 16), (4, 32), (4, 128), (4, 256), (2, 6), (1, 5), (3, 8), (8, 4)]
+
+
+@pytest.mark.parametrize("H,C", HEAD_SHAPES)
+def test_gat_short_segments_through_csc_perm(H, C):
+    """tracks: many short segments, rows gathered through a permutation, some targets empty"""
+    m, n, E0 = 16, 300, 1500
+    idx_np, _ = gasfm_cpu.synthetic_observations(m, n, E0, seed=H * 7 + C)
+    E = idx_np.shape[1]
+    oi = ObservationIndex(torch.from_numpy(idx_np).to(DEV), m, n + 5)      # 5 trailing tracks without observations
+    _, XL, XR, att, bias, dOut = _gat_case(E, n + 5, H, C, seed=C)
+    out = _check_gat(idx_np[1], XL, XR, att, bias, dOut, n + 5, H, C, oi.by_track)
+    assert torch.equal(out[-5:].cpu(), torch.from_numpy(bias).expand(5, -1))   # empty segment -> exactly bias
+
+
+@pytest.mark.parametrize("H,C", HEAD_SHAPES)
+def test_gat_long_segments_chunked(H, C):
+    """views: few long contiguous segments -> chunked schedule + log-sum-exp merge"""
+    m, n, E0 = 9, 400, 2600
+    idx_np, _ = gasfm_cpu.synthetic_observations(m, n, E0, seed=H + C)
+    E = idx_np.shape[1]
+    oi = ObservationIndex(torch.from_numpy(idx_np).to(DEV), m + 2, n)      # 2 trailing views without observations
+    assert oi.by_view.chunk > 0
+    _, XL, XR, att, bias, dOut = _gat_case(E, m + 2, H, C, seed=C + 1)
+    _check_gat(idx_np[0], XL, XR, att, bias, dOut, m + 2, H, C, oi.by_view)
+
+
+@pytest.mark.parametrize("H,C,E,chunk", [(4, 16, 5000, None), (4, 256, 300, None), (4, 8, 70, 8), (4, 64, 1, 8), (2, 6, 100, 8)])
+def test_gat_single_target_global_graph(H, C, E, chunk):
+    """view2global / scenepoint2global: ONE segment holding every edge; with a subset permutation"""
+    rng = np.random.default_rng(E)
+    n_rows = E + 7
+    keep = np.sort(rng.choice(n_rows, size=E, replace=False))
+    seg_ptr = torch.tensor([0, E], dtype=torch.int32, device=DEV)
+    plan = SegmentPlan(seg_ptr, torch.from_numpy(keep.astype(np.int32)).to(DEV), 1, E, chunk or single_segment_chunk(E), DEV)
+    _, XL, XR, att, bias, dOut = _gat_case(n_rows, 1, H, C, seed=3)
+    _check_gat(np.zeros(E, np.int64), XL, XR, att, bias, dOut, 1, H, C, plan, perm_rows=keep)
+
+
+def test_gat_stateless_broadcast_query_and_strided_rows():
+    """first block: query = lin_r.bias broadcast to every target; XL given as a strided slice"""
+    H, C, m, n = 4, 8, 12, 200
+    idx_np, _ = gasfm_cpu.synthetic_observations(m, n, 900, seed=9)
+    E = idx_np.shape[1]
+    oi = ObservationIndex(torch.from_numpy(idx_np).to(DEV), m, n)
+    for plan, tgt, T in ((oi.by_track, idx_np[1], n), (oi.by_view, idx_np[0], m)):
+        _, XL, XR, att, bias, dOut = _gat_case(E, T, H, C, seed=4, bcast=True)
+        _check_gat(tgt, XL, XR, att, bias, dOut, T, H, C, plan)
+        wide = torch.randn(E, 3 * H * C, device=DEV)
+        sl = wide[:, H * C: 2 * H * C]
+        o1 = ops.gat_edge_attention(sl, torch.from_numpy(XR).to(DEV), torch.from_numpy(att).to(DEV).view(1, H, C), None, plan, H)
+        o2 = ops.gat_edge_attention(sl.contiguous(), torch.from_numpy(XR).to(DEV), torch.from_numpy(att).to(DEV).view(1, H, C), None, plan, H)
+        assert torch.equal(o1, o2)
+
+
+def test_gat_large_scores_are_stable():
+    """softmax must survive scores of +-80 (max subtraction), like the reference's"""
+    H, C, E, T = 4, 8, 4000, 3
+    target, XL, XR, att, bias, dOut = _gat_case(E, T, H, C, seed=11)
+    XL *= 30.0
+    plan = plan_from_targets(torch.from_numpy(target).to(DEV), T)
+    out = _check_gat(target, XL, XR, att, bias, dOut, T, H, C, plan)
+    assert torch.isfinite(out).all()
+
+
+def test_gat_partial_statistics_merge_like_flash_attention():
+    """normalize=0 partials of two edge shards merge to the full result (the multi-GPU combine)"""
+    H, C, m, n = 4, 16, 10, 240
+    idx_np, _ = gasfm_cpu.synthetic_observations(m, n, 1500, seed=21)
+    E = idx_np.shape[1]
+    _, XL, XR, att, bias, _ = _gat_case(E, m, H, C, seed=5)
+    full, _, _ = gat_edge_c.gat_edge_fwd(XL, XR, att, None, idx_np[0], m, H, C)
+    half = idx_np[1] < n // 2
+    parts = []
+    for sel in (half, ~half):
+        sub = idx_np[:, sel]
+        oi = ObservationIndex(torch.from_numpy(np.ascontiguousarray(sub)).to(DEV), m, n)
+        o, mx, sm = ops.gat_edge_partial(torch.from_numpy(XL[sel]).to(DEV), torch.from_numpy(XR).to(DEV),
+                                         torch.from_numpy(att).to(DEV), oi.by_view, H)
+        parts.append((o.view(m, H, C), mx, sm))
+    M = torch.maximum(parts[0][1], parts[1][1])
+    num = sum(o * torch.exp(mx - M).unsqueeze(-1) for o, mx, _ in parts)
+    den = sum(sm * torch.exp(mx - M) for _, mx, sm in parts)
+    merged = (num / den.unsqueeze(-1)).reshape(m, H * C)
+    assert rel_err(merged, full) < FP32_TOL
+
+
+def test_gat_host_buffer_entry_point():
+    H, C, E, T = 4, 8, 500, 40
+    target, XL, XR, att, bias, _ = _gat_case(E, T, H, C, seed=2)
+    rng = np.random.default_rng(0)
+    shuffle = rng.permutation(E)                       # host API takes edges in any order
+    target, XL = target[shuffle], np.ascontiguousarray(XL[shuffle])
+    out = np.zeros((T, H * C), np.float32)
+    lib = _lib.load()
+    tgt = np.ascontiguousarray(target, np.int64)
+    rc = lib.gasfm_gat_edge_fwd_host(XL.ctypes.data, XR.ctypes.data, att.ctypes.data, bias.ctypes.data, tgt.ctypes.data,
+                                     E, T, H, C, ctypes.c_float(0.2), out.ctypes.data)
+    assert rc == 0, _lib.last_error()
+    ref, _, _ = gat_edge_c.gat_edge_fwd(XL, XR, att, bias, target, T, H, C)
+    assert rel_err(out, ref) < FP32_TOL
+
+
+def test_pyg_style_forward_on_arbitrary_graph():
+    from gasfm_b200.models.gatv2 import GATv2Conv
+    from oracle.gatv2conv import GATv2Conv as RefConv
+    torch.manual_seed(0)
+    ours, ref = GATv2Conv(12, 8, heads=4, add_self_loops=False).to(DEV), RefConv(12, 8, heads=4, add_self_loops=False)
+    ref.load_state_dict({k: v.cpu() for k, v in ours.state_dict().items()})
+    x = torch.randn(50, 12)
+    ei = torch.stack((torch.randint(0, 50, (300,)), torch.randint(0, 50, (300,))))
+    want = ref(x.double() if False else x, ei)
+    got = ours(x.to(DEV), ei.to(DEV))
+    assert rel_err(got, want.detach().numpy()) < 5e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# LayerNorm+ReLU, pooling, observation update
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w", [2, 32, 256, 12, 34, 1024])
+@pytest.mark.parametrize("affine", [True, False])
+def test_ln_relu_forward_backward(w, affine):
+    torch.manual_seed(w)
+    E = 777
+    x = torch.randn(E, w, dtype=torch.float64) * 2 + 0.3
+    gamma = (torch.randn(w, dtype=torch.float64) * 0.5 + 1).requires_grad_(True)
+    beta = (torch.randn(w, dtype=torch.float64) * 0.2).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ref = torch.relu(torch.nn.functional.layer_norm(xr, (w,), gamma, beta, 1e-5)) if affine else torch.relu(xr)
+    dy = torch.randn(E, w, dtype=torch.float64)
+    ref.backward(dy)
+    xg = x.float().to(DEV).requires_grad_(True)
+    gg = gamma.detach().float().to(DEV).requires_grad_(True)
+    bg = beta.detach().float().to(DEV).requires_grad_(True)
+    y = ops.ln_relu(xg, gg, bg, 1e-5) if affine else ops.ln_relu(xg)
+    y.backward(dy.float().to(DEV))
+    assert rel_err(y, ref.detach().numpy()) < FP32_TOL
+    assert rel_err(xg.grad, xr.grad.numpy()) < GRAD_TOL
+    if affine:
+        assert rel_err(gg.grad, gamma.grad.numpy()) < GRAD_TOL
+        assert rel_err(bg.grad, beta.grad.numpy()) < GRAD_TOL
+
+
+@pytest.mark.parametrize("w", [6, 32, 256, 3, 100])
+def test_row_col_pooling_matches_reference_golden_and_oracle(w):
+    g = load_golden("pooling")
+    idx = torch.from_numpy(g["indices"])
+    m, n = int(g["shape"][0]), int(g["shape"][1])
+    if w == 6:
+        feat = torch.from_numpy(g["feat"])
+    else:
+        feat = torch.randn(idx.shape[1], w)
+    sm = sparse_utils.SparseMat(feat.to(DEV).requires_grad_(True), idx.to(DEV),
+                                torch.from_numpy(g["cam_per_pts"]).to(DEV), torch.from_numpy(g["pts_per_cam"]).to(DEV), (m, n, w))
+    s0, s1 = sm.sum(0), sm.sum(1)
+    assert rel_err(s0, gasfm_cpu.sparse_sum(feat.double(), idx, (m, n, w), 0).numpy()) < FP32_TOL
+    assert rel_err(s1, gasfm_cpu.sparse_sum(feat.double(), idx, (m, n, w), 1).numpy()) < FP32_TOL
+    if w == 6:
+        np.testing.assert_allclose(s0.detach().cpu().numpy(), g["sum0"], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(s1.detach().cpu().numpy(), g["sum1"], rtol=1e-5, atol=1e-5)
+        m0 = sm.mean(0).detach().cpu().numpy()
+        assert np.array_equal(np.isnan(m0), np.isnan(g["mean0"]))      # 0/0 for empty tracks, as in the reference
+        np.testing.assert_allclose(np.nan_to_num(m0), np.nan_to_num(g["mean0"]), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(sm.mean(1).detach().cpu().numpy(), g["mean1"], rtol=1e-5, atol=1e-5)
+    # backward of pooling = broadcast
+    (s0 * 2.0).sum().backward()
+    assert rel_err(sm.values.grad, np.full((idx.shape[1], w), 2.0)) < 1e-6
+    mean_cols = sparse_utils.sparse_mean(sm, 0)
+    cnt = np.maximum(np.bincount(g["indices"][1], minlength=n), 1)[:, None]
+    assert rel_err(mean_cols, gasfm_cpu.sparse_sum(feat.double(), idx, (m, n, w), 0).numpy() / cnt) < FP32_TOL
+
+
+def test_set_of_set_layer_matches_reference_golden():
+    from gasfm_b200.models.layers import SetOfSetLayer
+    g = load_golden("pooling")
+    layer = SetOfSetLayer(6, 10)
+    layer.load_state_dict({k[len("param."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param.")})
+    idx = torch.from_numpy(g["indices"])
+    sm = sparse_utils.SparseMat(torch.from_numpy(g["feat"]).to(DEV), idx.to(DEV), torch.from_numpy(g["cam_per_pts"]).to(DEV),
+                                torch.from_numpy(g["pts_per_cam"]).to(DEV), (7, 50, 6))
+    out = layer.to(DEV)(sm)
+    np.testing.assert_allclose(out.values.detach().cpu().numpy(), g["sos_out"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("w,d0", [(32, 2), (256, 2), (20, 0), (16, 3), (6, 2)])
+def test_edge_update_forward_backward(w, d0):
+    m, n = 11, 150
+    idx_np, _ = gasfm_cpu.synthetic_observations(m, n, 700, seed=w)
+    E = idx_np.shape[1]
+    oi = ObservationIndex(torch.from_numpy(idx_np).to(DEV), m, n)
+    torch.manual_seed(1)
+    mk = lambda *s: torch.randn(*s, dtype=torch.float64).requires_grad_(True)  # noqa: E731
+    P, S, V, gl, skip = mk(E, w), mk(n, w), mk(m, w), mk(1, w), mk(E, w)
+    x0, W0 = (mk(E, d0), mk(w, d0)) if d0 else (None, None)
+    r, c = torch.from_numpy(idx_np[0]), torch.from_numpy(idx_np[1])
+    ref = P + 0.25 * (S[c] + V[r] + gl + (x0 @ W0.T if d0 else 0)) + skip
+    dout = torch.randn(E, w, dtype=torch.float64)
+    ref.backward(dout)
+    f = lambda t: None if t is None else t.detach().float().to(DEV).requires_grad_(True)  # noqa: E731
+    Pg, Sg, Vg, gg, sg, x0g, W0g = map(f, (P, S, V, gl, skip, x0, W0))
+    out = ops.edge_update(Pg, x0g, W0g, Sg, Vg, gg, sg, oi, 1.0, 0.25)
+    out.backward(dout.float().to(DEV))
+    assert rel_err(out, ref.detach().numpy()) < FP32_TOL
+    for got, want in ((Pg, P), (Sg, S), (Vg, V), (gg, gl), (sg, skip), (x0g, x0), (W0g, W0)):
+        if want is not None:
+            assert rel_err(got.grad, want.grad.numpy()) < GRAD_TOL
