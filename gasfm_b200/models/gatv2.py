@@ -51,7 +51,10 @@ class GATv2Conv(nn.Module):
     def project_targets(self, x_agg):
         """Query projection; ``None`` = zero query features -> one broadcast row ``lin_r.bias``."""
         if x_agg is None:
-            return self.lin_r.bias.unsqueeze(0)
+            # zero query features: x_r = 0 @ W^T + b.  The (exactly zero) weight term keeps lin_r.weight in
+            # the autograd graph so that it receives the same all-zero gradient it gets in the reference
+            # (whose training loop concatenates every parameter's .grad, code/train.py:137).
+            return (self.lin_r.bias + self.lin_r.weight.sum() * 0.0).unsqueeze(0)
         return F.linear(x_agg, self.lin_r.weight, self.lin_r.bias)
 
     def aggregate(self, x_elements, x_agg, plan, projected_sources=None):
