@@ -564,15 +564,24 @@ __global__ void __launch_bounds__(kBwdThreads) gat_bwd_kernel(GatBwdArgs p) {
 }
 
 // dXR of multi-chunk segments (sum of chunk partials) and zero rows for empty segments.
-template <int HC>
-__global__ void __launch_bounds__(128) gat_bwd_merge_kernel(GatBwdArgs p) {
+// grid = (segments, column tiles of 32); the 8 warps of a CTA split the segment's chunks.
+__global__ void __launch_bounds__(256) gat_bwd_merge_kernel(GatBwdArgs p, int HC) {
+  __shared__ float sm[8][33];
   const int t = blockIdx.x;
   const int c0 = __ldg(p.chunk_ptr + t), c1 = __ldg(p.chunk_ptr + t + 1);
   if (c1 - c0 == 1) return;
-  for (int j = threadIdx.x; j < HC; j += blockDim.x) {
-    float a = 0.f;
-    for (int k = c0; k < c1; ++k) a += p.ws_dxr[(int64_t)k * HC + j];
-    p.dXR[(int64_t)t * HC + j] = a;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int j = blockIdx.y * 32 + lane;
+  float a = 0.f;
+  if (j < HC)
+    for (int k = c0 + wid; k < c1; k += 8) a += p.ws_dxr[(int64_t)k * HC + j];
+  sm[wid][lane] = a;
+  __syncthreads();
+  if (wid == 0 && j < HC) {
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += sm[w][lane];
+    p.dXR[(int64_t)t * HC + j] = r;
   }
 }
 
@@ -806,7 +815,7 @@ static int launch_bwd(const GatBwdArgs& a, int* n_blocks_out, cudaStream_t st) {
   } else {
     blocks = bwd_grid_blocks(a.max_chunks, kBwdThreads / 32);
     gat_bwd_kernel<H, C, true><<<blocks, kBwdThreads, 0, st>>>(a);
-    if (a.n_seg > 0) gat_bwd_merge_kernel<H * C><<<a.n_seg, 128, 0, st>>>(a);
+    if (a.n_seg > 0) gat_bwd_merge_kernel<<<dim3(a.n_seg, (H * C + 31) / 32), 256, 0, st>>>(a, H * C);
   }
   *n_blocks_out = blocks;
   return check_launch("gat_edge_bwd");

@@ -136,16 +136,26 @@ __global__ void __launch_bounds__(256) seg_sum_kernel(SegSumArgs p) {
   }
 }
 
-__global__ void __launch_bounds__(128) seg_sum_merge_kernel(SegSumArgs p) {
+// grid = (segments, column tiles of 32); the 8 warps of a CTA split the segment's chunks.
+__global__ void __launch_bounds__(256) seg_sum_merge_kernel(SegSumArgs p) {
+  __shared__ float sm[8][33];
   const int t = blockIdx.x;
   const int c0 = __ldg(p.chunk_ptr + t), c1 = __ldg(p.chunk_ptr + t + 1);
   if (c1 - c0 == 1) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int j = blockIdx.y * 32 + lane;
   const int len = __ldg(p.seg_ptr + t + 1) - __ldg(p.seg_ptr + t);
   const float f = p.mean_mode ? (len > 0 ? p.scale / (float)len : 0.f) : p.scale;
-  for (int j = threadIdx.x; j < p.width; j += blockDim.x) {
-    float a = 0.f;
-    for (int k = c0; k < c1; ++k) a += p.ws[(int64_t)k * p.width + j];
-    p.out[(int64_t)t * p.width + j] = a * f;
+  float a = 0.f;
+  if (j < p.width)
+    for (int k = c0 + wid; k < c1; k += 8) a += p.ws[(int64_t)k * p.width + j];
+  sm[wid][lane] = a;
+  __syncthreads();
+  if (wid == 0 && j < p.width) {
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += sm[w][lane];
+    p.out[(int64_t)t * p.width + j] = r * f;
   }
 }
 
@@ -157,7 +167,7 @@ static void launch_seg_sum(const SegSumArgs& a, cudaStream_t st) {
     seg_sum_kernel<VEC, LPR, NV, false><<<ceil_div(warps, 8), 256, 0, st>>>(a);
   } else {
     seg_sum_kernel<VEC, LPR, NV, true><<<ceil_div(a.max_chunks, 8), 256, 0, st>>>(a);
-    seg_sum_merge_kernel<<<a.n_seg, 128, 0, st>>>(a);
+    seg_sum_merge_kernel<<<dim3(a.n_seg, (a.width + 31) / 32), 256, 0, st>>>(a);
   }
 }
 

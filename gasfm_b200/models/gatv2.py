@@ -60,6 +60,11 @@ class GATv2Conv(nn.Module):
     def aggregate(self, x_elements, x_agg, plan, projected_sources=None):
         """[T, H*C] attention-aggregate of the element rows over ``plan``'s segments."""
         xl = self.project_sources(x_elements) if projected_sources is None else projected_sources
+        shard = getattr(plan, "shard", None)
+        if shard is not None and shard.world > 1:
+            # track-sharded scene: this rank holds only part of every segment -> merge across ranks
+            from .. import dist as gdist
+            return gdist.sharded_gat(xl, self.project_targets(x_agg), self.att, self.bias, plan, self.heads, shard.group)
         return ops.gat_edge_attention(xl, self.project_targets(x_agg), self.att, self.bias, plan, self.heads)
 
     def forward(self, x, edge_index):

@@ -83,10 +83,14 @@ def plan_for(graph_wrapper, proj_features=None):
             with torch.cuda.device(dev):
                 plan = SegmentPlan(seg_ptr, perm, 1, k, single_segment_chunk(k), dev)
             setattr(graph_wrapper, _PLAN_ATTR, plan)
+        plan.shard = getattr(graph_wrapper, "shard", None)     # set for track-sharded scenes (gasfm_b200.dist)
         return plan
     assert proj_features is not None
     idx = index_for(proj_features)
-    return idx.by_view if graph_wrapper.agg_dim == 1 else idx.by_track
+    if graph_wrapper.agg_dim == 1:
+        idx.by_view.shard = getattr(graph_wrapper, "shard", None)
+        return idx.by_view
+    return idx.by_track
 
 
 # ---------------------------------------------------------------------------------------------

@@ -382,11 +382,23 @@ def _nan_to_zero_mean(values, indices, shape, dim):
 # ----------------------------------------------------------------------------------------
 def synthetic_observations(m, n, n_obs, seed, banded=True):
     """Row-major sorted, deduplicated observation list with >= 2 views per track and
-    >= 8 points per view.  Track j gets k_j = 2 + Poisson(E/n - 2) views (capped at m),
-    drawn around a track-specific centre when ``banded`` (mimics real visibility)."""
-    rng = np.random.default_rng(seed)
+    >= 8 points per view.  Track j gets k_j = 2 + Poisson(mean - 2) views (capped at m),
+    drawn around a track-specific centre when ``banded`` (mimics real visibility).  Duplicates
+    are dropped, so the per-track mean is re-tuned (at most 4 times) until E is within 1% of
+    ``n_obs``."""
     mean_deg = max(n_obs / n, 2.0)
-    k = np.minimum(2 + rng.poisson(mean_deg - 2.0, size=n), m).astype(np.int64)
+    for attempt in range(4):
+        idx, vals = _synthetic_observations_once(m, n, mean_deg, seed, banded)
+        got = idx.shape[1]
+        if abs(got - n_obs) <= 0.01 * n_obs or mean_deg >= m:
+            break
+        mean_deg = min(float(m), max(2.0, 2.0 + (mean_deg - 2.0) * (n_obs - 2.0 * n) / max(got - 2.0 * n, 1.0)))
+    return idx, vals
+
+
+def _synthetic_observations_once(m, n, mean_deg, seed, banded):
+    rng = np.random.default_rng(seed)
+    k = np.minimum(2 + rng.poisson(max(mean_deg - 2.0, 0.0), size=n), m).astype(np.int64)
     cols = np.repeat(np.arange(n, dtype=np.int64), k)
     if banded:
         centre = rng.uniform(0, m, size=n)

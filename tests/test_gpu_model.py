@@ -148,3 +148,16 @@ def test_full_size_properties_cfg2():
     tot = XL.double().sum(0)
     for plan in (oi.by_view, oi.by_track):
         assert torch.allclose(seg_sum_raw(XL, plan).double().sum(0), tot, rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_track_sharded_model_matches_single_gpu():
+    """N=2 over NCCL: sharded forward/backward == single-GPU forward/backward (tools/check_sharded_model.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631",
+                        os.path.join(root, "tools", "check_sharded_model.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
