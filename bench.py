@@ -129,6 +129,15 @@ def timed(fn, steps, warmup, sync_dist=False):
     return ms
 
 
+def timed_batches(fn, batches=5, per_batch=5, warmup=5):
+    """Average launch duration over batches x per_batch launches (CUDA events).  A batch that is more
+    than 10x the median batch (a one-off stall of a fresh process, seen once on this pool) is dropped."""
+    ms = [timed(fn, per_batch, warmup if b == 0 else 0) for b in range(batches)]
+    med = float(np.median(ms))
+    kept = [t for t in ms if t <= 10 * med]
+    return float(np.mean(kept))
+
+
 def kernel_roofline(cfg, peak_gbs, peak_kind):
     """Edge-attention kernels alone at the workload's shapes (E observations, HC = n_feat_proj):
     algorithmic bytes / CUDA-event time.  XL (E x HC fp32 = 512 MB at cfg2) exceeds the
@@ -151,8 +160,8 @@ def kernel_roofline(cfg, peak_gbs, peak_kind):
         out, mx, sm = ops.gat_edge_partial(XL, XR, att, plan, H)
         out = out / sm.repeat_interleave(HC // H, dim=1).clamp_min(1e-30)
         dO = torch.randn(T, HC, device=dev)
-        fwd_ms = timed(lambda: ops.gat_edge_partial(XL, XR, att, plan, H), 20, 5)
-        bwd_ms = timed(lambda: ops.gat_edge_backward_raw(XL, XR, att, out, mx, sm, dO, plan, H), 20, 5)
+        fwd_ms = timed_batches(lambda: ops.gat_edge_partial(XL, XR, att, plan, H))
+        bwd_ms = timed_batches(lambda: ops.gat_edge_backward_raw(XL, XR, att, out, mx, sm, dO, plan, H))
         fwd_bytes = E * (HC * 4 + 4) + T * (2 * HC * 4 + 8 * H)
         bwd_bytes = E * (2 * HC * 4 + 4) + T * (4 * HC * 4 + 8 * H)
         res[f"gat_fwd_{name}"] = dict(ms=fwd_ms, bytes=fwd_bytes, gbs=fwd_bytes / fwd_ms / 1e6)

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgasfm_b200.so")
+LIB_PATH = os.environ.get("GASFM_B200_LIB", os.path.join(_HERE, "lib", "libgasfm_b200.so"))  # override: A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gasfm_b200.h")
 
 _c = ctypes

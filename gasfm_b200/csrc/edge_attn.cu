@@ -246,8 +246,11 @@ __device__ __forceinline__ void finalize_segment(const GatFwdArgs& p, int t, int
   }
 }
 
+// Resident CTAs per SM (register cap), measured on B200 at H*C = 256 (profiles/r01_edge_kernel_occupancy_ab.md):
+// the gathered short-segment schedule wants more warps in flight (3 CTAs, <= 80 regs, a few spills),
+// the contiguous chunked schedule is faster with 2 CTAs and no spills.
 template <int H, int C, bool CHUNKED>
-__global__ void __launch_bounds__(256) gat_fwd_kernel(GatFwdArgs p) {
+__global__ void __launch_bounds__(256, (H * C <= 256) ? (CHUNKED ? 2 : 3) : 1) gat_fwd_kernel(GatFwdArgs p) {
   using L = Lay<H, C>;
   const int lane = threadIdx.x & 31;
   const int lir = lane % L::LPR;
@@ -490,7 +493,7 @@ __device__ __forceinline__ void sum_across_groups(float4 (&a)[L::NV]) {
 }
 
 template <int H, int C, bool CHUNKED>
-__global__ void __launch_bounds__(kBwdThreads) gat_bwd_kernel(GatBwdArgs p) {
+__global__ void __launch_bounds__(kBwdThreads, (H * C <= 256) ? (CHUNKED ? 2 : 3) : 1) gat_bwd_kernel(GatBwdArgs p) {
   using L = Lay<H, C>;
   constexpr int NW = kBwdThreads / 32;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
