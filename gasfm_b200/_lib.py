@@ -37,6 +37,9 @@ SIGNATURES = {
     "gasfm_ln_relu_bwd_ws_bytes": (_SZ, [_L, _I]),
     "gasfm_ln_relu_bwd": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _P]),
     "gasfm_edge_update_fwd": (_I, [_P, _L, _P, _I, _P, _P, _P, _P, _P, _L, _P, _P, _L, _I, _F, _F, _P, _P]),
+    "gasfm_split_tf32": (_I, [_P, _P, _P, _L, _P]),
+    "gasfm_linear_tf32x3_supported": (_I, [_L, _I, _I, _L, _L]),
+    "gasfm_linear_tf32x3": (_I, [_P, _L, _P, _P, _P, _P, _L, _L, _I, _I, _P]),
     "gasfm_csr_build_host": (_I, [_P, _L, _I, _I, _P, _P, _P]),
     "gasfm_gat_edge_fwd_host": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P]),
 }

@@ -1,0 +1,327 @@
+// C[M,N] = A[M,K] * B[N,K]^T (+ bias), fp32 in / fp32 out, on the 5th-generation tensor cores
+// (tcgen05.mma kind::tf32, accumulators in TMEM, operands staged by TMA) with the 3xTF32 split
+//     A*B ~= A_hi*B_hi + A_lo*B_hi + A_hi*B_lo,     x_hi = tf32(x), x_lo = x - x_hi
+// which keeps fp32-level accuracy (~1e-6 relative), as the reference's fp32 GEMMs have
+// (TF32 is off by default in PyTorch), while leaving the SIMT pipes.
+//
+// This is the dense per-observation projection of the GASFM layers: lin_l of the two GATv2 graphs
+// and lin_proj of the observation update ([E,d] x [d,d'] with E in the millions, d <= 256), and the
+// matching input gradients dX = dY * W.  Replaces cuBLAS SGEMM behind torch.nn.functional.linear
+// at reference call sites code/models/layers.py:329,426 (GATv2Conv.lin_l) and :941 (lin_proj).
+//
+// Kernel structure (one persistent CTA per SM, 10 warps):
+//   warp 0      TMA producer: A tile [128 x 32] fp32, B_hi / B_lo tiles [N x 32] per K-block (SWIZZLE_128B)
+//   warp 1      TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit to the barriers
+//   warps 2-5   splitter: rewrite the A tile in place as tf32(A) and write A - tf32(A) next to it
+//   warps 6-9   epilogue: tcgen05.ld the 128 x N accumulator, add bias, store rows to global
+// Pipelines: smem ring full -> split_done -> (mma) -> empty; TMEM ring tmem_full <-> tmem_empty (2 accumulators).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "../../include/gasfm_b200.h"
+
+namespace gasfm {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;            // 32 fp32 = 128 bytes = one SWIZZLE_128B atom row
+constexpr int kUmmaK = 8;              // tf32: 32 bytes per MMA along K
+constexpr int kStages = 2;
+constexpr int kGemmThreads = 320;
+constexpr int kATileBytes = kBlockM * kBlockK * 4;   // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address and
+// offsets in 16-byte units, LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows x 128 B), version 1.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ float tf32_hi(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+struct GemmArgs {
+  const float* bias; float* C; int64_t ldc; int64_t M; int N; int K; int tmem_cols;
+};
+
+template <int kDummy>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                   const __grid_constant__ CUtensorMap map_blo, GemmArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stage][A_hi 16K | A_lo 16K | B_hi N*128 | B_lo N*128], all 1024-aligned (N*128 is a multiple of 1024 for N%8==0)
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_tile_bytes = p.N * kBlockK * 4;
+  const int stage_bytes = 2 * kATileBytes + 2 * b_tile_bytes;
+  __shared__ uint64_t full_bar[kStages], split_bar[kStages], empty_bar[kStages], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float bias_s[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k_blocks = (p.K + kBlockK - 1) / kBlockK;
+  const int64_t num_tiles = (p.M + kBlockM - 1) / kBlockM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&split_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int j = threadIdx.x; j < 256; j += kGemmThreads) bias_s[j] = (p.bias && j < p.N) ? p.bias[j] : 0.f;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+  const int acc_cols = p.tmem_cols / 2;     // column offset of the second accumulator
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], kATileBytes + 2 * b_tile_bytes);
+          tma_load_2d(st, &map_a, &full_bar[stage], kb * kBlockK, (int)(tile * kBlockM));
+          tma_load_2d(st + 2 * kATileBytes, &map_bhi, &full_bar[stage], kb * kBlockK, 0);
+          tma_load_2d(st + 2 * kATileBytes + b_tile_bytes, &map_blo, &full_bar[stage], kb * kBlockK, 0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&split_bar[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t a_lo = a_hi + kATileBytes;
+          const uint32_t b_hi = a_hi + 2 * kATileBytes;
+          const uint32_t b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint32_t koff = k * kUmmaK * 4;   // bytes along K inside the 128-byte swizzle row
+            const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+            umma_tf32(d_tmem, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, first);
+            umma_tf32(d_tmem, make_desc(a_lo + koff), make_desc(b_hi + koff), idesc, 1u);
+            umma_tf32(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);            // smem stage reusable once these MMAs retire
+          if (kb == num_k_blocks - 1) umma_commit(&tmem_full_bar[acc]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== splitter (128 threads) =====================
+    const int t = threadIdx.x - 64;
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < num_k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        float4* a = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
+        float4* lo = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + kATileBytes);
+        // element-wise at identical (swizzled) addresses, so the layout TMA produced is preserved
+#pragma unroll
+        for (int i = 0; i < kATileBytes / 16 / 128; ++i) {
+          const int idx = t + i * 128;
+          float4 v = a[idx], h, l;
+          h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          a[idx] = h;
+          lo[idx] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+        mbar_arrive(&split_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 6..9 -> TMEM lane quarters 2,3,0,1) =====================
+    const int quarter = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t row = tile * kBlockM + quarter * 32 + lane;
+      float* crow = p.C + row * p.ldc;
+      const uint32_t taddr0 = tmem_base + (uint32_t)(acc * acc_cols) + ((uint32_t)(quarter * 32) << 16);
+      for (int c0 = 0; c0 < p.N; c0 += 32) {
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr0 + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < p.M) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (c0 + j < p.N) {
+              float4 v;
+              v.x = __uint_as_float(r[j]) + bias_s[c0 + j];
+              v.y = __uint_as_float(r[j + 1]) + bias_s[c0 + j + 1];
+              v.z = __uint_as_float(r[j + 2]) + bias_s[c0 + j + 2];
+              v.w = __uint_as_float(r[j + 3]) + bias_s[c0 + j + 3];
+              *reinterpret_cast<float4*>(crow + c0 + j) = v;
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = w[i], h = tf32_hi(x);
+  hi[i] = h;
+  lo[i] = x - h;
+}
+
+// ---- host: tensor maps via the driver entry point (no link-time dependency on libcuda) -----------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// row-major [rows, cols] fp32 with row stride ld (elements); box = [box_rows x 32 cols], SWIZZLE_128B
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("gemm_tf32x3: cuTensorMapEncodeTiled is unavailable"); return 1; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_tf32x3: cuTensorMapEncodeTiled failed (%d)", (int)r); return 1; }
+  return 0;
+}
+
+}  // namespace gasfm
+
+using namespace gasfm;
+
+extern "C" int gasfm_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  split_tf32_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(w, hi, lo, n);
+  return check_launch("split_tf32");
+}
+
+extern "C" int gasfm_linear_tf32x3_supported(int64_t M, int N, int K, int64_t lda, int64_t ldc) {
+  return (M > 0 && N >= 16 && N <= 256 && N % 16 == 0 && K >= 4 && K % 4 == 0 && lda % 4 == 0 && ldc % 4 == 0) ? 1 : 0;
+}
+
+extern "C" int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo, const float* bias,
+                                   float* C, int64_t ldc, int64_t M, int N, int K, void* stream) {
+  GASFM_REQUIRE(gasfm_linear_tf32x3_supported(M, N, K, lda, ldc), "linear_tf32x3: unsupported shape M=%lld N=%d K=%d lda=%lld ldc=%lld",
+                (long long)M, N, K, (long long)lda, (long long)ldc);
+  GASFM_REQUIRE(((uintptr_t)A | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C) % 16 == 0, "linear_tf32x3: pointers must be 16-byte aligned");
+  CUtensorMap ma, mh, ml;
+  if (make_map(&ma, A, M, K, lda, kBlockM) || make_map(&mh, B_hi, N, K, K, N) || make_map(&ml, B_lo, N, K, K, N)) return 1;
+  int tmem_cols = 32;
+  while (tmem_cols < 2 * N) tmem_cols <<= 1;
+  const size_t smem = (size_t)kStages * (2 * kATileBytes + 2 * (size_t)N * kBlockK * 4) + 1024;
+  static size_t smem_allowed = 0;   // static smem (barriers, bias) also counts against the 227 KB per-CTA limit
+  if (smem > smem_allowed) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("linear_tf32x3: cannot reserve %zu bytes of shared memory (%s)", smem, cudaGetErrorString(e));
+      return (int)e;
+    }
+    smem_allowed = smem;
+  }
+  const int64_t tiles = (M + kBlockM - 1) / kBlockM;
+  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  GemmArgs args{bias, C, ldc, M, N, K, tmem_cols};
+  gemm_tf32x3_kernel<0><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ma, mh, ml, args);
+  return check_launch("linear_tf32x3");
+}

@@ -286,3 +286,71 @@ class _EdgeUpdate(torch.autograd.Function):
 
 def edge_update(P, x0, W0, S, V, g, skip, index, pscale=1.0, scale=0.25):
     return _EdgeUpdate.apply(P, x0, W0, S, V, g, skip, index, pscale, scale)
+
+
+# ---------------------------------------------------------------------------------------------
+# dense per-observation projection on the tensor cores (tcgen05, 3xTF32 split)
+# ---------------------------------------------------------------------------------------------
+def _split_tf32(w):
+    w = w.contiguous()
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    with torch.cuda.device(w.device):
+        _lib.call("gasfm_split_tf32", _lib.ptr(w), _lib.ptr(hi), _lib.ptr(lo), w.numel(), _lib.stream_ptr())
+    return hi, lo
+
+
+def gemm_tf32x3_supported(M, N, K, lda, ldc):
+    return bool(_lib.load().gasfm_linear_tf32x3_supported(int(M), int(N), int(K), int(lda), int(ldc)))
+
+
+def gemm_tf32x3(a, b, bias=None):
+    """a [M,K] (rows contiguous, any row stride) times b[N,K]^T (+ bias[N]) -> [M,N], fp32 accuracy."""
+    a, lda = _rows(a)
+    M, K = a.shape
+    N = b.shape[0]
+    hi, lo = _split_tf32(b)
+    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.call("gasfm_linear_tf32x3", _lib.ptr(a), lda, _lib.ptr(hi), _lib.ptr(lo),
+                  _lib.ptr(None if bias is None else bias.contiguous()), _lib.ptr(c), N, M, N, K, _lib.stream_ptr())
+    return c
+
+
+class _LinearTC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return gemm_tf32x3(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            M, N = dy.shape
+            K = weight.shape[1]
+            if gemm_tf32x3_supported(M, K, N, N, K):
+                dx = gemm_tf32x3(dy, weight.t())           # dX[M,K] = dY[M,N] * (W^T)[K,N]^T
+            else:
+                dx = dy @ weight
+        if ctx.needs_input_grad[1]:
+            dw = dy.t() @ x
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(dim=0)
+        return dx, dw, db
+
+
+TENSOR_CORE_MIN_ROWS = 4096   # below this the launch overhead dominates; cuBLAS is fine
+
+
+def linear(x, weight, bias=None):
+    """``F.linear`` for the observation-level projections: tcgen05 3xTF32 GEMM when the shape allows
+    (N <= 256, multiples of 16 / 4), cuBLAS fp32 otherwise (tiny first-layer widths)."""
+    M, K = x.shape
+    N = weight.shape[0]
+    lda = x.stride(0) if x.stride(1) == 1 else K
+    if x.is_cuda and M >= TENSOR_CORE_MIN_ROWS and gemm_tf32x3_supported(M, N, K, lda, N):
+        return _LinearTC.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)

@@ -166,6 +166,19 @@ GASFM_API int gasfm_edge_update_fwd(const float* P, int64_t ldp, const float* x0
                           int64_t n_obs, int width, float pscale, float scale, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Dense per-observation projection on the tensor cores (tcgen05, 3xTF32 split = fp32-level accuracy)
+ *   C[M,N] = A[M,K] * B[N,K]^T + bias      fp32 in, fp32 out, N <= 256 (multiple of 16), K multiple of 4
+ * Replaces cuBLAS SGEMM for GATv2Conv.lin_l (models/layers.py:329,426 via PyG) and lin_proj
+ * (models/layers.py:941) and their input gradients.  B_hi / B_lo are the tf32 split of the weight
+ * matrix, produced by gasfm_split_tf32 (hi = tf32(w), lo = w - hi).
+ * ------------------------------------------------------------------------------------- */
+GASFM_API int gasfm_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream);
+GASFM_API int gasfm_linear_tf32x3_supported(int64_t M, int N, int K, int64_t lda, int64_t ldc);
+GASFM_API int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo,
+                                  const float* bias, float* C, int64_t ldc, int64_t M, int N, int K,
+                                  void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (inputs and outputs in HOST memory; allocation and the
  * host<->device copies happen inside the call).  These are what a non-torch host binds.
  * ------------------------------------------------------------------------------------- */
