@@ -22,7 +22,8 @@ SIGNATURES = {
     "gasfm_m2sparse_count": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "gasfm_m2sparse_ws_bytes": (_SZ, [_I, _I]),
     "gasfm_m2sparse_fill": (_I, [_P, _P, _P, _I, _I, _L, _P, _P, _P, _P]),
-    "gasfm_csr_build": (_I, [_P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "gasfm_csr_build_ws_bytes": (_SZ, [_L, _I]),
+    "gasfm_csr_build": (_I, [_P, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gasfm_plan_chunks": (_I, [_P, _I, _I, _P, _P, _I, _P]),
     "gasfm_gat_ws_bytes": (_SZ, [_I, _I, _I]),
     "gasfm_gat_edge_fwd": (_I, [_P, _L, _P, _L, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _F, _I,
@@ -40,6 +41,9 @@ SIGNATURES = {
     "gasfm_split_tf32": (_I, [_P, _P, _P, _L, _P]),
     "gasfm_linear_tf32x3_supported": (_I, [_L, _I, _I, _L, _L]),
     "gasfm_linear_tf32x3": (_I, [_P, _L, _P, _P, _P, _P, _L, _L, _I, _I, _P]),
+    "gasfm_wgrad_tf32x3_supported": (_I, [_L, _I, _I, _L, _L]),
+    "gasfm_wgrad_tf32x3_ws_bytes": (_SZ, [_I, _I]),
+    "gasfm_wgrad_tf32x3": (_I, [_P, _L, _P, _L, _L, _I, _I, _P, _P, _P]),
     "gasfm_csr_build_host": (_I, [_P, _L, _I, _I, _P, _P, _P]),
     "gasfm_gat_edge_fwd_host": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P]),
 }

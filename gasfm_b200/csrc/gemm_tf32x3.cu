@@ -16,6 +16,7 @@
 //   warps 6-9   epilogue: tcgen05.ld the 128 x N accumulator, add bias, store rows to global
 // Pipelines: smem ring full -> split_done -> (mma) -> empty; TMEM ring tmem_full <-> tmem_empty (2 accumulators).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/gasfm_b200.h"
@@ -248,6 +249,204 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 }
 
+// =============================================================================================
+// Weight gradient:  dW[Nout,Kout] = dY[E,Nout]^T * X[E,Kout]   (reduction over the E observation rows)
+//
+// Both operands are activations stored row-major with the reduction index E as the slow dimension,
+// i.e. they are MN-major UMMA operands: a TMA box of [32 columns x 16 rows] lands in shared memory as
+// 16 rows of 128 bytes (TMA SWIZZLE_128B_ATOM_32B), which is exactly the canonical MN-major tf32 layout
+// (UMMA SWIZZLE_128B_BASE32B) ((4,8,m),(4,k)) : ((1,4,LBO),(32,SBO)) with LBO = box size, SBO = 512 B.  Each CTA owns a
+// contiguous range of E, accumulates the full [Nout x Kout] result in TMEM (2 x 256 columns) and
+// writes one partial; a small kernel sums the partials (deterministic split-K).
+// Both operands need the hi/lo split, done in place by the 8 worker warps, which also run the epilogue.
+// =============================================================================================
+constexpr int kWgRows = 16;                       // E rows per pipeline stage
+constexpr int kWgBoxBytes = 32 * kWgRows * 4;     // 2 KB
+constexpr int kWgStages = 3;
+constexpr int kWgThreads = 320;
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(kWgBoxBytes >> 4) << 16;        // LBO: next 32-column block
+  d |= (uint64_t)(512 >> 4) << 32;                // SBO: next swizzle atom (4 rows of 128 B) along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                         // SWIZZLE_128B_BASE32B: the only MN-major layout for tf32
+  return d;
+}
+
+struct WgradArgs {
+  float* ws; int64_t E; int Nout; int Kout; int m_tiles; int a_boxes; int b_boxes; int tmem_cols; int64_t rows_per_cta; int pass_stages;
+};
+
+template <int kDummy>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, WgradArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // stage: [A_hi a_boxes*2K | A_lo | B_hi b_boxes*2K | B_lo]
+  const int a_bytes = p.a_boxes * kWgBoxBytes, b_bytes = p.b_boxes * kWgBoxBytes;
+  const int stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  __shared__ uint64_t full_bar[kWgStages], split_bar[kWgStages], empty_bar[kWgStages], done_bar, drained_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row_begin = (int64_t)blockIdx.x * p.rows_per_cta;
+  const int64_t row_end = min(row_begin + p.rows_per_cta, p.E);
+  const int num_stages_total = row_end > row_begin ? (int)((row_end - row_begin + kWgRows - 1) / kWgRows) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&split_bar[s], 256); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&done_bar, 1);
+    mbar_init(&drained_bar, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+  // The tensor core accumulates in fp32 without rounding to nearest, so the error of a TMEM accumulator
+  // grows with the length of the chain.  The E range of a CTA is therefore processed in passes of
+  // pass_stages stages; after each pass the accumulator is drained and added into the CTA's partial.
+  const int num_passes = num_stages_total > 0 ? (num_stages_total + p.pass_stages - 1) / p.pass_stages : 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < num_stages_total; ++it) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + (size_t)stage * stage_bytes;
+        const int e0 = (int)(row_begin + (int64_t)it * kWgRows);
+        mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+        for (int j = 0; j < p.a_boxes; ++j) tma_load_2d(st + j * kWgBoxBytes, &map_dy, &full_bar[stage], j * 32, e0);
+        for (int j = 0; j < p.b_boxes; ++j) tma_load_2d(st + 2 * a_bytes + j * kWgBoxBytes, &map_x, &full_bar[stage], j * 32, e0);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D=f32, A=B=tf32, both MN-major (bits 15, 16), N = Kout, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(p.Kout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < num_stages_total; ++it) {
+        const int in_pass = it % p.pass_stages;
+        if (in_pass == 0 && it > 0) {
+          // previous pass fully issued: signal it, then wait until the workers have drained TMEM
+          umma_commit(&done_bar);
+          mbar_wait(&drained_bar, (uint32_t)((it / p.pass_stages - 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        mbar_wait(&split_bar[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t a_lo = a_hi + a_bytes, b_hi = a_hi + 2 * a_bytes, b_lo = b_hi + b_bytes;
+#pragma unroll
+        for (int k = 0; k < kWgRows / kUmmaK; ++k) {
+          const uint32_t koff = k * 1024;                      // 8 rows of 128 B
+          const uint32_t acc = (in_pass == 0 && k == 0) ? 0u : 1u;
+          for (int mt = 0; mt < p.m_tiles; ++mt) {
+            const uint32_t d = tmem_base + (uint32_t)(mt * p.Kout);
+            const uint32_t moff = mt * 4 * kWgBoxBytes;        // 128 columns of dY = 4 boxes
+            umma_tf32(d, make_desc_mn(a_hi + moff + koff), make_desc_mn(b_hi + koff), idesc, acc);
+            umma_tf32(d, make_desc_mn(a_lo + moff + koff), make_desc_mn(b_hi + koff), idesc, 1u);
+            umma_tf32(d, make_desc_mn(a_hi + moff + koff), make_desc_mn(b_lo + koff), idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&done_bar);
+    }
+  } else {
+    // ===================== 8 worker warps: split both operands, then epilogue =====================
+    const int t = threadIdx.x - 64;                            // 0..255
+    int stage = 0; uint32_t phase = 0;
+    const int a_vec = a_bytes / 16, tot_vec = (a_bytes + b_bytes) / 16;
+    // epilogue role: warps 2..5 -> M tile 0, warps 6..9 -> M tile 1; TMEM lane quarter = warp % 4
+    const int mt = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int n_out = mt * 128 + quarter * 32 + lane;
+    float* dst = p.ws + ((int64_t)blockIdx.x * p.Nout + n_out) * p.Kout;
+    const uint32_t taddr0 = tmem_base + (uint32_t)(mt * p.Kout) + ((uint32_t)(quarter * 32) << 16);
+    for (int pass = 0; pass < num_passes; ++pass) {
+      const int it_end = min(num_stages_total, (pass + 1) * p.pass_stages);
+      for (int it = pass * p.pass_stages; it < it_end; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        uint8_t* st = smem + (size_t)stage * stage_bytes;
+        for (int idx = t; idx < tot_vec; idx += 256) {
+          const bool is_a = idx < a_vec;
+          float4* hi = reinterpret_cast<float4*>(is_a ? st : st + 2 * a_bytes) + (is_a ? idx : idx - a_vec);
+          float4* lo = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(hi) + (is_a ? a_bytes : b_bytes));
+          float4 v = *hi, h, l;
+          h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          *hi = h;
+          *lo = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&split_bar[stage]);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+      // drain this pass's accumulator into the CTA's partial
+      if (num_stages_total > 0) {
+        mbar_wait(&done_bar, (uint32_t)(pass & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      if (mt < p.m_tiles) {
+        for (int c0 = 0; c0 < p.Kout; c0 += 16) {
+          uint32_t r[16];
+          if (num_stages_total > 0) {
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr0 + (uint32_t)c0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = 0u;
+          }
+          if (n_out < p.Nout) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+              if (pass > 0) {
+                const float4 o = *reinterpret_cast<const float4*>(dst + c0 + j);
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+              }
+              *reinterpret_cast<float4*>(dst + c0 + j) = v;
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&drained_bar);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// out[i] = sum_r ws[r, i] for i < width (width = Nout*Kout), deterministic
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int rows, int64_t width, float* __restrict__ out) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= width) return;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < rows; ++r) {
+    const float4 v = *reinterpret_cast<const float4*>(ws + (int64_t)r * width + i);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + i) = a;
+}
+
 __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -272,18 +471,22 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// row-major [rows, cols] fp32 with row stride ld (elements); box = [box_rows x 32 cols], SWIZZLE_128B
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// row-major [rows, cols] fp32 with row stride ld (elements); box = [box_rows x box_cols], SWIZZLE_128B
+static int make_map_box(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
+                        CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("gemm_tf32x3: cuTensorMapEncodeTiled is unavailable"); return 1; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("gemm_tf32x3: cuTensorMapEncodeTiled failed (%d)", (int)r); return 1; }
   return 0;
+}
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  return make_map_box(map, base, rows, cols, ld, box_rows, kBlockK);
 }
 
 }  // namespace gasfm
@@ -324,4 +527,51 @@ extern "C" int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_h
   GemmArgs args{bias, C, ldc, M, N, K, tmem_cols};
   gemm_tf32x3_kernel<0><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ma, mh, ml, args);
   return check_launch("linear_tf32x3");
+}
+
+extern "C" int gasfm_wgrad_tf32x3_supported(int64_t E, int Nout, int Kout, int64_t lddy, int64_t ldx) {
+  return (E > 0 && Nout >= 4 && Nout <= 256 && Nout % 4 == 0 && Kout >= 16 && Kout <= 256 && Kout % 16 == 0 && lddy % 4 == 0 && ldx % 4 == 0) ? 1 : 0;
+}
+
+extern "C" size_t gasfm_wgrad_tf32x3_ws_bytes(int Nout, int Kout) {
+  return (size_t)kNumSMs * Nout * Kout * sizeof(float);
+}
+
+extern "C" int gasfm_wgrad_tf32x3(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t E, int Nout, int Kout,
+                                  float* dW, void* ws, void* stream) {
+  GASFM_REQUIRE(gasfm_wgrad_tf32x3_supported(E, Nout, Kout, lddy, ldx), "wgrad_tf32x3: unsupported shape E=%lld Nout=%d Kout=%d",
+                (long long)E, Nout, Kout);
+  GASFM_REQUIRE(ws != nullptr && ((uintptr_t)dY | (uintptr_t)X | (uintptr_t)dW | (uintptr_t)ws) % 16 == 0, "wgrad_tf32x3: bad pointers");
+  CUtensorMap mdy, mx;
+  // MN-major tf32 operands only exist in the 128B-swizzle-with-32B-atom layout (UMMA SWIZZLE_128B_BASE32B)
+  if (make_map_box(&mdy, dY, E, Nout, lddy, kWgRows, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+      make_map_box(&mx, X, E, Kout, ldx, kWgRows, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+  const int m_tiles = (Nout + 127) / 128;
+  const int a_boxes = m_tiles * 4, b_boxes = (Kout + 31) / 32;
+  int tmem_cols = 32;
+  while (tmem_cols < m_tiles * Kout) tmem_cols <<= 1;
+  const size_t smem = (size_t)kWgStages * 2 * (a_boxes + b_boxes) * kWgBoxBytes + 1024;
+  static size_t smem_allowed = 0;
+  if (smem > smem_allowed) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tf32x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("wgrad_tf32x3: cannot reserve %zu bytes of shared memory (%s)", smem, cudaGetErrorString(e)); return (int)e; }
+    smem_allowed = smem;
+  }
+  const int64_t units = (E + kWgRows - 1) / kWgRows;
+  const int grid = (int)(units < kNumSMs ? units : kNumSMs);
+  const int64_t rows_per_cta = ((units + grid - 1) / grid) * kWgRows;
+  static int pass_stages = 0;
+  if (pass_stages == 0) {
+    const char* env = getenv("GASFM_WGRAD_PASS_STAGES");   // tuning knob; default chosen from the A/B in profiles/
+    pass_stages = env ? atoi(env) : 64;
+    if (pass_stages < 1) pass_stages = 64;
+  }
+  WgradArgs a{(float*)ws, E, Nout, Kout, m_tiles, a_boxes, b_boxes, tmem_cols, rows_per_cta, pass_stages};
+  cudaStream_t st = (cudaStream_t)stream;
+  wgrad_tf32x3_kernel<0><<<grid, kWgThreads, smem, st>>>(mdy, mx, a);
+  int rc = check_launch("wgrad_tf32x3");
+  if (rc) return rc;
+  const int64_t width = (int64_t)Nout * Kout;
+  wgrad_reduce_kernel<<<ceil_div(width / 4, 256), 256, 0, st>>>((const float*)ws, grid, width, dW);
+  return check_launch("wgrad_tf32x3(reduce)");
 }

@@ -51,7 +51,8 @@ extern "C" const char* gasfm_last_error(void) { return g_err; }
 extern "C" int gasfm_csr_build_host(const int64_t* indices_host, int64_t n_obs, int m, int n, int32_t* row_ptr_host,
                                     int32_t* col_ptr_host, int32_t* csc_perm_host) {
   GASFM_REQUIRE(indices_host && row_ptr_host && col_ptr_host && csc_perm_host, "csr_build_host: NULL argument");
-  DevBuf idx, ri, ci, rp, cp, perm, status;
+  DevBuf idx, ri, ci, rp, cp, perm, status, ws;
+  CU_OK(ws.alloc(gasfm_csr_build_ws_bytes(n_obs, n)), "csr_build_host");
   CU_OK(idx.alloc((size_t)2 * n_obs * sizeof(int64_t)), "csr_build_host");
   CU_OK(ri.alloc((size_t)n_obs * 4), "csr_build_host");
   CU_OK(ci.alloc((size_t)n_obs * 4), "csr_build_host");
@@ -61,7 +62,7 @@ extern "C" int gasfm_csr_build_host(const int64_t* indices_host, int64_t n_obs, 
   CU_OK(status.alloc(4), "csr_build_host");
   CU_OK(cudaMemcpy(idx.p, indices_host, (size_t)2 * n_obs * sizeof(int64_t), cudaMemcpyHostToDevice), "csr_build_host");
   int rc = gasfm_csr_build(idx.as<int64_t>(), n_obs, m, n, ri.as<int32_t>(), ci.as<int32_t>(), rp.as<int32_t>(),
-                           cp.as<int32_t>(), perm.as<int32_t>(), status.as<int32_t>(), nullptr);
+                           cp.as<int32_t>(), perm.as<int32_t>(), status.as<int32_t>(), ws.p, nullptr);
   if (rc) return rc;
   int32_t st = 0;
   CU_OK(cudaMemcpy(&st, status.p, 4, cudaMemcpyDeviceToHost), "csr_build_host");
@@ -82,7 +83,8 @@ extern "C" int gasfm_gat_edge_fwd_host(const float* XL_host, const float* XR_hos
   // so the CSC half of csr_build yields the stable grouping by target.
   std::vector<int64_t> pairs((size_t)2 * n_obs);
   for (int64_t e = 0; e < n_obs; ++e) { pairs[e] = e; pairs[n_obs + e] = target_host[e]; }
-  DevBuf idx, ri, ci, rp, cp, perm, status, xl, xr, att, bias, out, smax, ssum, ws, cptr, cseg;
+  DevBuf idx, ri, ci, rp, cp, perm, status, xl, xr, att, bias, out, smax, ssum, ws, cptr, cseg, csr_ws;
+  CU_OK(csr_ws.alloc(gasfm_csr_build_ws_bytes(n_obs, n_seg)), "gat_edge_fwd_host");
   CU_OK(idx.alloc(pairs.size() * sizeof(int64_t)), "gat_edge_fwd_host");
   CU_OK(ri.alloc(n_obs * 4), "gat_edge_fwd_host");
   CU_OK(ci.alloc(n_obs * 4), "gat_edge_fwd_host");
@@ -104,7 +106,7 @@ extern "C" int gasfm_gat_edge_fwd_host(const float* XL_host, const float* XR_hos
   if (bias_host) CU_OK(cudaMemcpy(bias.p, bias_host, HC * 4, cudaMemcpyHostToDevice), "gat_edge_fwd_host");
   GASFM_REQUIRE(n_obs < (int64_t)INT32_MAX, "gat_edge_fwd_host: too many edges");
   int rc = gasfm_csr_build(idx.as<int64_t>(), n_obs, (int)n_obs, n_seg, ri.as<int32_t>(), ci.as<int32_t>(),
-                           rp.as<int32_t>(), cp.as<int32_t>(), perm.as<int32_t>(), status.as<int32_t>(), nullptr);
+                           rp.as<int32_t>(), cp.as<int32_t>(), perm.as<int32_t>(), status.as<int32_t>(), csr_ws.p, nullptr);
   if (rc) return rc;
   int32_t st = 0;
   CU_OK(cudaMemcpy(&st, status.p, 4, cudaMemcpyDeviceToHost), "gat_edge_fwd_host");

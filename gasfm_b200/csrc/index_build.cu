@@ -317,36 +317,32 @@ extern "C" int gasfm_m2sparse_fill(const float* M, const float* Ns, const uint8_
   return check_launch("m2sparse_fill");
 }
 
+extern "C" size_t gasfm_csr_build_ws_bytes(int64_t n_obs, int n) {
+  return ((size_t)n + (size_t)n_obs + 8) * sizeof(int32_t);
+}
+
 extern "C" int gasfm_csr_build(const int64_t* indices, int64_t n_obs, int m, int n, int32_t* row_idx,
                                int32_t* col_idx, int32_t* row_ptr, int32_t* col_ptr, int32_t* csc_perm,
-                               int32_t* status, void* stream) {
+                               int32_t* status, void* ws, void* stream) {
   GASFM_REQUIRE(m > 0 && n > 0 && n_obs >= 0, "csr_build: bad sizes");
   GASFM_REQUIRE(n_obs < (int64_t)INT32_MAX, "csr_build: more than 2^31 observations");
+  GASFM_REQUIRE(ws != nullptr, "csr_build: workspace of gasfm_csr_build_ws_bytes() bytes required");
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(status, 0, sizeof(int32_t), st);
-  // col_ptr doubles as the count buffer, csc_perm's tail is not needed for that: use col_ptr[0..n)
   cudaMemsetAsync(col_ptr, 0, (size_t)(n + 1) * sizeof(int32_t), st);
   if (n_obs == 0) {
     cudaMemsetAsync(row_ptr, 0, (size_t)(m + 1) * sizeof(int32_t), st);
     return check_launch("csr_build(empty)");
   }
   const int blocks = ceil_div(n_obs, 256);
-  // counts go to a scratch area carved from csc_perm? No: keep it simple and exact -- a temporary.
-  int32_t* cnt = nullptr;
-  int32_t* tmp = nullptr;
-  if (cudaMallocAsync(&cnt, (size_t)n * sizeof(int32_t), st) != cudaSuccess ||
-      cudaMallocAsync(&tmp, (size_t)n_obs * sizeof(int32_t), st) != cudaSuccess) {
-    set_error("csr_build: out of memory for scratch (%lld observations)", (long long)n_obs);
-    return 2;
-  }
+  int32_t* cnt = (int32_t*)ws;                 // [n] per-track counters
+  int32_t* tmp = cnt + n;                      // [n_obs] claimed (unordered) CSC slots
   cudaMemsetAsync(cnt, 0, (size_t)n * sizeof(int32_t), st);
   csr_cast_kernel<<<blocks, 256, 0, st>>>(indices, n_obs, m, n, row_idx, col_idx, row_ptr, cnt, status);
   scan_excl_kernel<<<1, 1024, 0, st>>>(LoadI32{cnt}, n, col_ptr);
   cudaMemsetAsync(cnt, 0, (size_t)n * sizeof(int32_t), st);
   csc_claim_kernel<<<blocks, 256, 0, st>>>(col_idx, n_obs, col_ptr, cnt, tmp);
   csc_sort_kernel<<<ceil_div((int64_t)n * 32, 256), 256, 0, st>>>(col_ptr, n, tmp, csc_perm);
-  cudaFreeAsync(cnt, st);
-  cudaFreeAsync(tmp, st);
   return check_launch("csr_build");
 }
 

@@ -87,10 +87,11 @@ class ObservationIndex:
         self.col_ptr = torch.empty(n + 1, **i32)
         self.csc_perm = torch.empty(E, **i32)
         status = torch.zeros(1, **i32)
+        ws = torch.empty(_lib.size_query("gasfm_csr_build_ws_bytes", E, self.n) // 4 + 1, **i32)
         with torch.cuda.device(dev):
             _lib.call("gasfm_csr_build", _lib.ptr(indices), E, self.m, self.n, _lib.ptr(self.row_idx),
                       _lib.ptr(self.col_idx), _lib.ptr(self.row_ptr), _lib.ptr(self.col_ptr),
-                      _lib.ptr(self.csc_perm), _lib.ptr(status), _lib.stream_ptr())
+                      _lib.ptr(self.csc_perm), _lib.ptr(status), _lib.ptr(ws), _lib.stream_ptr())
             if validate:
                 st = int(status.item())
                 if st & 1:
@@ -134,9 +135,10 @@ def plan_from_targets(dst, n_targets):
     row_idx, col_idx = torch.empty(E, **i32), torch.empty(E, **i32)
     row_ptr, col_ptr = torch.empty(E + 1, **i32), torch.empty(n_targets + 1, **i32)
     perm, status = torch.empty(E, **i32), torch.zeros(1, **i32)
+    ws = torch.empty(_lib.size_query("gasfm_csr_build_ws_bytes", E, int(n_targets)) // 4 + 1, **i32)
     with torch.cuda.device(dev):
         _lib.call("gasfm_csr_build", _lib.ptr(pairs), E, max(E, 1), int(n_targets), _lib.ptr(row_idx), _lib.ptr(col_idx),
-                  _lib.ptr(row_ptr), _lib.ptr(col_ptr), _lib.ptr(perm), _lib.ptr(status), _lib.stream_ptr())
+                  _lib.ptr(row_ptr), _lib.ptr(col_ptr), _lib.ptr(perm), _lib.ptr(status), _lib.ptr(ws), _lib.stream_ptr())
         if int(status.item()) != 0:
             raise ValueError("edge targets out of range")
         avg = E / max(1, n_targets)

@@ -46,7 +46,8 @@ class GATv2Conv(nn.Module):
             self.bias.zero_()
 
     def project_sources(self, x_elements):
-        return F.linear(x_elements, self.lin_l.weight, self.lin_l.bias)
+        """lin_l on the source rows: tcgen05 3xTF32 GEMM for observation-sized inputs (ops.linear)."""
+        return ops.linear(x_elements, self.lin_l.weight, self.lin_l.bias)
 
     def project_targets(self, x_agg):
         """Query projection; ``None`` = zero query features -> one broadcast row ``lin_r.bias``."""

@@ -14,7 +14,8 @@ Node-level work (``[m, .]``, ``[n, .]``, ``[1, .]`` LayerNorms, Linears, MLPs) i
 cuBLAS through torch.
 """
 import torch
-from torch.nn import Linear, ReLU, LayerNorm, Sequential, Module, Identity
+from torch import nn
+from torch.nn import ReLU, Sequential, Module, Identity
 from torch.nn import functional as F
 
 from .. import ops
@@ -23,6 +24,35 @@ from ..utils.sparse_utils import SparseMat
 from ..utils import sparse_utils
 from ..utils.pos_enc_utils import get_embedder
 from .gatv2 import GATv2Conv
+
+
+class Linear(nn.Linear):
+    """``nn.Linear`` (same parameters / state_dict) whose forward runs the tcgen05 3xTF32 GEMM when the
+    input has thousands of rows (observation- and point-level features) and cuBLAS fp32 otherwise."""
+
+    def forward(self, x):
+        if x.dim() == 2 and x.is_cuda and x.dtype == torch.float32:
+            return ops.linear(x, self.weight, self.bias)
+        return F.linear(x, self.weight, self.bias)
+
+
+class LayerNorm(nn.LayerNorm):
+    """``nn.LayerNorm`` (same parameters); ``relu_(ln(x))`` patterns call ``ln_relu`` to get one fused kernel."""
+
+    def ln_relu(self, x):
+        if (x.dim() == 2 and x.is_cuda and x.dtype == torch.float32 and x.shape[0] >= 256 and x.shape[1] <= 1024
+                and self.elementwise_affine and self.bias is not None):
+            return ops.ln_relu(x, self.weight, self.bias, self.eps)
+        return F.relu(F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps))
+
+
+class _NormReluProj(Sequential):
+    """Sequential(LayerNorm, ReLU[, Linear]) with the state_dict layout of the reference's
+    ``norm_and_proj_*`` modules (indices 0 and 2), evaluated with the fused LayerNorm+ReLU kernel."""
+
+    def forward(self, x):
+        x = self[0].ln_relu(x)
+        return self[2](x) if len(self) > 2 else x
 
 
 def get_linear_layers(feats, init_activation=False, final_activation=False, norm=True):
@@ -131,7 +161,7 @@ class SetOfSetProjectionFeatureUpdate(Module):
         self.lin_proj = Linear(d_in, d_out)
 
     def forward(self, scenepoint_features, view_features, global_features, x):
-        proj = F.linear(x.values, 0.25 * self.lin_proj.weight, 0.25 * self.lin_proj.bias)
+        proj = ops.linear(x.values, 0.25 * self.lin_proj.weight, 0.25 * self.lin_proj.bias)
         new = ops.edge_update(proj, None, None, scenepoint_features, view_features, global_features, None,
                               index_for(x), 1.0, 0.25)
         return x.with_values(new)
@@ -282,7 +312,7 @@ class _AxialAttentionUpdate(Module):
             mods = [LayerNorm(n_feat_out), ReLU(inplace=True)]
             if n_feat_proj_in != n_feat_out:
                 mods.append(Linear(n_feat_out, n_feat_proj_in))
-            query_proj = Sequential(*mods)
+            query_proj = _NormReluProj(*mods)
         graph_conv = GATv2Conv(n_feat_proj_in, n_feat_agg // n_heads, heads=n_heads, add_self_loops=False)
         out_proj = Linear(n_feat_agg, n_feat_out) if n_feat_agg != n_feat_out else None
         norm_pre_mlp = LayerNorm(n_feat_out) if use_norm_pre_mlp else None
@@ -302,7 +332,7 @@ class _AxialAttentionUpdate(Module):
             x = prev + x
         h = x
         if norm_pre_mlp is not None:
-            h = F.relu(norm_pre_mlp(h))
+            h = norm_pre_mlp.ln_relu(h)
         return x + mlp(h)
 
 
@@ -386,7 +416,7 @@ class ViewAndScenePoint2Global(Module):
             mods = [LayerNorm(n_feat_global_out), ReLU(inplace=True)]
             if width != n_feat_global_out:
                 mods.append(Linear(n_feat_global_out, width))
-            return Sequential(*mods)
+            return _NormReluProj(*mods)
 
         if stateful:
             self.norm_and_proj_global2view = query_proj(n_feat_view_in)
@@ -422,7 +452,7 @@ class ViewAndScenePoint2Global(Module):
             x = prev_global_features + x
         h = x
         if self.use_norm_pre_mlp:
-            h = F.relu(self.norm_pre_mlp(h))
+            h = self.norm_pre_mlp.ln_relu(h)
         return x + self.mlp(h)
 
 
@@ -441,8 +471,8 @@ class _Global2Node(Module):
 
     @staticmethod
     def _run(prev, glob, node_norm, global_norm, lin_node, lin_global, mlp):
-        x = prev if node_norm is None else F.relu(node_norm(prev))
-        g = glob if global_norm is None else F.relu(global_norm(glob))
+        x = prev if node_norm is None else node_norm.ln_relu(prev)
+        g = glob if global_norm is None else global_norm.ln_relu(glob)
         x = lin_node(x) + lin_global(g)
         if mlp is not None:
             x = mlp(F.relu(x))
@@ -594,9 +624,9 @@ class GraphAttnSfMProjectionFeatureUpdate(Module):
         (layers.py:911-956).  ``residual`` (extension): SparseMat added to the result inside the same
         kernel -- the skip connection of GraphAttnSfMLayer (layers.py:254-261)."""
         if self.normalize_global_features:
-            scenepoint_features = F.relu(self.scenepoint_norm_layer(scenepoint_features))
-            view_features = F.relu(self.view_norm_layer(view_features))
-            global_features = F.relu(self.global_norm_layer(global_features))
+            scenepoint_features = self.scenepoint_norm_layer.ln_relu(scenepoint_features)
+            view_features = self.view_norm_layer.ln_relu(view_features)
+            global_features = self.global_norm_layer.ln_relu(global_features)
         sp = self.lin_scenepoint(scenepoint_features)
         view = self.lin_view(view_features)
         glob = self.lin_global(global_features)
@@ -605,10 +635,10 @@ class GraphAttnSfMProjectionFeatureUpdate(Module):
         x0 = w0 = None
         if isinstance(x, _LazyFeatureCat) and x._extra.shape[2] <= 4:
             d_main = x._main.shape[2]
-            proj = F.linear(x._main.values, 0.25 * w[:, :d_main], 0.25 * b)
+            proj = ops.linear(x._main.values, 0.25 * w[:, :d_main], 0.25 * b)
             x0, w0 = x._extra.values, w[:, d_main:]
         else:
-            proj = F.linear(x.values, 0.25 * w, 0.25 * b)
+            proj = ops.linear(x.values, 0.25 * w, 0.25 * b)
         has_mlp = self.n_hidden_layers_proj_update > 0
         fused_skip = None if (residual is None or has_mlp) else residual.values
         new = ops.edge_update(proj, x0, w0, sp, view, glob, fused_skip, index_for(x), 1.0, 0.25)
@@ -626,7 +656,7 @@ class ProjLayer(Module):
         self.lin_proj = Linear(n_feat_proj_in, n_feat_proj_out)
 
     def forward(self, x):
-        return x.with_values(self.lin_proj(x.values))
+        return x.with_values(ops.linear(x.values, self.lin_proj.weight, self.lin_proj.bias))
 
 
 def normalize_projection_features(x, norm_layer=None):

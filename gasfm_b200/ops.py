@@ -316,6 +316,24 @@ def gemm_tf32x3(a, b, bias=None):
     return c
 
 
+def wgrad_tf32x3_supported(E, n_out, k_out, lddy, ldx):
+    return bool(_lib.load().gasfm_wgrad_tf32x3_supported(int(E), int(n_out), int(k_out), int(lddy), int(ldx)))
+
+
+def wgrad_tf32x3(dy, x):
+    """dW[Nout,Kout] = dy[E,Nout]^T @ x[E,Kout] on the tensor cores (3xTF32, deterministic split-K)."""
+    dy, lddy = _rows(dy)
+    x, ldx = _rows(x)
+    E, n_out = dy.shape
+    k_out = x.shape[1]
+    dw = torch.empty((n_out, k_out), dtype=torch.float32, device=dy.device)
+    ws = torch.empty(_lib.size_query("gasfm_wgrad_tf32x3_ws_bytes", n_out, k_out) // 4, dtype=torch.float32, device=dy.device)
+    with torch.cuda.device(dy.device):
+        _lib.call("gasfm_wgrad_tf32x3", _lib.ptr(dy), lddy, _lib.ptr(x), ldx, E, n_out, k_out, _lib.ptr(dw), _lib.ptr(ws),
+                  _lib.stream_ptr())
+    return dw
+
+
 class _LinearTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -336,7 +354,11 @@ class _LinearTC(torch.autograd.Function):
             else:
                 dx = dy @ weight
         if ctx.needs_input_grad[1]:
-            dw = dy.t() @ x
+            lddx = x.stride(0) if x.stride(1) == 1 else x.shape[1]
+            if wgrad_tf32x3_supported(dy.shape[0], dy.shape[1], x.shape[1], dy.shape[1], lddx):
+                dw = wgrad_tf32x3(dy, x)
+            else:
+                dw = dy.t() @ x
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum(dim=0)
         return dx, dw, db

@@ -76,10 +76,12 @@ GASFM_API int gasfm_m2sparse_fill(const float* M, const float* Ns, const uint8_t
  *   row_idx[E], col_idx[E]  int32 copies of indices
  *   row_ptr[m+1]            CSR over views (storage order is already CSR order)
  *   col_ptr[n+1], csc_perm[E]  CSC over tracks; csc_perm is the STABLE sort by column
- * Returns an error if indices are out of range or not sorted row-major. */
+ * ``status`` (device int32) is set to 1 if indices are out of range, 2 if they are not sorted row-major.
+ * ``ws`` needs gasfm_csr_build_ws_bytes(n_obs, n) bytes of device scratch (no allocation inside). */
+GASFM_API size_t gasfm_csr_build_ws_bytes(int64_t n_obs, int n);
 GASFM_API int gasfm_csr_build(const int64_t* indices, int64_t n_obs, int m, int n,
                     int32_t* row_idx, int32_t* col_idx, int32_t* row_ptr,
-                    int32_t* col_ptr, int32_t* csc_perm, int32_t* status, void* stream);
+                    int32_t* col_ptr, int32_t* csc_perm, int32_t* status, void* ws, void* stream);
 
 /* Chunk tables of a plan (see header comment).  chunk_ptr[T+1], chunk_seg[max_chunks]. */
 GASFM_API int gasfm_plan_chunks(const int32_t* seg_ptr, int n_seg, int chunk, int32_t* chunk_ptr,
@@ -177,6 +179,13 @@ GASFM_API int gasfm_linear_tf32x3_supported(int64_t M, int N, int K, int64_t lda
 GASFM_API int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo,
                                   const float* bias, float* C, int64_t ldc, int64_t M, int N, int K,
                                   void* stream);
+
+/* Weight gradient of the same projections: dW[Nout,Kout] = dY[E,Nout]^T * X[E,Kout], 3xTF32 on tcgen05,
+ * deterministic split-K over the SMs.  ``ws`` needs gasfm_wgrad_tf32x3_ws_bytes(Nout,Kout) bytes. */
+GASFM_API int gasfm_wgrad_tf32x3_supported(int64_t E, int Nout, int Kout, int64_t lddy, int64_t ldx);
+GASFM_API size_t gasfm_wgrad_tf32x3_ws_bytes(int Nout, int Kout);
+GASFM_API int gasfm_wgrad_tf32x3(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t E,
+                                 int Nout, int Kout, float* dW, void* ws, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (inputs and outputs in HOST memory; allocation and the

@@ -348,3 +348,61 @@ def test_edge_update_forward_backward(w, d0):
     for got, want in ((Pg, P), (Sg, S), (Vg, V), (gg, gl), (sg, skip), (x0g, x0), (W0g, W0)):
         if want is not None:
             assert rel_err(got.grad, want.grad.numpy()) < GRAD_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 3xTF32 GEMM
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 16, 32), (1000, 256, 256), (4097, 32, 32), (300, 64, 100), (20000, 256, 260),
+                                   (5000, 48, 36), (129, 256, 4), (70000, 128, 64)])
+def test_gemm_tf32x3_has_fp32_accuracy(M, N, K):
+    """C = A W^T + b on the tensor cores must keep fp32-level accuracy (the reference's GEMMs are true
+    fp32): within 5x of cuBLAS fp32's own error against fp64, and ~100x better than single-pass TF32."""
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) / K ** 0.5
+    b = torch.randn(N, device=DEV)
+    ref = a.double() @ w.double().t() + b.double()
+    got = ops.gemm_tf32x3(a, w, b)
+    err = ((got.double() - ref).abs().max() / ref.abs().max()).item()
+    err32 = ((torch.nn.functional.linear(a, w, b).double() - ref).abs().max() / ref.abs().max()).item()
+    assert err < max(5 * err32, 4e-6), (err, err32)
+    # strided A (a column slice of a wider matrix) and no bias
+    wide = torch.randn(M, K + 8, device=DEV)
+    got2 = ops.gemm_tf32x3(wide[:, 4:4 + K], w)
+    ref2 = wide[:, 4:4 + K].double() @ w.double().t()
+    assert ((got2.double() - ref2).abs().max() / ref2.abs().max()).item() < max(5 * err32, 4e-6)
+
+
+def test_linear_autograd_matches_fp64():
+    torch.manual_seed(3)
+    M, N, K = 6000, 64, 32
+    x = torch.randn(M, K, device=DEV, requires_grad=True)
+    w = (torch.randn(N, K, device=DEV) / K ** 0.5).requires_grad_(True)
+    b = torch.randn(N, device=DEV, requires_grad=True)
+    dy = torch.randn(M, N, device=DEV)
+    y = ops.linear(x, w, b)
+    assert y.grad_fn is not None and type(y.grad_fn).__name__.startswith("_LinearTC")
+    y.backward(dy)
+    xd, wd, bd = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    (torch.nn.functional.linear(xd, wd, bd) * dy.double()).sum().backward()
+    assert rel_err(y, torch.nn.functional.linear(xd, wd, bd).detach().cpu().numpy()) < FP32_TOL
+    assert rel_err(x.grad, xd.grad.cpu().numpy()) < FP32_TOL
+    assert rel_err(w.grad, wd.grad.cpu().numpy()) < GRAD_TOL
+    assert rel_err(b.grad, bd.grad.cpu().numpy()) < GRAD_TOL
+
+
+@pytest.mark.parametrize("E,Nout,Kout", [(16, 32, 32), (1000, 256, 256), (4099, 32, 32), (3000, 64, 48), (70001, 256, 32),
+                                         (300000, 32, 256), (17, 4, 16)])
+def test_wgrad_tf32x3_has_fp32_accuracy(E, Nout, Kout):
+    """dW = dY^T X on the tensor cores (MN-major operands, split-K over SMs, accumulator drained every
+    256 stages): error against fp64 within 5x of cuBLAS fp32's, never worse than 1e-5 of the largest entry."""
+    torch.manual_seed(E + Nout)
+    dy = torch.randn(E, Nout, device=DEV)
+    x = torch.randn(E, Kout, device=DEV)
+    ref = dy.double().t() @ x.double()
+    got = ops.wgrad_tf32x3(dy, x)
+    err = ((got.double() - ref).abs().max() / ref.abs().max()).item()
+    err32 = (((dy.t() @ x).double() - ref).abs().max() / ref.abs().max()).item()
+    assert err < max(5 * err32, 1e-5), (err, err32)
+    assert torch.equal(got, ops.wgrad_tf32x3(dy, x))           # deterministic split-K

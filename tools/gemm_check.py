@@ -45,3 +45,18 @@ for M, N, K in shapes:
     flops = 2.0 * M * N * K
     print(f"M={M} N={N} K={K}: err 3xTF32 {err:.2e} | cuBLAS fp32 {err32:.2e} | cuBLAS tf32 {err19:.2e} || "
           f"ours {t_ours:.3f} ms ({flops/t_ours/1e9:.1f} TFLOP/s, {(M*K+M*N)*4/t_ours/1e6:.0f} GB/s) cuBLAS fp32 {t_cublas:.3f} ms", flush=True)
+
+print("---- weight gradient dW = dY^T X ----")
+for E, Nout, Kout in [(16, 32, 32), (1000, 256, 256), (4099, 32, 32), (3000, 64, 48), (20000, 256, 256), (495592, 256, 256), (495592, 32, 32), (495592, 256, 32)]:
+    dy = torch.randn(E, Nout, device=dev)
+    x = torch.randn(E, Kout, device=dev)
+    ref = dy.double().t() @ x.double()
+    got = ops.wgrad_tf32x3(dy, x)
+    torch.cuda.synchronize()
+    err = ((got.double() - ref).abs().max() / ref.abs().max()).item()
+    c32 = dy.t() @ x
+    err32 = ((c32.double() - ref).abs().max() / ref.abs().max()).item()
+    t_ours = tm(lambda: ops.wgrad_tf32x3(dy, x))
+    t_cublas = tm(lambda: dy.t() @ x)
+    print(f"E={E} Nout={Nout} Kout={Kout}: err 3xTF32 {err:.2e} | cuBLAS fp32 {err32:.2e} || ours {t_ours:.3f} ms "
+          f"({2.0*E*Nout*Kout/t_ours/1e9:.1f} TFLOP/s, {(E*Nout+E*Kout)*4/t_ours/1e6:.0f} GB/s) cuBLAS fp32 {t_cublas:.3f} ms", flush=True)
