@@ -28,6 +28,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CFG2 = dict(name="cfg2", m=300, n=50_000, n_obs=500_000, n_feat_proj=256, num_layers=12, seed=0)
+# BASELINE.json configs[2] (1,000 views x 300k points, ~5M observations) at the shipped width and at d=256
+CFG3 = dict(name="cfg3", m=1000, n=300_000, n_obs=5_000_000, n_feat_proj=32, num_layers=12, seed=0)
+CFG3_WIDE = dict(CFG3, name="cfg3_d256", n_feat_proj=256)
+WORKLOADS = {"cfg2": CFG2, "cfg3": CFG3, "cfg3_d256": CFG3_WIDE}
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
 
 
@@ -138,16 +142,23 @@ def timed_batches(fn, batches=5, per_batch=5, warmup=5):
     return float(np.mean(kept))
 
 
-def kernel_roofline(cfg, peak_gbs, peak_kind):
-    """Edge-attention kernels alone at the workload's shapes (E observations, HC = n_feat_proj):
-    algorithmic bytes / CUDA-event time.  XL (E x HC fp32 = 512 MB at cfg2) exceeds the
-    126 MB L2, so successive launches cannot be served from cache."""
+def kernel_roofline(cfg, peaks, peak_kind):
+    """The hot kernels alone at the workload's shapes (E observations, width d = n_feat_proj), CUDA events.
+
+    Edge-attention kernels: HBM-bound; achieved = algorithmic bytes / time over the
+    measured copy bandwidth.  tcgen05 3xTF32 GEMMs: 3 tf32 MMAs per product, so the binding roof at
+    d = 256 is the tensor pipe: achieved = 3 * 2MNK / time over the tf32 rate, taken as half of the
+    measured dense bf16 rate (tf32 runs at half the bf16 MMA rate); their HBM fraction is listed too.
+    Every E-sized operand (E x 256 fp32 = 507 MB) exceeds the 126 MB L2, so launches are cold.
+    ``calls_per_step`` x time picks the dominant kernel of the step."""
     from gasfm_b200 import ops
     from gasfm_b200.index import ObservationIndex
     from oracle import gasfm_cpu
 
+    peak_gbs = float(peaks["hbm_gbs"])
+    peak_tf32 = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
     dev = torch.device("cuda")
-    H, HC = 4, cfg["n_feat_proj"]
+    H, HC, L = 4, cfg["n_feat_proj"], cfg["num_layers"]
     idx, _ = gasfm_cpu.synthetic_observations(cfg["m"], cfg["n"], cfg["n_obs"], cfg["seed"])
     E = idx.shape[1]
     oi = ObservationIndex(torch.from_numpy(idx).to(dev), cfg["m"], cfg["n"])
@@ -164,16 +175,34 @@ def kernel_roofline(cfg, peak_gbs, peak_kind):
         bwd_ms = timed_batches(lambda: ops.gat_edge_backward_raw(XL, XR, att, out, mx, sm, dO, plan, H))
         fwd_bytes = E * (HC * 4 + 4) + T * (2 * HC * 4 + 8 * H)
         bwd_bytes = E * (2 * HC * 4 + 4) + T * (4 * HC * 4 + 8 * H)
-        res[f"gat_fwd_{name}"] = dict(ms=fwd_ms, bytes=fwd_bytes, gbs=fwd_bytes / fwd_ms / 1e6)
-        res[f"gat_bwd_{name}"] = dict(ms=bwd_ms, bytes=bwd_bytes, gbs=bwd_bytes / bwd_ms / 1e6)
+        res[f"gat_fwd_{name}"] = dict(bound="hbm", ms=fwd_ms, work=fwd_bytes, calls=L + 1)
+        res[f"gat_bwd_{name}"] = dict(bound="hbm", ms=bwd_ms, work=bwd_bytes, calls=L + 1)
+        del XR, out, dO
+    if ops.gemm_tf32x3_supported(E, HC, HC, HC, HC):
+        W = torch.randn(HC, HC, device=dev) / HC ** 0.5
+        hi, lo = ops._split_tf32(W)
+        gemm_ms = timed_batches(lambda: ops.gemm_tf32x3(XL, W))
+        wg_ms = timed_batches(lambda: ops.wgrad_tf32x3(XL, XL))
+        n_gemm = 3 * (L - 1) + 2                      # lin_l x2 + lin_proj per stateful block, lin_l x2 in the final update
+        flops = 3 * 2.0 * E * HC * HC
+        res["gemm_tf32x3 (fwd + dX)"] = dict(bound="tensor", ms=gemm_ms, work=flops, calls=2 * n_gemm, hbm_bytes=2 * E * HC * 4)
+        res["wgrad_tf32x3 (dW)"] = dict(bound="tensor", ms=wg_ms, work=flops, calls=n_gemm, hbm_bytes=2 * E * HC * 4)
     for v in res.values():
-        v["frac"] = v["gbs"] / peak_gbs
-    dom = max(res, key=lambda k: res[k]["ms"])
-    roof = {"bound": "hbm", "kernel": dom, "achieved": round(res[dom]["gbs"], 1), "peak": peak_gbs,
-            "peak_source": peak_kind, "unit": "GB/s", "frac": round(res[dom]["frac"], 4), "traffic": None,
-            "algorithmic_bytes_per_launch": res[dom]["bytes"],
-            "all_kernels": {k: {"ms": round(v["ms"], 4), "GB/s": round(v["gbs"], 1), "frac": round(v["frac"], 4)}
-                            for k, v in res.items()}}
+        if v["bound"] == "hbm":
+            v["achieved"], v["peak"], v["unit"] = v["work"] / v["ms"] / 1e6, peak_gbs, "GB/s"
+        else:
+            v["achieved"], v["peak"], v["unit"] = v["work"] / v["ms"] / 1e9, peak_tf32, "TFLOP/s"
+            v["hbm_frac"] = round(v["hbm_bytes"] / v["ms"] / 1e6 / peak_gbs, 4)
+        v["frac"] = v["achieved"] / v["peak"]
+    dom = max(res, key=lambda k: res[k]["ms"] * res[k]["calls"])
+    d = res[dom]
+    roof = {"bound": d["bound"], "kernel": dom, "achieved": round(d["achieved"], 1), "peak": round(d["peak"], 1),
+            "peak_source": peak_kind + (" (hbm_gbs)" if d["bound"] == "hbm" else " (bf16_tflops / 2 = tf32 MMA rate)"),
+            "unit": d["unit"], "frac": round(d["frac"], 4), "traffic": None,
+            "algorithmic_work_per_launch": d["work"], "ms_per_launch": round(d["ms"], 4),
+            "all_kernels": {k: {"bound": v["bound"], "ms": round(v["ms"], 4), "calls_per_step": v["calls"],
+                                "achieved": round(v["achieved"], 1), "unit": v["unit"], "frac": round(v["frac"], 4),
+                                **({"hbm_frac": v["hbm_frac"]} if "hbm_frac" in v else {})} for k, v in res.items()}}
     return roof
 
 
@@ -234,7 +263,7 @@ def workload_config(cfg, E, n_gpus):
     return {"workload": f"{cfg['name']}: GASFM fwd+bwd, {cfg['m']} views x {cfg['n']} points, E={E} observations, "
                         f"n_feat_proj={cfg['n_feat_proj']}, 4 heads, {cfg['num_layers']} layers, shipped other widths",
             "edge_level_gats_per_step": 2 * (cfg["num_layers"] + 1),
-            "cache": "inputs larger than L2 (one [E,256] fp32 tensor = 512 MB > 126 MB L2)",
+            "cache": f"inputs larger than L2 (one [E,{cfg['n_feat_proj']}] fp32 tensor = {E * cfg['n_feat_proj'] * 4 / 1e6:.0f} MB vs 126 MB L2)",
             "parallelism": "single GPU" if n_gpus == 1 else f"tracks sharded over {n_gpus} GPUs"}
 
 
@@ -245,6 +274,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
+                    help="default cfg2 = the configuration the headline metric is quoted on")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = one scene of N x the workload's tracks; strong = the workload's scene itself")
+    ap.add_argument("--no-roofline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -258,9 +292,10 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         from gasfm_b200 import dist as gdist
-        return gdist.bench_main(args, CFG2, workload_config, ClockSampler, measured_peaks, timed, surrogate_loss)
+        return gdist.bench_main(args, WORKLOADS[args.workload], workload_config, ClockSampler, measured_peaks, timed,
+                                surrogate_loss)
     dev = torch.device("cuda", local_rank)
-    cfg = dict(CFG2)
+    cfg = dict(WORKLOADS[args.workload])
     peaks, peak_kind = measured_peaks()
 
     conf, model, scene_host = build_workload(cfg)
@@ -306,7 +341,7 @@ def main():
     d2h = d2h_holder["Ps"].numel() * 4 + d2h_holder["pts"].numel() * 4 + 4
     e2e_value = E * n_gat / (e2e_ms / 1e3)
 
-    roofline = kernel_roofline(cfg, float(peaks["hbm_gbs"]), peak_kind)
+    roofline = None if args.no_roofline else kernel_roofline(cfg, peaks, peak_kind)
     line = {"metric": "gat_layer_edges_per_sec_fwd_bwd", "value": value, "unit": "edges/s", "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -1,0 +1,267 @@
+// Small dense helpers on the SIMT pipes (sm_100a), for shapes where a 128-wide tensor-core tile would be
+// mostly padding:
+//   wgrad_small   dW[Nout,Kout] = dY[E,Nout]^T X[E,Kout] for Nout, Kout in {32, 64} (the shipped d = 32 widths)
+//   x0_bwd        the rank-d0 (d0 <= 4) part of the observation update's backward:
+//                 dx0[E,d0] = scale * dOut[E,W] W0[W,d0],  dW0[W,d0] = scale * dOut^T x0
+// Both are single passes over E-sized inputs (HBM-bound) with fp32 round-to-nearest accumulation and a
+// deterministic two-stage reduction (per-CTA partials -> column sum).
+#include "common.cuh"
+#include "../../include/gasfm_b200.h"
+
+namespace gasfm {
+
+constexpr int kWsBlocks = kNumSMs * 2;
+constexpr int kWsWarps = 8;
+
+// One warp owns a [Nout x Kout] accumulator: lane l holds rows l, l+32 (RPL = Nout/32) x all Kout columns.
+// Rows are streamed through a per-warp shared tile; x values are read back as broadcast float4.
+template <int NOUT, int KOUT>
+__global__ void __launch_bounds__(kWsWarps * 32) wgrad_small_kernel(const float* __restrict__ dY, int64_t lddy,
+                                                                    const float* __restrict__ X, int64_t ldx, int64_t E,
+                                                                    float* __restrict__ ws) {
+  constexpr int RPL = NOUT / 32;
+  constexpr int TR = 8;                                    // rows per tile
+  // one static buffer: per-warp row tiles during the main loop, the CTA accumulator afterwards
+  __shared__ __align__(16) float s_buf[kWsWarps * TR * (NOUT + KOUT)];
+  static_assert(kWsWarps * TR * (NOUT + KOUT) >= NOUT * KOUT, "accumulator must fit in the tile buffer");
+  float (*s_dy)[TR][NOUT] = reinterpret_cast<float (*)[TR][NOUT]>(s_buf);
+  float (*s_x)[TR][KOUT] = reinterpret_cast<float (*)[TR][KOUT]>(s_buf + kWsWarps * TR * NOUT);
+  float* s_acc = s_buf;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float acc[RPL][KOUT];
+#pragma unroll
+  for (int r = 0; r < RPL; ++r)
+#pragma unroll
+    for (int k = 0; k < KOUT; ++k) acc[r][k] = 0.f;
+  const int64_t n_tiles = (E + TR - 1) / TR;
+  const int64_t warp = (int64_t)blockIdx.x * kWsWarps + wid, n_warps = (int64_t)gridDim.x * kWsWarps;
+  for (int64_t t = warp; t < n_tiles; t += n_warps) {
+    const int64_t e0 = t * TR;
+    // cooperative, coalesced tile load (float4 per lane)
+#pragma unroll
+    for (int i = lane; i < TR * NOUT / 4; i += 32) {
+      const int r = i / (NOUT / 4), c = (i % (NOUT / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e0 + r < E) v = ld_stream4(dY + (e0 + r) * lddy + c);
+      *reinterpret_cast<float4*>(&s_dy[wid][r][c]) = v;
+    }
+#pragma unroll
+    for (int i = lane; i < TR * KOUT / 4; i += 32) {
+      const int r = i / (KOUT / 4), c = (i % (KOUT / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e0 + r < E) v = ld_stream4(X + (e0 + r) * ldx + c);
+      *reinterpret_cast<float4*>(&s_x[wid][r][c]) = v;
+    }
+    __syncwarp();
+#pragma unroll 4
+    for (int r = 0; r < TR; ++r) {
+      float d[RPL];
+#pragma unroll
+      for (int q = 0; q < RPL; ++q) d[q] = s_dy[wid][r][lane + 32 * q];
+#pragma unroll
+      for (int k = 0; k < KOUT; k += 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(&s_x[wid][r][k]);   // same address in all lanes: broadcast
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) {
+          acc[q][k] = fmaf(d[q], xv.x, acc[q][k]);
+          acc[q][k + 1] = fmaf(d[q], xv.y, acc[q][k + 1]);
+          acc[q][k + 2] = fmaf(d[q], xv.z, acc[q][k + 2]);
+          acc[q][k + 3] = fmaf(d[q], xv.w, acc[q][k + 3]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // deterministic CTA reduction: warps add their accumulators one after the other
+  __syncthreads();                                         // every warp is done with its tiles: reuse the buffer
+  for (int j = threadIdx.x; j < NOUT * KOUT; j += blockDim.x) s_acc[j] = 0.f;
+  __syncthreads();
+  for (int w = 0; w < kWsWarps; ++w) {
+    if (wid == w) {
+#pragma unroll
+      for (int q = 0; q < RPL; ++q)
+#pragma unroll
+        for (int k = 0; k < KOUT; ++k) s_acc[(lane + 32 * q) * KOUT + k] += acc[q][k];
+    }
+    __syncthreads();
+  }
+  for (int j = threadIdx.x; j < NOUT * KOUT; j += blockDim.x) ws[(int64_t)blockIdx.x * NOUT * KOUT + j] = s_acc[j];
+}
+
+__global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restrict__ ws, int rows, int64_t width, float scale,
+                                                          float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= width) return;
+  float a = 0.f;
+  for (int r = 0; r < rows; ++r) a += ws[(int64_t)r * width + i];
+  out[i] = a * scale;
+}
+
+// ---- x0 backward ------------------------------------------------------------------------------------
+constexpr int kX0Threads = 256;
+template <int LPR, int NV>
+__global__ void __launch_bounds__(kX0Threads) x0_bwd_kernel(const float* __restrict__ dOut, int64_t E, int width,
+                                                            const float* __restrict__ x0, const float* __restrict__ W0, int d0,
+                                                            float scale, float* __restrict__ dx0, float* __restrict__ ws) {
+  constexpr int RPW = 32 / LPR;
+  constexpr int NW = kX0Threads / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lir = lane % LPR, grp = lane / LPR;
+  const unsigned mask = group_mask<LPR>(lane);
+  const int nvec = width / 4;
+  // W0 rows of this lane's channels, and the dW0 accumulators: [NV][4 channels][4 (d0 <= 4)]
+  float w[NV][4][4], dw[NV][4][4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = 4 * (lir + LPR * v) + k;
+        w[v][k][q] = (lir + LPR * v < nvec && q < d0) ? W0[(int64_t)c * d0 + q] : 0.f;
+        dw[v][k][q] = 0.f;
+      }
+  const int64_t stride = (int64_t)gridDim.x * NW * RPW;
+  for (int64_t row = ((int64_t)blockIdx.x * NW + wid) * RPW + grp; row < E; row += stride) {
+    float xr[4], s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) xr[q] = q < d0 ? __ldg(x0 + row * d0 + q) : 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (lir + LPR * v < nvec) {
+        const float4 g = ld_stream4(dOut + row * width + 4 * (lir + LPR * v));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float gk = comp(g, k);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            s[q] = fmaf(gk, w[v][k][q], s[q]);
+            dw[v][k][q] = fmaf(gk, xr[q], dw[v][k][q]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int off = LPR / 2; off > 0; off >>= 1) s[q] += __shfl_xor_sync(mask, s[q], off);
+    }
+    if (lir == 0) {
+      for (int q = 0; q < d0; ++q) dx0[row * d0 + q] = scale * s[q];
+    }
+  }
+  // dW0: groups -> warp -> CTA -> workspace row [width * 4]
+  __syncwarp();
+  if (RPW > 1) {
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dw[v][k][q] += __shfl_xor_sync(0xffffffffu, dw[v][k][q], off);
+  }
+  extern __shared__ float sm[];   // [NW][width*4]
+  const int W4 = width * 4;
+  if (grp == 0) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      if (lir + LPR * v < nvec) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sm[wid * W4 + (4 * (lir + LPR * v) + k) * 4 + q] = dw[v][k][q];
+      }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < W4; j += kX0Threads) {
+    float a = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < NW; ++ww) a += sm[ww * W4 + j];
+    ws[(int64_t)blockIdx.x * W4 + j] = a;
+  }
+}
+
+// dW0[c, q] = scale * sum_blocks ws[b][c*4 + q]
+__global__ void x0_bwd_reduce_kernel(const float* __restrict__ ws, int rows, int width, int d0, float scale, float* __restrict__ dW0) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= width * d0) return;
+  const int c = j / d0, q = j % d0;
+  float a = 0.f;
+  for (int r = 0; r < rows; ++r) a += ws[(int64_t)r * width * 4 + c * 4 + q];
+  dW0[j] = a * scale;
+}
+
+static int x0_blocks(int64_t E) {
+  int64_t need = (E + 63) / 64;
+  int64_t cap = (int64_t)kNumSMs * 4;
+  return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+}  // namespace gasfm
+
+using namespace gasfm;
+
+extern "C" int gasfm_wgrad_small_supported(int Nout, int Kout, int64_t lddy, int64_t ldx) {
+  return ((Nout == 32 || Nout == 64) && (Kout == 32 || Kout == 64) && lddy % 4 == 0 && ldx % 4 == 0) ? 1 : 0;
+}
+extern "C" size_t gasfm_wgrad_small_ws_bytes(int Nout, int Kout) { return (size_t)kWsBlocks * Nout * Kout * sizeof(float); }
+
+extern "C" int gasfm_wgrad_small(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t E, int Nout, int Kout,
+                                 float* dW, void* ws, void* stream) {
+  GASFM_REQUIRE(gasfm_wgrad_small_supported(Nout, Kout, lddy, ldx), "wgrad_small: unsupported shape %d x %d", Nout, Kout);
+  GASFM_REQUIRE(ws && ((uintptr_t)dY | (uintptr_t)X) % 16 == 0, "wgrad_small: bad pointers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t tiles = (E + 7) / 8;
+  int blocks = (int)((tiles + kWsWarps - 1) / kWsWarps);
+  if (blocks > kWsBlocks) blocks = kWsBlocks;
+  if (blocks < 1) blocks = 1;
+  float* w = (float*)ws;
+  if (Nout == 32 && Kout == 32) wgrad_small_kernel<32, 32><<<blocks, kWsWarps * 32, 0, st>>>(dY, lddy, X, ldx, E, w);
+  else if (Nout == 32 && Kout == 64) wgrad_small_kernel<32, 64><<<blocks, kWsWarps * 32, 0, st>>>(dY, lddy, X, ldx, E, w);
+  else if (Nout == 64 && Kout == 32) wgrad_small_kernel<64, 32><<<blocks, kWsWarps * 32, 0, st>>>(dY, lddy, X, ldx, E, w);
+  else wgrad_small_kernel<64, 64><<<blocks, kWsWarps * 32, 0, st>>>(dY, lddy, X, ldx, E, w);
+  int rc = check_launch("wgrad_small");
+  if (rc) return rc;
+  const int64_t width = (int64_t)Nout * Kout;
+  partial_sum_kernel<<<ceil_div(width, 256), 256, 0, st>>>(w, blocks, width, 1.f, dW);
+  return check_launch("wgrad_small(reduce)");
+}
+
+extern "C" size_t gasfm_x0_bwd_ws_bytes(int64_t E, int width) { return (size_t)x0_blocks(E) * width * 4 * sizeof(float); }
+
+extern "C" int gasfm_x0_bwd(const float* dOut, int64_t E, int width, const float* x0, const float* W0, int d0, float scale,
+                            float* dx0, float* dW0, void* ws, void* stream) {
+  GASFM_REQUIRE(width > 0 && width % 4 == 0 && width <= 1024, "x0_bwd: width %d must be a multiple of 4 and <= 1024", width);
+  GASFM_REQUIRE(d0 >= 1 && d0 <= 4, "x0_bwd: d0 = %d not in 1..4", d0);
+  GASFM_REQUIRE(ws && (uintptr_t)dOut % 16 == 0, "x0_bwd: bad pointers");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (E <= 0) {
+    cudaMemsetAsync(dW0, 0, (size_t)width * d0 * sizeof(float), st);
+    return check_launch("x0_bwd(empty)");
+  }
+  const int blocks = x0_blocks(E);
+  const size_t smem = (size_t)(kX0Threads / 32) * width * 4 * sizeof(float);
+  const int nvec = width / 4;
+#define CALL_X0(VEC, LPR, NV)                                                                                    \
+  do {                                                                                                           \
+    if (smem > 48 * 1024)                                                                                        \
+      cudaFuncSetAttribute(x0_bwd_kernel<LPR, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    x0_bwd_kernel<LPR, NV><<<blocks, kX0Threads, smem, st>>>(dOut, E, width, x0, W0, d0, scale, dx0, (float*)ws); \
+  } while (0)
+  if (nvec <= 1) CALL_X0(4, 1, 1);
+  else if (nvec <= 2) CALL_X0(4, 2, 1);
+  else if (nvec <= 4) CALL_X0(4, 4, 1);
+  else if (nvec <= 8) CALL_X0(4, 8, 1);
+  else if (nvec <= 16) CALL_X0(4, 16, 1);
+  else if (nvec <= 32) CALL_X0(4, 32, 1);
+  else if (nvec <= 64) CALL_X0(4, 32, 2);
+  else if (nvec <= 128) CALL_X0(4, 32, 4);
+  else CALL_X0(4, 32, 8);
+#undef CALL_X0
+  int rc = check_launch("x0_bwd");
+  if (rc) return rc;
+  x0_bwd_reduce_kernel<<<ceil_div((int64_t)width * d0, 256), 256, 0, st>>>((const float*)ws, blocks, width, d0, scale, dW0);
+  return check_launch("x0_bwd(reduce)");
+}

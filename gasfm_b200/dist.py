@@ -201,7 +201,8 @@ def bench_main(args, cfg, workload_config, ClockSampler, measured_peaks, timed, 
     dev = torch.device("cuda", local_rank)
     dist.init_process_group("nccl", device_id=dev)
     cfg = dict(cfg)
-    n_total, obs_total = cfg["n"] * world, cfg["n_obs"] * world
+    weak = getattr(args, "scaling", "weak") == "weak"
+    n_total, obs_total = (cfg["n"] * world, cfg["n_obs"] * world) if weak else (cfg["n"], cfg["n_obs"])
     idx, vals = gasfm_cpu.synthetic_observations(cfg["m"], n_total, obs_total, cfg["seed"])
     E_total = idx.shape[1]
     scene_host = shard_scene(idx, vals, cfg["m"], n_total, rank, world).pin_memory()
@@ -241,13 +242,13 @@ def bench_main(args, cfg, workload_config, ClockSampler, measured_peaks, timed, 
     dist.all_reduce(d2h)
     if rank == 0:
         wc = workload_config(cfg, E_total, world)
-        wc["workload"] = (f"{cfg['name']} per GPU, weak scaling: ONE scene of {cfg['m']} views x {n_total} points, "
+        wc["workload"] = (f"{cfg['name']}{' per GPU, weak scaling' if weak else ', strong scaling'}: ONE scene of {cfg['m']} views x {n_total} points, "
                           f"E={E_total} observations, tracks sharded over {world} GPUs (per-view softmax statistics "
                           f"merged by NCCL all-reduce), n_feat_proj={cfg['n_feat_proj']}, 4 heads, {cfg['num_layers']} layers")
         line = {"metric": "gat_layer_edges_per_sec_fwd_bwd", "value": E_total * n_gat / (ms / 1e3), "unit": "edges/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": wc,
+                "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": wc,
                 "e2e": {"value": E_total * n_gat / (e2e_ms / 1e3), "unit": "edges/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h.item())},
                 "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches), "clocks": clocks,

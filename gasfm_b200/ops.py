@@ -276,10 +276,18 @@ class _EdgeUpdate(torch.autograd.Function):
             dV = seg_sum_raw(d_out, index.by_view, scale)
         dg = dV.sum(dim=0, keepdim=True) if (has_g and ctx.needs_input_grad[5]) else None
         dx0 = dW0 = None
-        if x0 is not None:
-            if ctx.needs_input_grad[1]:
+        if x0 is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
+            E, w = d_out.shape
+            d0 = x0.shape[1]
+            if w % 4 == 0 and w <= 1024 and 1 <= d0 <= 4:
+                dx0 = torch.empty((E, d0), dtype=torch.float32, device=d_out.device)
+                dW0 = torch.empty((w, d0), dtype=torch.float32, device=d_out.device)
+                ws = torch.empty(max(1, _lib.size_query("gasfm_x0_bwd_ws_bytes", E, w) // 4), dtype=torch.float32, device=d_out.device)
+                with torch.cuda.device(d_out.device):
+                    _lib.call("gasfm_x0_bwd", _lib.ptr(d_out), E, w, _lib.ptr(x0), _lib.ptr(W0), d0, float(scale),
+                              _lib.ptr(dx0), _lib.ptr(dW0), _lib.ptr(ws), _lib.stream_ptr())
+            else:
                 dx0 = torch.mm(d_out, W0).mul_(scale)
-            if ctx.needs_input_grad[2]:
                 dW0 = torch.mm(d_out.t(), x0).mul_(scale)
         return (dP, dx0, dW0, dS, dV if has_V else None, dg, d_out if has_skip else None, None, None, None)
 
@@ -321,12 +329,19 @@ def wgrad_tf32x3_supported(E, n_out, k_out, lddy, ldx):
 
 
 def wgrad_tf32x3(dy, x):
-    """dW[Nout,Kout] = dy[E,Nout]^T @ x[E,Kout] on the tensor cores (3xTF32, deterministic split-K)."""
+    """dW[Nout,Kout] = dy[E,Nout]^T @ x[E,Kout]: tensor cores (3xTF32, deterministic split-K), or the SIMT
+    register-tiled kernel for the narrow shipped widths (32 / 64)."""
     dy, lddy = _rows(dy)
     x, ldx = _rows(x)
     E, n_out = dy.shape
     k_out = x.shape[1]
     dw = torch.empty((n_out, k_out), dtype=torch.float32, device=dy.device)
+    if _lib.load().gasfm_wgrad_small_supported(n_out, k_out, lddy, ldx):
+        ws = torch.empty(_lib.size_query("gasfm_wgrad_small_ws_bytes", n_out, k_out) // 4, dtype=torch.float32, device=dy.device)
+        with torch.cuda.device(dy.device):
+            _lib.call("gasfm_wgrad_small", _lib.ptr(dy), lddy, _lib.ptr(x), ldx, E, n_out, k_out, _lib.ptr(dw), _lib.ptr(ws),
+                      _lib.stream_ptr())
+        return dw
     ws = torch.empty(_lib.size_query("gasfm_wgrad_tf32x3_ws_bytes", n_out, k_out) // 4, dtype=torch.float32, device=dy.device)
     with torch.cuda.device(dy.device):
         _lib.call("gasfm_wgrad_tf32x3", _lib.ptr(dy), lddy, _lib.ptr(x), ldx, E, n_out, k_out, _lib.ptr(dw), _lib.ptr(ws),

@@ -187,6 +187,20 @@ GASFM_API size_t gasfm_wgrad_tf32x3_ws_bytes(int Nout, int Kout);
 GASFM_API int gasfm_wgrad_tf32x3(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t E,
                                  int Nout, int Kout, float* dW, void* ws, void* stream);
 
+/* The same weight gradient for the narrow shipped widths (Nout, Kout in {32, 64}) on the SIMT pipes, where a
+ * 128-wide tensor-core tile would be mostly padding; fp32 round-to-nearest accumulation, deterministic. */
+GASFM_API int gasfm_wgrad_small_supported(int Nout, int Kout, int64_t lddy, int64_t ldx);
+GASFM_API size_t gasfm_wgrad_small_ws_bytes(int Nout, int Kout);
+GASFM_API int gasfm_wgrad_small(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t E, int Nout,
+                                int Kout, float* dW, void* ws, void* stream);
+
+/* Backward of the rank-d0 term of gasfm_edge_update_fwd in one pass over dOut[E,width]:
+ *   dx0[E,d0] = scale * dOut W0,   dW0[width,d0] = scale * dOut^T x0        (d0 <= 4)
+ * (the cat(x, x0) half of lin_proj, models/layers.py:245-251, 941). */
+GASFM_API size_t gasfm_x0_bwd_ws_bytes(int64_t E, int width);
+GASFM_API int gasfm_x0_bwd(const float* dOut, int64_t E, int width, const float* x0, const float* W0, int d0,
+                           float scale, float* dx0, float* dW0, void* ws, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (inputs and outputs in HOST memory; allocation and the
  * host<->device copies happen inside the call).  These are what a non-torch host binds.

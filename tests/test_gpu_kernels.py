@@ -406,3 +406,41 @@ def test_wgrad_tf32x3_has_fp32_accuracy(E, Nout, Kout):
     err32 = (((dy.t() @ x).double() - ref).abs().max() / ref.abs().max()).item()
     assert err < max(5 * err32, 1e-5), (err, err32)
     assert torch.equal(got, ops.wgrad_tf32x3(dy, x))           # deterministic split-K
+
+
+@pytest.mark.parametrize("E,Nout,Kout", [(5, 32, 32), (4099, 32, 32), (30000, 64, 32), (30001, 32, 64), (9000, 64, 64)])
+def test_wgrad_small_widths(E, Nout, Kout):
+    """shipped widths (32 / 64): SIMT register-tiled dW, plain fp32 accuracy, deterministic"""
+    torch.manual_seed(E)
+    wide = torch.randn(E, Nout + 8, device=DEV)
+    dy, x = wide[:, 4:4 + Nout], torch.randn(E, Kout, device=DEV)      # strided dY rows
+    assert _lib.load().gasfm_wgrad_small_supported(Nout, Kout, Nout + 8, Kout)
+    got = ops.wgrad_tf32x3(dy, x)
+    ref = dy.double().t() @ x.double()
+    assert rel_err(got, ref.cpu().numpy()) < 2e-6
+    assert torch.equal(got, ops.wgrad_tf32x3(dy, x))
+
+
+def test_full_size_edge_kernels_cfg3():
+    """BASELINE.json configs[2] size (1000 views x 300k tracks, ~5M observations) at the shipped width:
+    size-independent properties of the edge kernels at full size."""
+    m, n, H, C = 1000, 300000, 4, 8
+    idx_np, _ = gasfm_cpu.synthetic_observations(m, n, 5_000_000, seed=0)
+    E = idx_np.shape[1]
+    oi = ObservationIndex(torch.from_numpy(idx_np).to(DEV), m, n)
+    torch.manual_seed(0)
+    XL = torch.randn(E, H * C, device=DEV)
+    att = torch.randn(1, H, C, device=DEV) * 0.3
+    for plan, T in ((oi.by_view, m), (oi.by_track, n)):
+        XR = torch.randn(T, H * C, device=DEV)
+        const = torch.arange(H * C, device=DEV, dtype=torch.float32).repeat(E, 1) * 0.1
+        out = ops.gat_edge_attention(const, XR, att, None, plan, H)
+        assert torch.allclose(out, const[:1].expand(T, -1), atol=2e-5, rtol=1e-5)     # weights sum to one
+        xl, xr = XL.clone().requires_grad_(True), XR.clone().requires_grad_(True)
+        o = ops.gat_edge_attention(xl, xr, att, None, plan, H)
+        o.sum().backward()
+        # with dOut = 1:  sum over a segment of dXL = sum_e alpha_e + sum_e dz_e = 1 + dXR[t]
+        seg_tot = ops.seg_sum_raw(xl.grad, plan)
+        nonempty = (plan.seg_ptr[1:] > plan.seg_ptr[:-1]).unsqueeze(1)
+        assert torch.allclose(seg_tot, torch.where(nonempty, 1.0 + xr.grad, torch.zeros_like(seg_tot)), atol=5e-4)
+    assert torch.equal(oi.csc_perm.long(), torch.argsort(torch.from_numpy(idx_np[1]).to(DEV), stable=True))

@@ -11,4 +11,4 @@ cfg = dict(bench.CFG2)
 if len(sys.argv) >= 5:
     cfg.update(m=int(sys.argv[1]), n=int(sys.argv[2]), n_obs=int(sys.argv[3]), n_feat_proj=int(sys.argv[4]))
 peaks, kind = bench.measured_peaks()
-print(json.dumps(bench.kernel_roofline(cfg, float(peaks["hbm_gbs"]), kind)))
+print(json.dumps(bench.kernel_roofline(cfg, peaks, kind)))

@@ -1,5 +1,5 @@
 """Kernel-time breakdown of one GASFM fwd+bwd step (torch.profiler, CUDA activity).
-Usage: python tools/profile_step.py [n_feat_proj] [num_layers] > gpurun_out/step_profile.txt"""
+Usage: python tools/profile_step.py [cfg2|cfg3|cfg3_d256] [num_layers] > gpurun_out/step_profile.txt"""
 import os
 import sys
 
@@ -8,9 +8,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 
-cfg = dict(bench.CFG2)
-if len(sys.argv) > 1:
-    cfg["n_feat_proj"] = int(sys.argv[1])
+cfg = dict(bench.WORKLOADS[sys.argv[1]] if len(sys.argv) > 1 else bench.CFG2)
 if len(sys.argv) > 2:
     cfg["num_layers"] = int(sys.argv[2])
 conf, model, scene = bench.build_workload(cfg)
