@@ -49,6 +49,9 @@ SIGNATURES = {
     "gasfm_wgrad_small": (_I, [_P, _L, _P, _L, _L, _I, _I, _P, _P, _P]),
     "gasfm_x0_bwd_ws_bytes": (_SZ, [_L, _I]),
     "gasfm_x0_bwd": (_I, [_P, _L, _I, _P, _P, _I, _F, _P, _P, _P, _P]),
+    "gasfm_esfm_loss_ws_bytes": (_SZ, [_L]),
+    "gasfm_esfm_loss_fwd": (_I, [_P, _P, _L, _P, _P, _P, _L, _F, _I, _F, _P, _P, _P]),
+    "gasfm_esfm_loss_bwd": (_I, [_P, _P, _L, _P, _P, _P, _L, _F, _I, _F, _P, _P, _I, _P, _P]),
     "gasfm_csr_build_host": (_I, [_P, _L, _I, _I, _P, _P, _P]),
     "gasfm_gat_edge_fwd_host": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P]),
 }

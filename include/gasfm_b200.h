@@ -202,6 +202,23 @@ GASFM_API int gasfm_x0_bwd(const float* dOut, int64_t E, int width, const float*
                            float scale, float* dx0, float* dW0, void* ws, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Sparse ESFM reprojection loss over the E observed (view, point) pairs (ESFMLoss.forward,
+ * loss_functions.py:85-123, without the dense [m,3,n] tensors).  Ps[m,3,4], pts3D[4,n] (row-major), obs[E,2]
+ * = SparseMat.values (normalised measurements).  out[0] = loss, out[1] = #observations with a valid depth.
+ * Backward: G[E,16] = per-observation contributions (cols 0-11 -> dPs[row], 12-15 -> dpts3D[:,col]) after the
+ * reference's gradient hook (grad_mode 0 none, 1 = normalise where depth valid / #valid, 2 = normalise all / E);
+ * ``upstream`` and ``stats`` (= out of the forward) are DEVICE scalars, so nothing synchronises.
+ * ------------------------------------------------------------------------------------- */
+GASFM_API size_t gasfm_esfm_loss_ws_bytes(int64_t E);
+GASFM_API int gasfm_esfm_loss_fwd(const float* Ps, const float* pts3D, int64_t n, const float* obs,
+                                  const int32_t* row_idx, const int32_t* col_idx, int64_t E, float margin,
+                                  int hinge, float hinge_weight, float* out, void* ws, void* stream);
+GASFM_API int gasfm_esfm_loss_bwd(const float* Ps, const float* pts3D, int64_t n, const float* obs,
+                                  const int32_t* row_idx, const int32_t* col_idx, int64_t E, float margin,
+                                  int hinge, float hinge_weight, const float* upstream, const float* stats,
+                                  int grad_mode, float* G, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (inputs and outputs in HOST memory; allocation and the
  * host<->device copies happen inside the call).  These are what a non-torch host binds.
  * ------------------------------------------------------------------------------------- */

@@ -378,6 +378,73 @@ def _nan_to_zero_mean(values, indices, shape, dim):
 
 
 # ----------------------------------------------------------------------------------------
+# f1: ESFM reprojection loss, dense like the reference (loss_functions.py:69-123)
+# ----------------------------------------------------------------------------------------
+def esfm_loss(Ps, pts3D, indices, values, m, n, margin=1e-4, hinge_loss=True, hinge_loss_weight=1.0,
+              grad_equalization=True, normalize_valid_only=True):
+    """ESFMLoss.forward on dense [m,3,n] tensors, including the gradient hook on ``Ps @ pts3D``
+    (loss_functions.py:101-110).  ``indices/values``: the scene's observations (normalised)."""
+    valid = torch.zeros(m, n, dtype=torch.bool)
+    valid[indices[0], indices[1]] = True
+    norm_M = torch.zeros(m, 2, n, dtype=Ps.dtype)
+    norm_M[indices[0], :, indices[1]] = values.to(Ps.dtype)
+    pts_2d = Ps @ pts3D
+    z = pts_2d[:, 2, :]
+    ok = (z >= margin) if hinge_loss else (z.abs() >= margin)           # geo_utils.py:721-726
+    if not hinge_loss:
+        hinge_loss_weight = 0
+    if grad_equalization and pts_2d.requires_grad:
+        if normalize_valid_only:
+            count = max(1, int((valid & ok).sum()))
+            pts_2d.register_hook(lambda g: torch.where(ok[:, None, :].expand(-1, 3, -1), F.normalize(g, dim=1) / count, g))
+        else:
+            pts_2d.register_hook(lambda g: F.normalize(g, dim=1) / valid.sum())
+    hinge = (margin - z) * hinge_loss_weight
+    proj = pts_2d / torch.where(ok, z, torch.ones_like(z)).unsqueeze(1)
+    err = (proj[:, 0:2, :] - norm_M).norm(dim=1)
+    return torch.where(ok, err, hinge)[valid].mean()
+
+
+# ----------------------------------------------------------------------------------------
+# f4: DPESFM SetOfSetNet (models/SetOfSet.py) on the set-of-set layer above
+# ----------------------------------------------------------------------------------------
+def set_of_set_forward(params, scene, block_size, proj_feat_normalization, add_skipconn):
+    """SetOfSetNet.forward (models/SetOfSet.py:102-142) for calibrated / quaternion outputs."""
+    p = _P(params)
+    x = scene["x"]["values"].to(next(iter(params.values())).dtype)
+    idx, shape = scene["x"]["indices"], scene["x"]["shape"]
+
+    def normalize(v):                                                    # layers.py:977 (no norm layer)
+        return v - v.mean(dim=0, keepdim=True)
+
+    b = 0
+    while p.has(f"equivariant_blocks.{b}.layers.0.projection_feature_update.lin_proj.weight"):
+        pb = p.sub(f"equivariant_blocks.{b}")
+        xl = x
+        for i in range(block_size):
+            xl = set_of_set_layer(pb.sub(f"layers.{i}"), xl, idx, shape)
+            if i < block_size - 1:
+                if proj_feat_normalization:
+                    xl = normalize(xl)
+                xl = F.relu(xl)
+        if add_skipconn:
+            skip = x
+            if pb.has("skip_projection.lin_proj.weight"):
+                skip = _linear(pb, "skip_projection.lin_proj", skip)
+                if proj_feat_normalization:
+                    skip = normalize(skip)
+            xl = skip + xl
+        x = F.relu(xl)
+        b += 1
+    pg = p.sub("final_global_update")
+    n_in = _linear(pg, "lin_scenepoint", _nan_to_zero_mean(x, idx, shape, 0))
+    m_in = _linear(pg, "lin_view", _nan_to_zero_mean(x, idx, shape, 1))
+    m_out = _mlp(p, "view_head", F.relu(m_in))
+    n_out = _mlp(p, "scenepoint_head", F.relu(n_in)).T
+    return {"Ps_norm": decode_views(m_out), "pts3D": torch.cat((n_out, n_out.new_ones(1, n_out.shape[1])), dim=0)}
+
+
+# ----------------------------------------------------------------------------------------
 # synthetic scenes (SURVEY.md section 8d) -- sparse-first, never builds the dense M
 # ----------------------------------------------------------------------------------------
 def synthetic_observations(m, n, n_obs, seed, banded=True):

@@ -187,9 +187,100 @@ def main():
         fix.update({f"param.{k}": v for k, v in sd.items()})
         fix["conf_json"] = np.array(__import__("json").dumps(conf_d))
         np.savez_compressed(os.path.join(HERE, f"model_{name}.npz"), **to_np(fix))
+    make_loss_and_dpesfm(ref)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+LOSS_VARIANTS = {
+    "shipped": dict(hinge_loss=True, hinge_loss_weight=1, pts_grad_equalization_pre_perspective_divide=True,
+                    normalize_grad_wrt_valid_projections_only=True),
+    "no_equalization": dict(hinge_loss=True, hinge_loss_weight=0.5, pts_grad_equalization_pre_perspective_divide=False,
+                            normalize_grad_wrt_valid_projections_only=False),
+    "normalize_all": dict(hinge_loss=True, hinge_loss_weight=1, pts_grad_equalization_pre_perspective_divide=True,
+                          normalize_grad_wrt_valid_projections_only=False),
+    "no_hinge": dict(hinge_loss=False, hinge_loss_weight=1, pts_grad_equalization_pre_perspective_divide=True,
+                     normalize_grad_wrt_valid_projections_only=True),
+}
+
+
+class _FakeCuda(torch.Tensor):
+    """ESFMLoss asserts ``data.valid_pts.is_cuda`` (loss_functions.py:122); the fixtures are made on CPU."""
+    @property
+    def is_cuda(self):
+        return True
+
+
+def make_loss_and_dpesfm(ref):
+    import importlib
+    lf = importlib.import_module("loss_functions")
+    # ---- ESFMLoss: value and gradients for four hook / hinge settings --------------------------------
+    m, n = 9, 70
+    M, Ns = random_dense_scene(m, n, 0.45, 21)
+    data = ref.SceneData.SceneData(M, Ns, torch.zeros(m, 3, 4), "loss", calibrated=True)
+    data.valid_pts = torch.Tensor._make_subclass(_FakeCuda, data.valid_pts)
+    g = torch.Generator().manual_seed(5)
+    Ps0 = torch.randn(m, 3, 4, generator=g)
+    X0 = torch.cat((torch.randn(3, n, generator=g), torch.ones(1, n)))
+    Ps0[:, 2, 3] += 2.0                      # most depths positive, some negative -> both branches
+    fix = dict(M=M, Ns=Ns, Ps=Ps0, pts3D=X0, indices=data.x.indices, values=data.x.values)
+    for name, lc in LOSS_VARIANTS.items():
+        conf = ref.ConfigTree.from_dict({"model": {"view_head": {"enabled": True}, "scenepoint_head": {"enabled": True}},
+                                         "loss": dict(infinity_pts_margin=1e-4, **lc)})
+        for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+            Ps = Ps0.detach().clone().to(dtype).requires_grad_(True)
+            X = X0.detach().clone().to(dtype).requires_grad_(True)
+            data._norm_M = data._norm_M.to(dtype)
+            loss = lf.ESFMLoss(conf)({"Ps_norm": Ps, "pts3D": X}, data)
+            (loss * 3.0).backward()
+            fix[f"{name}.{tag}.loss"], fix[f"{name}.{tag}.dPs"], fix[f"{name}.{tag}.dpts3D"] = loss.detach(), Ps.grad.clone(), X.grad.clone()
+            P2, X2 = Ps0.detach().clone().to(dtype).requires_grad_(True), X0.detach().clone().to(dtype).requires_grad_(True)
+            l2 = gasfm_cpu.esfm_loss(P2, X2, data.x.indices, data.x.values, m, n, 1e-4, lc["hinge_loss"], lc["hinge_loss_weight"],
+                                     lc["pts_grad_equalization_pre_perspective_divide"], lc["normalize_grad_wrt_valid_projections_only"])
+            (l2 * 3.0).backward()
+            tol = 1e-5 if dtype == torch.float32 else 1e-12
+            assert abs(l2.item() - loss.item()) <= tol * max(1.0, abs(loss.item())), (name, tag)
+            assert (P2.grad - Ps.grad).abs().max() <= tol * 10 and (X2.grad - X.grad).abs().max() <= tol * 10, (name, tag)
+        fix[f"{name}.conf_json"] = np.array(__import__("json").dumps(lc))
+    np.savez_compressed(os.path.join(HERE, "esfm_loss.npz"), **to_np(fix))
+    print("esfm_loss ok:", {k: float(fix[f"{k}.f64.loss"]) for k in LOSS_VARIANTS})
+
+    # ---- DPESFM SetOfSetNet ---------------------------------------------------------------------------
+    for name, over in (("dpesfm_shipped_like", dict()), ("dpesfm_skipconn", dict(add_skipconn_for_residual_blocks=True, num_blocks=2, block_size=2))):
+        model_d = dict(type="SetOfSet.SetOfSetNet", num_features=24, proj_feat_normalization=True,
+                       add_skipconn_for_residual_blocks=False, num_blocks=1, block_size=3, pos_emb_n_freq=0,
+                       depth_head=dict(enabled=False, n_feat=16, n_hidden_layers=1),
+                       view_head=dict(enabled=True, n_hidden_layers=2, rot_representation="quat"),
+                       scenepoint_head=dict(enabled=True, n_hidden_layers=2))
+        model_d.update(over)
+        conf_d = dict(dataset=dict(calibrated=True), model=model_d)
+        torch.manual_seed(31)
+        net = ref.SetOfSet.SetOfSetNet(ref.ConfigTree.from_dict(conf_d))
+        m, n = 8, 60
+        M, Ns = random_dense_scene(m, n, 0.4, 33)
+        fix = dict(M=M, Ns=Ns, conf_json=np.array(__import__("json").dumps(conf_d)))
+        fix.update({f"param.{k}": v.clone() for k, v in net.state_dict().items()})
+        for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+            mdl = net.to(dtype)
+            mdl.zero_grad()
+            d2 = ref.SceneData.SceneData(M.to(dtype), Ns.to(dtype), torch.zeros(m, 3, 4, dtype=dtype), name, calibrated=True)
+            out = mdl(d2)
+            w = torch.linspace(0.5, 1.5, out["Ps_norm"].numel(), dtype=dtype).reshape(out["Ps_norm"].shape)
+            w2 = torch.linspace(-1.0, 1.0, out["pts3D"].numel(), dtype=dtype).reshape(out["pts3D"].shape)
+            ((out["Ps_norm"] * w).sum() + (out["pts3D"] * w2).sum()).backward()
+            fix[f"out.{tag}.Ps_norm"], fix[f"out.{tag}.pts3D"] = out["Ps_norm"].detach(), out["pts3D"].detach()
+            for k, v in mdl.named_parameters():
+                fix[f"grad.{tag}.{k}"] = v.grad.detach().clone()
+            params = {k: v.detach().clone() for k, v in mdl.state_dict().items()}
+            o = gasfm_cpu.set_of_set_forward(params, gasfm_cpu.make_scene(M.to(dtype), Ns.to(dtype)), model_d["block_size"],
+                                             model_d["proj_feat_normalization"], model_d["add_skipconn_for_residual_blocks"])
+            tol = 2e-5 if dtype == torch.float32 else 1e-11
+            for key in ("Ps_norm", "pts3D"):
+                assert (o[key] - out[key]).abs().max().item() <= tol * max(1.0, out[key].abs().max().item()), (name, tag, key)
+        net.to(torch.float32)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **to_np(fix))
+        print(name, "ok")
 
 
 def _patch_zero_query_dtype(ref, dtype):

@@ -110,3 +110,37 @@ def test_synthetic_scene_invariants():
     M = gasfm_cpu.dense_M_from_sparse(torch.from_numpy(idx), torch.from_numpy(vals), 30, 900)
     again = gasfm_cpu.make_scene(M, None)
     assert torch.equal(again["x"]["indices"], torch.from_numpy(idx))
+
+
+LOSS_VARIANTS = ("shipped", "no_equalization", "normalize_all", "no_hinge")
+
+
+@pytest.mark.parametrize("name", LOSS_VARIANTS)
+def test_esfm_loss_oracle_matches_reference(name):
+    """the dense loss restatement (incl. the gradient hook) against the reference's ESFMLoss."""
+    import json
+    g = load_golden("esfm_loss")
+    lc = json.loads(str(g[f"{name}.conf_json"]))
+    idx, vals = torch.from_numpy(g["indices"]), torch.from_numpy(g["values"])
+    m, n = g["Ps"].shape[0], g["pts3D"].shape[1]
+    Ps = torch.from_numpy(g["Ps"]).double().requires_grad_(True)
+    X = torch.from_numpy(g["pts3D"]).double().requires_grad_(True)
+    loss = gasfm_cpu.esfm_loss(Ps, X, idx, vals, m, n, 1e-4, lc["hinge_loss"], lc["hinge_loss_weight"],
+                               lc["pts_grad_equalization_pre_perspective_divide"], lc["normalize_grad_wrt_valid_projections_only"])
+    (loss * 3.0).backward()
+    assert abs(loss.item() - float(g[f"{name}.f64.loss"])) < 1e-6       # observations are stored in fp32
+    np.testing.assert_allclose(Ps.grad.numpy(), g[f"{name}.f64.dPs"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(X.grad.numpy(), g[f"{name}.f64.dpts3D"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["dpesfm_shipped_like", "dpesfm_skipconn"])
+def test_dpesfm_oracle_matches_reference(name):
+    import json
+    g = load_golden(name)
+    conf = json.loads(str(g["conf_json"]))["model"]
+    params = {k[len("param."):]: torch.from_numpy(g[k]).double() for k in g.files if k.startswith("param.")}
+    scene = gasfm_cpu.make_scene(torch.from_numpy(g["M"]).double(), torch.from_numpy(g["Ns"]).double())
+    out = gasfm_cpu.set_of_set_forward(params, scene, conf["block_size"], conf["proj_feat_normalization"],
+                                       conf["add_skipconn_for_residual_blocks"])
+    for key in ("Ps_norm", "pts3D"):
+        np.testing.assert_allclose(out[key].numpy(), g[f"out.f64.{key}"], rtol=1e-9, atol=1e-10)
