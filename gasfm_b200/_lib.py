@@ -40,13 +40,13 @@ SIGNATURES = {
     "gasfm_edge_update_fwd": (_I, [_P, _L, _P, _I, _P, _P, _P, _P, _P, _L, _P, _P, _L, _I, _F, _F, _P, _P]),
     "gasfm_split_tf32": (_I, [_P, _P, _P, _L, _P]),
     "gasfm_linear_tf32x3_supported": (_I, [_L, _I, _I, _L, _L]),
-    "gasfm_linear_tf32x3": (_I, [_P, _L, _P, _P, _P, _P, _L, _L, _I, _I, _P]),
+    "gasfm_linear_tf32x3": (_I, [_P, _L, _P, _P, _P, _P, _L, _L, _I, _I, _I, _P]),
     "gasfm_wgrad_tf32x3_supported": (_I, [_L, _I, _I, _L, _L]),
     "gasfm_wgrad_tf32x3_ws_bytes": (_SZ, [_I, _I]),
-    "gasfm_wgrad_tf32x3": (_I, [_P, _L, _P, _L, _L, _I, _I, _P, _P, _P]),
+    "gasfm_wgrad_tf32x3": (_I, [_P, _L, _P, _L, _L, _I, _I, _P, _P, _P, _P]),
     "gasfm_wgrad_small_supported": (_I, [_I, _I, _L, _L]),
     "gasfm_wgrad_small_ws_bytes": (_SZ, [_I, _I]),
-    "gasfm_wgrad_small": (_I, [_P, _L, _P, _L, _L, _I, _I, _P, _P, _P]),
+    "gasfm_wgrad_small": (_I, [_P, _L, _P, _L, _L, _I, _I, _P, _P, _P, _P]),
     "gasfm_x0_bwd_ws_bytes": (_SZ, [_L, _I]),
     "gasfm_x0_bwd": (_I, [_P, _L, _I, _P, _P, _I, _F, _P, _P, _P, _P]),
     "gasfm_esfm_loss_ws_bytes": (_SZ, [_L]),

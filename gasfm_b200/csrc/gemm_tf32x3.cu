@@ -9,12 +9,15 @@
 // matching input gradients dX = dY * W.  Replaces cuBLAS SGEMM behind torch.nn.functional.linear
 // at reference call sites code/models/layers.py:329,426 (GATv2Conv.lin_l) and :941 (lin_proj).
 //
-// Kernel structure (one persistent CTA per SM, 10 warps):
-//   warp 0      TMA producer: A tile [128 x 32] fp32, B_hi / B_lo tiles [N x 32] per K-block (SWIZZLE_128B)
+// Kernel structure (one persistent CTA per SM, 14 warps):
+//   warp 0      TMA producer: B_hi / B_lo tiles [N x 32] per K-block (SWIZZLE_128B; the weights stay in L2)
 //   warp 1      TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit to the barriers
-//   warps 2-5   splitter: rewrite the A tile in place as tf32(A) and write A - tf32(A) next to it
-//   warps 6-9   epilogue: tcgen05.ld the 128 x N accumulator, add bias, store rows to global
-// Pipelines: smem ring full -> split_done -> (mma) -> empty; TMEM ring tmem_full <-> tmem_empty (2 accumulators).
+//   warps 2-9   A producers: coalesced 128-bit global loads of the [128 x 32] fp32 tile (4 K-blocks prefetched
+//               in registers), split into tf32(A) and A - tf32(A), written to shared memory directly in
+//               the 128B-swizzled K-major layout the MMA descriptors expect (no TMA -> LDS -> STS round trip:
+//               ncu showed the shared-memory data pipe, not the tensor pipe, was the contended resource)
+//   warps 10-13 epilogue: tcgen05.ld the 128 x N accumulator, add bias, store rows to global
+// Pipelines: smem ring (B full, A split_done) -> mma -> empty; TMEM ring tmem_full <-> tmem_empty (2 accumulators).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -27,7 +30,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;            // 32 fp32 = 128 bytes = one SWIZZLE_128B atom row
 constexpr int kUmmaK = 8;              // tf32: 32 bytes per MMA along K
 constexpr int kStages = 2;
-constexpr int kGemmThreads = 320;
+constexpr int kGemmThreads = 448;          // TMA warp, MMA warp, 8 A-producer warps, 4 epilogue warps
+constexpr int kPrefetch = 4;               // K-blocks of A kept in flight per producer thread
 constexpr int kATileBytes = kBlockM * kBlockK * 4;   // 16 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -63,6 +67,29 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// TMA load whose bytes (and complete_tx) land at the same shared-memory offsets in every CTA of ``mask``
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit that arrives on the barrier at this offset in every CTA of ``mask``
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -94,13 +121,17 @@ __device__ __forceinline__ float tf32_hi(float x) {
 }
 
 struct GemmArgs {
-  const float* bias; float* C; int64_t ldc; int64_t M; int N; int K; int tmem_cols;
+  const float* A; int64_t lda; const float* bias; float* C; int64_t ldc; int64_t M; int N; int K; int tmem_cols; int accumulate;
 };
 
+// CTA pairs (cluster of 2): the weight tiles B_hi / B_lo are identical for every M tile, and re-streaming them
+// from L2 for each tile (80 KB per K-block per SM) ran into the L2 bandwidth cap.  Each CTA of a pair loads half
+// of the B rows and multicasts them into both CTAs' shared memory, halving the L2 traffic for B.  The pair walks
+// its M tiles in lockstep (tile = 2 * pair_step + cta_rank); the MMAs themselves stay cta_group::1.
+constexpr int kCluster = 2;
 template <int kDummy>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-                   const __grid_constant__ CUtensorMap map_blo, GemmArgs p) {
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, GemmArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stage][A_hi 16K | A_lo 16K | B_hi N*128 | B_lo N*128], all 1024-aligned (N*128 is a multiple of 1024 for N%8==0)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -113,9 +144,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k_blocks = (p.K + kBlockK - 1) / kBlockK;
   const int64_t num_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int64_t num_clusters = gridDim.x / kCluster, cluster_id = blockIdx.x / kCluster;
+  const int64_t num_pairs = (num_tiles + kCluster - 1) / kCluster;
+  // pair steps this cluster executes; BOTH CTAs run every step (a CTA whose tile is past the end feeds zeros
+  // and stores nothing) so that the shared pipeline of multicast loads never deadlocks
+  const int64_t my_steps = cluster_id < num_pairs ? (num_pairs - cluster_id + num_clusters - 1) / num_clusters : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&split_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&split_bar[s], 256); mbar_init(&empty_bar[s], kCluster); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -126,6 +163,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  cluster_sync();                            // the peer's barriers are initialised before any remote arrive / multicast
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
   const int acc_cols = p.tmem_cols / 2;     // column offset of the second accumulator
@@ -134,14 +172,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int half_rows = p.N / kCluster;                       // B rows this CTA fetches and multicasts
+      const int half_bytes = half_rows * kBlockK * 4;
+      for (int64_t it = 0; it < my_steps; ++it) {
         for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait(&empty_bar[stage], phase ^ 1);                 // both CTAs have retired the MMAs of this stage
           uint8_t* st = smem + (size_t)stage * stage_bytes;
-          mbar_expect_tx(&full_bar[stage], kATileBytes + 2 * b_tile_bytes);
-          tma_load_2d(st, &map_a, &full_bar[stage], kb * kBlockK, (int)(tile * kBlockM));
-          tma_load_2d(st + 2 * kATileBytes, &map_bhi, &full_bar[stage], kb * kBlockK, 0);
-          tma_load_2d(st + 2 * kATileBytes + b_tile_bytes, &map_blo, &full_bar[stage], kb * kBlockK, 0);
+          mbar_expect_tx(&full_bar[stage], 2 * b_tile_bytes);      // halves from both CTAs land here
+          tma_load_2d_mc(st + 2 * kATileBytes + cta_rank * half_bytes, &map_bhi, &full_bar[stage], kb * kBlockK,
+                         (int)cta_rank * half_rows, (uint16_t)((1u << kCluster) - 1));
+          tma_load_2d_mc(st + 2 * kATileBytes + b_tile_bytes + cta_rank * half_bytes, &map_blo, &full_bar[stage], kb * kBlockK,
+                         (int)cta_rank * half_rows, (uint16_t)((1u << kCluster) - 1));
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -153,12 +194,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int64_t it = 0; it < my_steps; ++it) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
-          mbar_wait(&split_bar[stage], phase);
+          mbar_wait(&full_bar[stage], phase);       // B_hi / B_lo landed (TMA)
+          mbar_wait(&split_bar[stage], phase);      // A_hi / A_lo written by the producer warps
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t a_lo = a_hi + kATileBytes;
@@ -172,42 +214,65 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             umma_tf32(d_tmem, make_desc(a_lo + koff), make_desc(b_hi + koff), idesc, 1u);
             umma_tf32(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), idesc, 1u);
           }
-          umma_commit(&empty_bar[stage]);            // smem stage reusable once these MMAs retire
+          umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << kCluster) - 1));   // frees the stage in BOTH CTAs' eyes
           if (kb == num_k_blocks - 1) umma_commit(&tmem_full_bar[acc]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < 6) {
-    // ===================== splitter (128 threads) =====================
+  } else if (warp < 10) {
+    // ===================== A producers (256 threads) =====================
+    // thread -> 16-byte chunk q of rows rg, rg+32, rg+64, rg+96: a warp-wide load covers 4 full 128-byte rows.
+    // kPrefetch K-blocks are kept in flight in registers (a ring with compile-time slots) so that HBM latency
+    // is covered by ~kPrefetch x 16 KB of outstanding loads per SM.
     const int t = threadIdx.x - 64;
+    const int q = t & 7, rg = t >> 3;
     int stage = 0; uint32_t phase = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        float4* a = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
-        float4* lo = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + kATileBytes);
-        // element-wise at identical (swizzled) addresses, so the layout TMA produced is preserved
+    const int64_t total = my_steps * num_k_blocks;           // K-blocks this CTA produces
+    float4 buf[kPrefetch][4];
+    auto load_block = [&](int64_t g, float4 (&v)[4]) {
+      const int64_t tile = (cluster_id + (g / num_k_blocks) * num_clusters) * kCluster + cta_rank;
+      const int kcol = (int)(g % num_k_blocks) * kBlockK + q * 4;
 #pragma unroll
-        for (int i = 0; i < kATileBytes / 16 / 128; ++i) {
-          const int idx = t + i * 128;
-          float4 v = a[idx], h, l;
-          h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
-          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          a[idx] = h;
-          lo[idx] = l;
+      for (int i = 0; i < 4; ++i) {
+        const int64_t row = tile * kBlockM + rg + 32 * i;
+        v[i] = (g < total && row < p.M && kcol < p.K) ? ld_stream4(p.A + row * p.lda + kcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+#pragma unroll
+    for (int u = 0; u < kPrefetch - 1; ++u) load_block(u, buf[u]);
+    for (int64_t g0 = 0; g0 < total; g0 += kPrefetch) {
+#pragma unroll
+      for (int u = 0; u < kPrefetch; ++u) {
+        const int64_t g = g0 + u;
+        load_block(g + kPrefetch - 1, buf[(u + kPrefetch - 1) % kPrefetch]);
+        if (g < total) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_hi = smem + (size_t)stage * stage_bytes;
+          uint8_t* a_lo = a_hi + kATileBytes;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = rg + 32 * i;
+            const int off = row * 128 + ((q ^ (row & 7)) << 4);   // SWIZZLE_128B: chunk ^= row % 8
+            float4 v = buf[u][i], h, l;
+            h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+            *reinterpret_cast<float4*>(a_hi + off) = h;
+            *reinterpret_cast<float4*>(a_lo + off) = l;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+          mbar_arrive(&split_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
-        mbar_arrive(&split_bar[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue (warps 6..9 -> TMEM lane quarters 2,3,0,1) =====================
+    // ===================== epilogue (warps 10..13 -> TMEM lane quarters 2,3,0,1) =====================
     const int quarter = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int64_t it = 0; it < my_steps; ++it) {
+      const int64_t tile = (cluster_id + it * num_clusters) * kCluster + cta_rank;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t row = tile * kBlockM + quarter * 32 + lane;
@@ -233,6 +298,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               v.y = __uint_as_float(r[j + 1]) + bias_s[c0 + j + 1];
               v.z = __uint_as_float(r[j + 2]) + bias_s[c0 + j + 2];
               v.w = __uint_as_float(r[j + 3]) + bias_s[c0 + j + 3];
+              if (p.accumulate) {                      // C += A W^T: sums the input gradients of projections that share x
+                const float4 o = *reinterpret_cast<const float4*>(crow + c0 + j);
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+              }
               *reinterpret_cast<float4*>(crow + c0 + j) = v;
             }
           }
@@ -244,6 +313,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
   }
   __syncthreads();
+  cluster_sync();                            // no CTA leaves while its peer may still multicast into its shared memory
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
@@ -276,7 +346,7 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
 }
 
 struct WgradArgs {
-  float* ws; int64_t E; int Nout; int Kout; int m_tiles; int a_boxes; int b_boxes; int tmem_cols; int64_t rows_per_cta; int pass_stages;
+  float* ws; float* ws_db; int64_t E; int Nout; int Kout; int m_tiles; int a_boxes; int b_boxes; int tmem_cols; int64_t rows_per_cta; int pass_stages;
 };
 
 template <int kDummy>
@@ -373,20 +443,30 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
     const int n_out = mt * 128 + quarter * 32 + lane;
     float* dst = p.ws + ((int64_t)blockIdx.x * p.Nout + n_out) * p.Kout;
     const uint32_t taddr0 = tmem_base + (uint32_t)(mt * p.Kout) + ((uint32_t)(quarter * 32) << 16);
+    // column sums of dY (= the bias gradient) ride along: a thread always meets the same (box, row, slot)
+    // positions of the dY tile, so it keeps one float4 of running sums per position (<= 4 positions)
+    float4 colsum[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) colsum[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int pass = 0; pass < num_passes; ++pass) {
       const int it_end = min(num_stages_total, (pass + 1) * p.pass_stages);
       for (int it = pass * p.pass_stages; it < it_end; ++it) {
         mbar_wait(&full_bar[stage], phase);
         uint8_t* st = smem + (size_t)stage * stage_bytes;
-        for (int idx = t; idx < tot_vec; idx += 256) {
-          const bool is_a = idx < a_vec;
-          float4* hi = reinterpret_cast<float4*>(is_a ? st : st + 2 * a_bytes) + (is_a ? idx : idx - a_vec);
-          float4* lo = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(hi) + (is_a ? a_bytes : b_bytes));
-          float4 v = *hi, h, l;
-          h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
-          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          *hi = h;
-          *lo = l;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = t + 256 * i;
+          if (idx < tot_vec) {
+            const bool is_a = idx < a_vec;
+            float4* hi = reinterpret_cast<float4*>(is_a ? st : st + 2 * a_bytes) + (is_a ? idx : idx - a_vec);
+            float4* lo = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(hi) + (is_a ? a_bytes : b_bytes));
+            float4 v = *hi, h, l;
+            h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+            *hi = h;
+            *lo = l;
+            if (i < 4 && is_a) { colsum[i].x += v.x; colsum[i].y += v.y; colsum[i].z += v.z; colsum[i].w += v.w; }
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&split_bar[stage]);
@@ -426,6 +506,28 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&drained_bar);
+    }
+    // bias gradient: scatter the per-position sums to S[row 0..15][logical column], then add the 16 rows.
+    // TMA SWIZZLE_128B_ATOM_32B stores logical 32-byte chunk c of row r at physical chunk c ^ (r & 3).
+    if (p.ws_db != nullptr) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");           // all 8 worker warps are past their last stage
+      float* S = reinterpret_cast<float*>(smem);               // 16 x 256 floats, reuses stage 0 (MMAs have retired)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = t + 256 * i;
+        if (idx < a_vec) {
+          const int j = idx >> 7, r = (idx & 127) >> 3, sl = idx & 7;
+          const int col = j * 32 + (((sl >> 1) ^ (r & 3)) << 3) + ((sl & 1) << 2);
+          *reinterpret_cast<float4*>(S + r * 256 + col) = colsum[i];
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (t < p.Nout) {
+        float a = 0.f;
+#pragma unroll
+        for (int r = 0; r < kWgRows; ++r) a += S[r * 256 + t];
+        p.ws_db[(int64_t)blockIdx.x * p.Nout + t] = a;
+      }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
@@ -504,12 +606,12 @@ extern "C" int gasfm_linear_tf32x3_supported(int64_t M, int N, int K, int64_t ld
 }
 
 extern "C" int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo, const float* bias,
-                                   float* C, int64_t ldc, int64_t M, int N, int K, void* stream) {
+                                   float* C, int64_t ldc, int64_t M, int N, int K, int accumulate, void* stream) {
   GASFM_REQUIRE(gasfm_linear_tf32x3_supported(M, N, K, lda, ldc), "linear_tf32x3: unsupported shape M=%lld N=%d K=%d lda=%lld ldc=%lld",
                 (long long)M, N, K, (long long)lda, (long long)ldc);
   GASFM_REQUIRE(((uintptr_t)A | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C) % 16 == 0, "linear_tf32x3: pointers must be 16-byte aligned");
-  CUtensorMap ma, mh, ml;
-  if (make_map(&ma, A, M, K, lda, kBlockM) || make_map(&mh, B_hi, N, K, K, N) || make_map(&ml, B_lo, N, K, K, N)) return 1;
+  CUtensorMap mh, ml;
+  if (make_map(&mh, B_hi, N, K, K, N / kCluster) || make_map(&ml, B_lo, N, K, K, N / kCluster)) return 1;
   int tmem_cols = 32;
   while (tmem_cols < 2 * N) tmem_cols <<= 1;
   const size_t smem = (size_t)kStages * (2 * kATileBytes + 2 * (size_t)N * kBlockK * 4) + 1024;
@@ -523,9 +625,10 @@ extern "C" int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_h
     smem_allowed = smem;
   }
   const int64_t tiles = (M + kBlockM - 1) / kBlockM;
-  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  GemmArgs args{bias, C, ldc, M, N, K, tmem_cols};
-  gemm_tf32x3_kernel<0><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(ma, mh, ml, args);
+  const int64_t pairs = (tiles + kCluster - 1) / kCluster;
+  const int grid = (int)(pairs < kNumSMs / kCluster ? pairs : kNumSMs / kCluster) * kCluster;
+  GemmArgs args{A, lda, bias, C, ldc, M, N, K, tmem_cols, accumulate};
+  gemm_tf32x3_kernel<0><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(mh, ml, args);
   return check_launch("linear_tf32x3");
 }
 
@@ -534,11 +637,11 @@ extern "C" int gasfm_wgrad_tf32x3_supported(int64_t E, int Nout, int Kout, int64
 }
 
 extern "C" size_t gasfm_wgrad_tf32x3_ws_bytes(int Nout, int Kout) {
-  return (size_t)kNumSMs * Nout * Kout * sizeof(float);
+  return ((size_t)kNumSMs * Nout * Kout + (size_t)kNumSMs * 256) * sizeof(float);
 }
 
 extern "C" int gasfm_wgrad_tf32x3(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t E, int Nout, int Kout,
-                                  float* dW, void* ws, void* stream) {
+                                  float* dW, float* dbias, void* ws, void* stream) {
   GASFM_REQUIRE(gasfm_wgrad_tf32x3_supported(E, Nout, Kout, lddy, ldx), "wgrad_tf32x3: unsupported shape E=%lld Nout=%d Kout=%d",
                 (long long)E, Nout, Kout);
   GASFM_REQUIRE(ws != nullptr && ((uintptr_t)dY | (uintptr_t)X | (uintptr_t)dW | (uintptr_t)ws) % 16 == 0, "wgrad_tf32x3: bad pointers");
@@ -566,12 +669,14 @@ extern "C" int gasfm_wgrad_tf32x3(const float* dY, int64_t lddy, const float* X,
     pass_stages = env ? atoi(env) : 64;
     if (pass_stages < 1) pass_stages = 64;
   }
-  WgradArgs a{(float*)ws, E, Nout, Kout, m_tiles, a_boxes, b_boxes, tmem_cols, rows_per_cta, pass_stages};
+  float* ws_db = dbias ? (float*)ws + (size_t)kNumSMs * Nout * Kout : nullptr;
+  WgradArgs a{(float*)ws, ws_db, E, Nout, Kout, m_tiles, a_boxes, b_boxes, tmem_cols, rows_per_cta, pass_stages};
   cudaStream_t st = (cudaStream_t)stream;
   wgrad_tf32x3_kernel<0><<<grid, kWgThreads, smem, st>>>(mdy, mx, a);
   int rc = check_launch("wgrad_tf32x3");
   if (rc) return rc;
   const int64_t width = (int64_t)Nout * Kout;
   wgrad_reduce_kernel<<<ceil_div(width / 4, 256), 256, 0, st>>>((const float*)ws, grid, width, dW);
+  if (dbias) wgrad_reduce_kernel<<<ceil_div(Nout / 4, 256), 256, 0, st>>>(ws_db, grid, Nout, dbias);
   return check_launch("wgrad_tf32x3(reduce)");
 }

@@ -18,7 +18,7 @@ constexpr int kWsWarps = 8;
 template <int NOUT, int KOUT>
 __global__ void __launch_bounds__(kWsWarps * 32) wgrad_small_kernel(const float* __restrict__ dY, int64_t lddy,
                                                                     const float* __restrict__ X, int64_t ldx, int64_t E,
-                                                                    float* __restrict__ ws) {
+                                                                    float* __restrict__ ws, float* __restrict__ ws_db) {
   constexpr int RPL = NOUT / 32;
   constexpr int TR = 8;                                    // rows per tile
   // one static buffer: per-warp row tiles during the main loop, the CTA accumulator afterwards
@@ -28,11 +28,13 @@ __global__ void __launch_bounds__(kWsWarps * 32) wgrad_small_kernel(const float*
   float (*s_x)[TR][KOUT] = reinterpret_cast<float (*)[TR][KOUT]>(s_buf + kWsWarps * TR * NOUT);
   float* s_acc = s_buf;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  float acc[RPL][KOUT];
+  float acc[RPL][KOUT], dsum[RPL];
 #pragma unroll
-  for (int r = 0; r < RPL; ++r)
+  for (int r = 0; r < RPL; ++r) {
+    dsum[r] = 0.f;
 #pragma unroll
     for (int k = 0; k < KOUT; ++k) acc[r][k] = 0.f;
+  }
   const int64_t n_tiles = (E + TR - 1) / TR;
   const int64_t warp = (int64_t)blockIdx.x * kWsWarps + wid, n_warps = (int64_t)gridDim.x * kWsWarps;
   for (int64_t t = warp; t < n_tiles; t += n_warps) {
@@ -57,7 +59,7 @@ __global__ void __launch_bounds__(kWsWarps * 32) wgrad_small_kernel(const float*
     for (int r = 0; r < TR; ++r) {
       float d[RPL];
 #pragma unroll
-      for (int q = 0; q < RPL; ++q) d[q] = s_dy[wid][r][lane + 32 * q];
+      for (int q = 0; q < RPL; ++q) { d[q] = s_dy[wid][r][lane + 32 * q]; dsum[q] += d[q]; }
 #pragma unroll
       for (int k = 0; k < KOUT; k += 4) {
         const float4 xv = *reinterpret_cast<const float4*>(&s_x[wid][r][k]);   // same address in all lanes: broadcast
@@ -86,6 +88,19 @@ __global__ void __launch_bounds__(kWsWarps * 32) wgrad_small_kernel(const float*
     __syncthreads();
   }
   for (int j = threadIdx.x; j < NOUT * KOUT; j += blockDim.x) ws[(int64_t)blockIdx.x * NOUT * KOUT + j] = s_acc[j];
+  if (ws_db != nullptr) {                                   // bias gradient = column sums of dY, same deterministic scheme
+    __syncthreads();
+    for (int j = threadIdx.x; j < NOUT; j += blockDim.x) s_acc[j] = 0.f;
+    __syncthreads();
+    for (int w = 0; w < kWsWarps; ++w) {
+      if (wid == w) {
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) s_acc[lane + 32 * q] += dsum[q];
+      }
+      __syncthreads();
+    }
+    for (int j = threadIdx.x; j < NOUT; j += blockDim.x) ws_db[(int64_t)blockIdx.x * NOUT + j] = s_acc[j];
+  }
 }
 
 __global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restrict__ ws, int rows, int64_t width, float scale,
@@ -206,10 +221,10 @@ using namespace gasfm;
 extern "C" int gasfm_wgrad_small_supported(int Nout, int Kout, int64_t lddy, int64_t ldx) {
   return ((Nout == 32 || Nout == 64) && (Kout == 32 || Kout == 64) && lddy % 4 == 0 && ldx % 4 == 0) ? 1 : 0;
 }
-extern "C" size_t gasfm_wgrad_small_ws_bytes(int Nout, int Kout) { return (size_t)kWsBlocks * Nout * Kout * sizeof(float); }
+extern "C" size_t gasfm_wgrad_small_ws_bytes(int Nout, int Kout) { return (size_t)kWsBlocks * (Nout * Kout + Nout) * sizeof(float); }
 
 extern "C" int gasfm_wgrad_small(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t E, int Nout, int Kout,
-                                 float* dW, void* ws, void* stream) {
+                                 float* dW, float* dbias, void* ws, void* stream) {
   GASFM_REQUIRE(gasfm_wgrad_small_supported(Nout, Kout, lddy, ldx), "wgrad_small: unsupported shape %d x %d", Nout, Kout);
   GASFM_REQUIRE(ws && ((uintptr_t)dY | (uintptr_t)X) % 16 == 0, "wgrad_small: bad pointers");
   cudaStream_t st = (cudaStream_t)stream;
@@ -218,14 +233,16 @@ extern "C" int gasfm_wgrad_small(const float* dY, int64_t lddy, const float* X, 
   if (blocks > kWsBlocks) blocks = kWsBlocks;
   if (blocks < 1) blocks = 1;
   float* w = (float*)ws;
-  if (Nout == 32 && Kout == 32) wgrad_small_kernel<32, 32><<<blocks, kWsWarps * 32, 0, st>>>(dY, lddy, X, ldx, E, w);
-  else if (Nout == 32 && Kout == 64) wgrad_small_kernel<32, 64><<<blocks, kWsWarps * 32, 0, st>>>(dY, lddy, X, ldx, E, w);
-  else if (Nout == 64 && Kout == 32) wgrad_small_kernel<64, 32><<<blocks, kWsWarps * 32, 0, st>>>(dY, lddy, X, ldx, E, w);
-  else wgrad_small_kernel<64, 64><<<blocks, kWsWarps * 32, 0, st>>>(dY, lddy, X, ldx, E, w);
+  float* wdb = dbias ? w + (size_t)kWsBlocks * Nout * Kout : nullptr;
+  if (Nout == 32 && Kout == 32) wgrad_small_kernel<32, 32><<<blocks, kWsWarps * 32, 0, st>>>(dY, lddy, X, ldx, E, w, wdb);
+  else if (Nout == 32 && Kout == 64) wgrad_small_kernel<32, 64><<<blocks, kWsWarps * 32, 0, st>>>(dY, lddy, X, ldx, E, w, wdb);
+  else if (Nout == 64 && Kout == 32) wgrad_small_kernel<64, 32><<<blocks, kWsWarps * 32, 0, st>>>(dY, lddy, X, ldx, E, w, wdb);
+  else wgrad_small_kernel<64, 64><<<blocks, kWsWarps * 32, 0, st>>>(dY, lddy, X, ldx, E, w, wdb);
   int rc = check_launch("wgrad_small");
   if (rc) return rc;
   const int64_t width = (int64_t)Nout * Kout;
   partial_sum_kernel<<<ceil_div(width, 256), 256, 0, st>>>(w, blocks, width, 1.f, dW);
+  if (dbias) partial_sum_kernel<<<1, 256, 0, st>>>(wdb, blocks, Nout, 1.f, dbias);
   return check_launch("wgrad_small(reduce)");
 }
 

@@ -272,11 +272,20 @@ class GraphAttnSfMLayer(Module):
             # also rectifies the values the residual branch reads.
             raw = x
 
-        scenepoint_features, view_features, global_features = self.global_feature_update(
+        # lin_l of both attention graphs and lin_proj all read x: one autograd node, so that the three input
+        # gradients are summed inside the GEMM epilogues (ops.linear_multi)
+        gfu, pfu = self.global_feature_update, self.projection_feature_update
+        d_main = x.shape[2]
+        conv_sp, conv_v = gfu.proj2scenepoint.graph_conv, gfu.proj2view.graph_conv
+        xl_sp, xl_v, proj = ops.linear_multi(x.values, [
+            (conv_sp.lin_l.weight, conv_sp.lin_l.bias), (conv_v.lin_l.weight, conv_v.lin_l.bias),
+            (0.25 * pfu.lin_proj.weight[:, :d_main], 0.25 * pfu.lin_proj.bias)])
+        scenepoint_features, view_features, global_features = gfu(
             x, graph_structure,
             prev_scenepoint_features = prev_scenepoint_features,
             prev_view_features = prev_view_features,
             prev_global_features = prev_global_features,
+            projected_sources = (xl_sp, xl_v),
         )
         feats = x
         if self.add_skipconn_from_init_projfeat:
@@ -291,8 +300,8 @@ class GraphAttnSfMLayer(Module):
                 if self.use_norm_proj_update:
                     residual = relu_on_projection_features(None, _fused_norm=(residual, self.residual_skipconn_proj_norm_layer))
                 residual = self.skip_projection(residual)
-        projection_features = self.projection_feature_update(
-            scenepoint_features, view_features, global_features, feats, residual = residual)
+        projection_features = pfu(scenepoint_features, view_features, global_features, feats, residual = residual,
+                                  projected = proj)
         return projection_features, scenepoint_features, view_features, global_features
 
 
@@ -574,13 +583,21 @@ class GraphAttnSfMGlobalFeatureUpdate(Module):
                                                        use_norm_global2scenepoint_update=True)
 
     def forward(self, x, graph_structure, prev_scenepoint_features=None, prev_view_features=None,
-                prev_global_features=None):
+                prev_global_features=None, projected_sources=None):
+        """``projected_sources`` (extension): (lin_l(x) of proj2scenepoint, lin_l(x) of proj2view) when the caller
+        already computed them; otherwise they are computed here (together, as one autograd node)."""
         m, n, n_feat_proj_in = x.shape
         assert n_feat_proj_in == self.n_feat_proj_in
+        if projected_sources is None:
+            conv_sp, conv_v = self.proj2scenepoint.graph_conv, self.proj2view.graph_conv
+            projected_sources = ops.linear_multi(x.values, [(conv_sp.lin_l.weight, conv_sp.lin_l.bias),
+                                                            (conv_v.lin_l.weight, conv_v.lin_l.bias)])
         scenepoint_features = self.proj2scenepoint(x, graph_structure['proj2scenepoint'],
-                                                   prev_scenepoint_features=prev_scenepoint_features)
+                                                   prev_scenepoint_features=prev_scenepoint_features,
+                                                   projected_sources=projected_sources[0])
         assert scenepoint_features.shape == (n, self.n_feat_scenepoint_out)
-        view_features = self.proj2view(x, graph_structure['proj2view'], prev_view_features=prev_view_features)
+        view_features = self.proj2view(x, graph_structure['proj2view'], prev_view_features=prev_view_features,
+                                       projected_sources=projected_sources[1])
         assert view_features.shape == (m, self.n_feat_view_out)
         global_features = None
         if self.output_global or self.global2view_and_global2scenepoint_enabled:
@@ -619,10 +636,11 @@ class GraphAttnSfMProjectionFeatureUpdate(Module):
             self.mlp = get_linear_layers(n_hidden_layers_proj_update * [n_feat_proj_out] + [n_feat_proj_out],
                                          init_activation=False, final_activation=False, norm=False)
 
-    def forward(self, scenepoint_features, view_features, global_features, x, residual=None):
+    def forward(self, scenepoint_features, view_features, global_features, x, residual=None, projected=None):
         """(lin_proj(x) + lin_sp(sp)[col] + lin_view(view)[row] + lin_global(g)) / 4 [-> relu -> mlp]
-        (layers.py:911-956).  ``residual`` (extension): SparseMat added to the result inside the same
-        kernel -- the skip connection of GraphAttnSfMLayer (layers.py:254-261)."""
+        (layers.py:911-956).  Extensions: ``residual`` = SparseMat added to the result inside the same
+        kernel (the skip connection of GraphAttnSfMLayer, layers.py:254-261); ``projected`` = the already
+        computed 0.25 * lin_proj over the main feature block of ``x``."""
         if self.normalize_global_features:
             scenepoint_features = self.scenepoint_norm_layer.ln_relu(scenepoint_features)
             view_features = self.view_norm_layer.ln_relu(view_features)
@@ -635,10 +653,12 @@ class GraphAttnSfMProjectionFeatureUpdate(Module):
         x0 = w0 = None
         if isinstance(x, _LazyFeatureCat) and x._extra.shape[2] <= 4:
             d_main = x._main.shape[2]
-            proj = ops.linear(x._main.values, 0.25 * w[:, :d_main], 0.25 * b)
+            proj = projected if projected is not None else ops.linear(x._main.values, 0.25 * w[:, :d_main], 0.25 * b)
             x0, w0 = x._extra.values, w[:, d_main:]
+        elif isinstance(x, _LazyFeatureCat):
+            proj = ops.linear(x.values, 0.25 * w, 0.25 * b)        # wide init features: materialised cat
         else:
-            proj = ops.linear(x.values, 0.25 * w, 0.25 * b)
+            proj = projected if projected is not None else ops.linear(x.values, 0.25 * w, 0.25 * b)
         has_mlp = self.n_hidden_layers_proj_update > 0
         fused_skip = None if (residual is None or has_mlp) else residual.values
         new = ops.edge_update(proj, x0, w0, sp, view, glob, fused_skip, index_for(x), 1.0, 0.25)

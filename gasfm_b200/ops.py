@@ -311,42 +311,68 @@ def gemm_tf32x3_supported(M, N, K, lda, ldc):
     return bool(_lib.load().gasfm_linear_tf32x3_supported(int(M), int(N), int(K), int(lda), int(ldc)))
 
 
-def gemm_tf32x3(a, b, bias=None):
-    """a [M,K] (rows contiguous, any row stride) times b[N,K]^T (+ bias[N]) -> [M,N], fp32 accuracy."""
+def gemm_tf32x3(a, b, bias=None, out=None, accumulate=False):
+    """a [M,K] (rows contiguous, any row stride) times b[N,K]^T (+ bias[N]) -> [M,N], fp32 accuracy.
+    ``out`` + ``accumulate``: out += a b^T (used to sum the input gradients of projections sharing x)."""
     a, lda = _rows(a)
     M, K = a.shape
     N = b.shape[0]
     hi, lo = _split_tf32(b)
-    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    c = torch.empty((M, N), dtype=torch.float32, device=a.device) if out is None else out
     with torch.cuda.device(a.device):
         _lib.call("gasfm_linear_tf32x3", _lib.ptr(a), lda, _lib.ptr(hi), _lib.ptr(lo),
-                  _lib.ptr(None if bias is None else bias.contiguous()), _lib.ptr(c), N, M, N, K, _lib.stream_ptr())
+                  _lib.ptr(None if bias is None else bias.contiguous()), _lib.ptr(c), N, M, N, K, int(bool(accumulate)),
+                  _lib.stream_ptr())
     return c
 
 
 def wgrad_tf32x3_supported(E, n_out, k_out, lddy, ldx):
-    return bool(_lib.load().gasfm_wgrad_tf32x3_supported(int(E), int(n_out), int(k_out), int(lddy), int(ldx)))
+    lib = _lib.load()
+    return bool(lib.gasfm_wgrad_small_supported(int(n_out), int(k_out), int(lddy), int(ldx)) or
+                lib.gasfm_wgrad_tf32x3_supported(int(E), int(n_out), int(k_out), int(lddy), int(ldx)))
 
 
-def wgrad_tf32x3(dy, x):
+def wgrad_tf32x3(dy, x, with_bias=False):
     """dW[Nout,Kout] = dy[E,Nout]^T @ x[E,Kout]: tensor cores (3xTF32, deterministic split-K), or the SIMT
-    register-tiled kernel for the narrow shipped widths (32 / 64)."""
+    register-tiled kernel for the narrow shipped widths (32 / 64).  ``with_bias`` also returns the column
+    sums of dy (the bias gradient), accumulated in the same pass."""
     dy, lddy = _rows(dy)
     x, ldx = _rows(x)
     E, n_out = dy.shape
     k_out = x.shape[1]
-    dw = torch.empty((n_out, k_out), dtype=torch.float32, device=dy.device)
-    if _lib.load().gasfm_wgrad_small_supported(n_out, k_out, lddy, ldx):
-        ws = torch.empty(_lib.size_query("gasfm_wgrad_small_ws_bytes", n_out, k_out) // 4, dtype=torch.float32, device=dy.device)
-        with torch.cuda.device(dy.device):
-            _lib.call("gasfm_wgrad_small", _lib.ptr(dy), lddy, _lib.ptr(x), ldx, E, n_out, k_out, _lib.ptr(dw), _lib.ptr(ws),
-                      _lib.stream_ptr())
-        return dw
-    ws = torch.empty(_lib.size_query("gasfm_wgrad_tf32x3_ws_bytes", n_out, k_out) // 4, dtype=torch.float32, device=dy.device)
-    with torch.cuda.device(dy.device):
-        _lib.call("gasfm_wgrad_tf32x3", _lib.ptr(dy), lddy, _lib.ptr(x), ldx, E, n_out, k_out, _lib.ptr(dw), _lib.ptr(ws),
+    dev = dy.device
+    dw = torch.empty((n_out, k_out), dtype=torch.float32, device=dev)
+    db = torch.empty(n_out, dtype=torch.float32, device=dev) if with_bias else None
+    small = _lib.load().gasfm_wgrad_small_supported(n_out, k_out, lddy, ldx)
+    name = "gasfm_wgrad_small" if small else "gasfm_wgrad_tf32x3"
+    ws = torch.empty(_lib.size_query(name + "_ws_bytes", n_out, k_out) // 4, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call(name, _lib.ptr(dy), lddy, _lib.ptr(x), ldx, E, n_out, k_out, _lib.ptr(dw), _lib.ptr(db), _lib.ptr(ws),
                   _lib.stream_ptr())
-    return dw
+    return (dw, db) if with_bias else dw
+
+
+def _linear_backward(x, weight, dy, need_x, need_w, need_b, dx_out=None):
+    """Gradients of y = x W^T + b on the tensor-core kernels; ``dx_out``: accumulate dX into this buffer."""
+    dy = dy.contiguous()
+    dx = dw = db = None
+    M, N = dy.shape
+    K = weight.shape[1]
+    if need_x:
+        if gemm_tf32x3_supported(M, K, N, N, K):
+            dx = gemm_tf32x3(dy, weight.t(), out=dx_out, accumulate=dx_out is not None)   # dX = dY (W^T)^T
+        elif dx_out is not None:
+            dx = dx_out.add_(dy @ weight)
+        else:
+            dx = dy @ weight
+    if need_w or need_b:
+        ldx = x.stride(0) if x.stride(1) == 1 else K
+        if wgrad_tf32x3_supported(M, N, K, N, ldx):
+            dw, db = wgrad_tf32x3(dy, x, with_bias=True)
+        else:
+            dw = dy.t() @ x
+            db = dy.sum(dim=0)
+    return dx, dw, db
 
 
 class _LinearTC(torch.autograd.Function):
@@ -359,27 +385,51 @@ class _LinearTC(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
-        dy = dy.contiguous()
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            M, N = dy.shape
-            K = weight.shape[1]
-            if gemm_tf32x3_supported(M, K, N, N, K):
-                dx = gemm_tf32x3(dy, weight.t())           # dX[M,K] = dY[M,N] * (W^T)[K,N]^T
-            else:
-                dx = dy @ weight
-        if ctx.needs_input_grad[1]:
-            lddx = x.stride(0) if x.stride(1) == 1 else x.shape[1]
-            if wgrad_tf32x3_supported(dy.shape[0], dy.shape[1], x.shape[1], dy.shape[1], lddx):
-                dw = wgrad_tf32x3(dy, x)
-            else:
-                dw = dy.t() @ x
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.sum(dim=0)
-        return dx, dw, db
+        dx, dw, db = _linear_backward(x, weight, dy, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                      ctx.has_bias and ctx.needs_input_grad[2])
+        return dx, dw, (db if ctx.has_bias else None)
+
+
+class _LinearMulti(torch.autograd.Function):
+    """Several projections of the SAME input: y_i = x W_i^T + b_i.  Backward sums the input gradients
+    inside the GEMM epilogue (dX += dY_i W_i) instead of materialising one dX per projection and adding."""
+
+    @staticmethod
+    def forward(ctx, x, *wb):
+        weights, biases = wb[0::2], wb[1::2]
+        ctx.save_for_backward(x, *weights)
+        ctx.n = len(weights)
+        return tuple(gemm_tf32x3(x, w, b) for w, b in zip(weights, biases))
+
+    @staticmethod
+    def backward(ctx, *dys):
+        x, *weights = ctx.saved_tensors
+        grads = []
+        dx = None
+        need_x = ctx.needs_input_grad[0]
+        for i, (w, dy) in enumerate(zip(weights, dys)):
+            g, dw, db = _linear_backward(x, w, dy, need_x, ctx.needs_input_grad[1 + 2 * i], ctx.needs_input_grad[2 + 2 * i],
+                                         dx_out=dx)
+            if need_x:
+                dx = g
+            grads += [dw, db]
+        return (dx, *grads)
 
 
 TENSOR_CORE_MIN_ROWS = 4096   # below this the launch overhead dominates; cuBLAS is fine
+
+
+def linear_multi(x, weights_and_biases):
+    """[(W_i, b_i)] -> tuple of x W_i^T + b_i; one autograd node when every shape fits the tensor-core kernel."""
+    M, K = x.shape
+    lda = x.stride(0) if x.stride(1) == 1 else K
+    ok = x.is_cuda and M >= TENSOR_CORE_MIN_ROWS and all(
+        b is not None and gemm_tf32x3_supported(M, w.shape[0], K, lda, w.shape[0]) and
+        gemm_tf32x3_supported(M, K, w.shape[0], w.shape[0], K) for w, b in weights_and_biases)
+    if ok:
+        flat = [t for wb in weights_and_biases for t in wb]
+        return _LinearMulti.apply(x, *flat)
+    return tuple(linear(x, w, b) for w, b in weights_and_biases)
 
 
 def linear(x, weight, bias=None):

@@ -178,21 +178,22 @@ GASFM_API int gasfm_split_tf32(const float* w, float* hi, float* lo, int64_t n, 
 GASFM_API int gasfm_linear_tf32x3_supported(int64_t M, int N, int K, int64_t lda, int64_t ldc);
 GASFM_API int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo,
                                   const float* bias, float* C, int64_t ldc, int64_t M, int N, int K,
-                                  void* stream);
+                                  int accumulate /* 1: C += A B^T + bias */, void* stream);
 
 /* Weight gradient of the same projections: dW[Nout,Kout] = dY[E,Nout]^T * X[E,Kout], 3xTF32 on tcgen05,
  * deterministic split-K over the SMs.  ``ws`` needs gasfm_wgrad_tf32x3_ws_bytes(Nout,Kout) bytes. */
 GASFM_API int gasfm_wgrad_tf32x3_supported(int64_t E, int Nout, int Kout, int64_t lddy, int64_t ldx);
 GASFM_API size_t gasfm_wgrad_tf32x3_ws_bytes(int Nout, int Kout);
 GASFM_API int gasfm_wgrad_tf32x3(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t E,
-                                 int Nout, int Kout, float* dW, void* ws, void* stream);
+                                 int Nout, int Kout, float* dW, float* dbias /* [Nout] column sums of dY, or NULL */,
+                                 void* ws, void* stream);
 
 /* The same weight gradient for the narrow shipped widths (Nout, Kout in {32, 64}) on the SIMT pipes, where a
  * 128-wide tensor-core tile would be mostly padding; fp32 round-to-nearest accumulation, deterministic. */
 GASFM_API int gasfm_wgrad_small_supported(int Nout, int Kout, int64_t lddy, int64_t ldx);
 GASFM_API size_t gasfm_wgrad_small_ws_bytes(int Nout, int Kout);
 GASFM_API int gasfm_wgrad_small(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t E, int Nout,
-                                int Kout, float* dW, void* ws, void* stream);
+                                int Kout, float* dW, float* dbias /* or NULL */, void* ws, void* stream);
 
 /* Backward of the rank-d0 term of gasfm_edge_update_fwd in one pass over dOut[E,width]:
  *   dx0[E,d0] = scale * dOut W0,   dW0[width,d0] = scale * dOut^T x0        (d0 <= 4)

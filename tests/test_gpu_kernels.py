@@ -444,3 +444,38 @@ def test_full_size_edge_kernels_cfg3():
         nonempty = (plan.seg_ptr[1:] > plan.seg_ptr[:-1]).unsqueeze(1)
         assert torch.allclose(seg_tot, torch.where(nonempty, 1.0 + xr.grad, torch.zeros_like(seg_tot)), atol=5e-4)
     assert torch.equal(oi.csc_perm.long(), torch.argsort(torch.from_numpy(idx_np[1]).to(DEV), stable=True))
+
+
+def test_linear_multi_sums_input_gradients_in_the_epilogue():
+    """three projections of one input (lin_l x2 + lin_proj): outputs, dX (accumulated in the GEMM epilogue),
+    dW and the fused bias gradients against fp64"""
+    torch.manual_seed(5)
+    M, K = 9000, 64
+    x = torch.randn(M, K, device=DEV, requires_grad=True)
+    ws = [(torch.randn(n, K, device=DEV) / K ** 0.5).requires_grad_(True) for n in (64, 32, 48)]
+    bs = [torch.randn(n, device=DEV, requires_grad=True) for n in (64, 32, 48)]
+    ys = ops.linear_multi(x, list(zip(ws, bs)))
+    assert type(ys[0].grad_fn).__name__.startswith("_LinearMulti")
+    dys = [torch.randn_like(y) for y in ys]
+    torch.autograd.backward(ys, dys)
+    xd = x.detach().double().requires_grad_(True)
+    wd = [w.detach().double().requires_grad_(True) for w in ws]
+    bd = [b.detach().double().requires_grad_(True) for b in bs]
+    yd = [torch.nn.functional.linear(xd, w, b) for w, b in zip(wd, bd)]
+    torch.autograd.backward(yd, [d.double() for d in dys])
+    for y, r in zip(ys, yd):
+        assert rel_err(y, r.detach().cpu().numpy()) < FP32_TOL
+    assert rel_err(x.grad, xd.grad.cpu().numpy()) < FP32_TOL
+    for w, r in zip(ws, wd):
+        assert rel_err(w.grad, r.grad.cpu().numpy()) < GRAD_TOL
+    for b, r in zip(bs, bd):
+        assert rel_err(b.grad, r.grad.cpu().numpy()) < GRAD_TOL
+
+
+@pytest.mark.parametrize("E,Nout,Kout", [(70001, 256, 256), (5000, 48, 80), (30000, 64, 64), (999, 32, 32)])
+def test_wgrad_fused_bias_gradient(E, Nout, Kout):
+    torch.manual_seed(E)
+    dy, x = torch.randn(E, Nout, device=DEV) + 0.3, torch.randn(E, Kout, device=DEV)
+    dw, db = ops.wgrad_tf32x3(dy, x, with_bias=True)
+    assert rel_err(db, dy.double().sum(0).cpu().numpy()) < 2e-6
+    assert torch.equal(dw, ops.wgrad_tf32x3(dy, x))
