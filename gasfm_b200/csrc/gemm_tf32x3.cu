@@ -121,7 +121,7 @@ __device__ __forceinline__ float tf32_hi(float x) {
 }
 
 struct GemmArgs {
-  const float* A; int64_t lda; const float* bias; float* C; int64_t ldc; int64_t M; int N; int K; int tmem_cols; int accumulate;
+  const float* A; int64_t lda; const float* bias; float* C; int64_t ldc; int64_t M; int N; int K; int tmem_cols; int accumulate; int debug;
 };
 
 // CTA pairs (cluster of 2): the weight tiles B_hi / B_lo are identical for every M tile, and re-streaming them
@@ -131,12 +131,14 @@ struct GemmArgs {
 constexpr int kCluster = 2;
 template <int kDummy>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, GemmArgs p) {
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+                   const __grid_constant__ CUtensorMap map_c, GemmArgs p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stage][A_hi 16K | A_lo 16K | B_hi N*128 | B_lo N*128], all 1024-aligned (N*128 is a multiple of 1024 for N%8==0)
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_tile_bytes = p.N * kBlockK * 4;
   const int stage_bytes = 2 * kATileBytes + 2 * b_tile_bytes;
+  uint8_t* c_stage = smem + (size_t)kStages * stage_bytes;      // 4 epilogue warps x [32 rows x 128 B], 1024-aligned
   __shared__ uint64_t full_bar[kStages], split_bar[kStages], empty_bar[kStages], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float bias_s[256];
@@ -178,6 +180,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_con
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);                 // both CTAs have retired the MMAs of this stage
           uint8_t* st = smem + (size_t)stage * stage_bytes;
+          if (p.debug & 4) { mbar_arrive(&full_bar[stage]); if (++stage == kStages) { stage = 0; phase ^= 1; } continue; }
           mbar_expect_tx(&full_bar[stage], 2 * b_tile_bytes);      // halves from both CTAs land here
           tma_load_2d_mc(st + 2 * kATileBytes + cta_rank * half_bytes, &map_bhi, &full_bar[stage], kb * kBlockK,
                          (int)cta_rank * half_rows, (uint16_t)((1u << kCluster) - 1));
@@ -208,6 +211,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_con
           const uint32_t b_lo = b_hi + b_tile_bytes;
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            if (p.debug & 2) break;
             const uint32_t koff = k * kUmmaK * 4;   // bytes along K inside the 128-byte swizzle row
             const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
             umma_tf32(d_tmem, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, first);
@@ -237,7 +241,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_con
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int64_t row = tile * kBlockM + rg + 32 * i;
-        v[i] = (g < total && row < p.M && kcol < p.K) ? ld_stream4(p.A + row * p.lda + kcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = (g < total && row < p.M && kcol < p.K && !(p.debug & 8)) ? ld_stream4(p.A + row * p.lda + kcol) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
 #pragma unroll
@@ -275,8 +279,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_con
       const int64_t tile = (cluster_id + it * num_clusters) * kCluster + cta_rank;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int64_t row = tile * kBlockM + quarter * 32 + lane;
-      float* crow = p.C + row * p.ldc;
+      const int row0 = (int)(tile * kBlockM) + quarter * 32;       // first C row of this warp's 32-row slab
+      uint8_t* stg = c_stage + (warp - 10) * 4096;
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * acc_cols) + ((uint32_t)(quarter * 32) << 16);
       for (int c0 = 0; c0 < p.N; c0 += 32) {
         uint32_t r[32];
@@ -289,28 +293,40 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_con
               "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr0 + (uint32_t)c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < p.M) {
+        // the previous chunk's bulk store must have finished READING the staging tile
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        // lane = row: write its 8 float4 into the 128B-swizzled tile (chunk ^= row % 8): conflict-free, and the
+        // layout a SWIZZLE_128B tensor map expects.  One TMA bulk store then writes 32 full 128-byte lines
+        // (rows >= M and columns >= N are clipped by the tensor map), instead of 32 x 16-byte pieces per instruction.
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (c0 + j < p.N) {
-              float4 v;
-              v.x = __uint_as_float(r[j]) + bias_s[c0 + j];
-              v.y = __uint_as_float(r[j + 1]) + bias_s[c0 + j + 1];
-              v.z = __uint_as_float(r[j + 2]) + bias_s[c0 + j + 2];
-              v.w = __uint_as_float(r[j + 3]) + bias_s[c0 + j + 3];
-              if (p.accumulate) {                      // C += A W^T: sums the input gradients of projections that share x
-                const float4 o = *reinterpret_cast<const float4*>(crow + c0 + j);
-                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-              }
-              *reinterpret_cast<float4*>(crow + c0 + j) = v;
-            }
-          }
+        for (int j = 0; j < 32; j += 4) {
+          float4 v;
+          v.x = __uint_as_float(r[j]) + bias_s[(c0 + j) & 255];
+          v.y = __uint_as_float(r[j + 1]) + bias_s[(c0 + j + 1) & 255];
+          v.z = __uint_as_float(r[j + 2]) + bias_s[(c0 + j + 2) & 255];
+          v.w = __uint_as_float(r[j + 3]) + bias_s[(c0 + j + 3) & 255];
+          *reinterpret_cast<float4*>(stg + lane * 128 + ((((j >> 2) ^ (lane & 7))) << 4)) = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && !(p.debug & 1)) {
+          if (p.accumulate)
+            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map_c),
+                         "r"(smem_u32(stg)), "r"(c0), "r"(row0)
+                         : "memory");
+          else
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&map_c),
+                         "r"(smem_u32(stg)), "r"(c0), "r"(row0)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&tmem_empty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk stores complete before exit
   }
   __syncthreads();
   cluster_sync();                            // no CTA leaves while its peer may still multicast into its shared memory
@@ -610,11 +626,12 @@ extern "C" int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_h
   GASFM_REQUIRE(gasfm_linear_tf32x3_supported(M, N, K, lda, ldc), "linear_tf32x3: unsupported shape M=%lld N=%d K=%d lda=%lld ldc=%lld",
                 (long long)M, N, K, (long long)lda, (long long)ldc);
   GASFM_REQUIRE(((uintptr_t)A | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C) % 16 == 0, "linear_tf32x3: pointers must be 16-byte aligned");
-  CUtensorMap mh, ml;
-  if (make_map(&mh, B_hi, N, K, K, N / kCluster) || make_map(&ml, B_lo, N, K, K, N / kCluster)) return 1;
+  CUtensorMap mh, ml, mc;
+  if (make_map(&mh, B_hi, N, K, K, N / kCluster) || make_map(&ml, B_lo, N, K, K, N / kCluster) ||
+      make_map_box(&mc, C, M, N, ldc, 32, 32)) return 1;
   int tmem_cols = 32;
   while (tmem_cols < 2 * N) tmem_cols <<= 1;
-  const size_t smem = (size_t)kStages * (2 * kATileBytes + 2 * (size_t)N * kBlockK * 4) + 1024;
+  const size_t smem = (size_t)kStages * (2 * kATileBytes + 2 * (size_t)N * kBlockK * 4) + 4 * 4096 + 1024;
   static size_t smem_allowed = 0;   // static smem (barriers, bias) also counts against the 227 KB per-CTA limit
   if (smem > smem_allowed) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -627,8 +644,10 @@ extern "C" int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_h
   const int64_t tiles = (M + kBlockM - 1) / kBlockM;
   const int64_t pairs = (tiles + kCluster - 1) / kCluster;
   const int grid = (int)(pairs < kNumSMs / kCluster ? pairs : kNumSMs / kCluster) * kCluster;
-  GemmArgs args{A, lda, bias, C, ldc, M, N, K, tmem_cols, accumulate};
-  gemm_tf32x3_kernel<0><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(mh, ml, args);
+  static int debug = -1;
+  if (debug < 0) { const char* env = getenv("GASFM_GEMM_DEBUG"); debug = env ? atoi(env) : 0; }   // phase-isolation knob for profiling
+  GemmArgs args{A, lda, bias, C, ldc, M, N, K, tmem_cols, accumulate, debug};
+  gemm_tf32x3_kernel<0><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(mh, ml, mc, args);
   return check_launch("linear_tf32x3");
 }
 

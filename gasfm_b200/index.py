@@ -88,7 +88,7 @@ class ObservationIndex:
         self.csc_perm = torch.empty(E, **i32)
         status = torch.zeros(1, **i32)
         ws = torch.empty(_lib.size_query("gasfm_csr_build_ws_bytes", E, self.n) // 4 + 1, **i32)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.call("gasfm_csr_build", _lib.ptr(indices), E, self.m, self.n, _lib.ptr(self.row_idx),
                       _lib.ptr(self.col_idx), _lib.ptr(self.row_ptr), _lib.ptr(self.col_ptr),
                       _lib.ptr(self.csc_perm), _lib.ptr(status), _lib.ptr(ws), _lib.stream_ptr())
@@ -117,7 +117,7 @@ class ObservationIndex:
             total = self.m if kind == "view" else self.n
             seg_ptr = torch.tensor([0, k], dtype=torch.int32, device=dev)
             perm = None if k == total else valid_ids.to(torch.int32)
-            with torch.cuda.device(dev):
+            with _lib.device_guard(dev):
                 plan = SegmentPlan(seg_ptr, perm, 1, k, single_segment_chunk(k), dev)
             plan.covers_all = perm is None
             self._global_plans[key] = plan
@@ -136,7 +136,7 @@ def plan_from_targets(dst, n_targets):
     row_ptr, col_ptr = torch.empty(E + 1, **i32), torch.empty(n_targets + 1, **i32)
     perm, status = torch.empty(E, **i32), torch.zeros(1, **i32)
     ws = torch.empty(_lib.size_query("gasfm_csr_build_ws_bytes", E, int(n_targets)) // 4 + 1, **i32)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gasfm_csr_build", _lib.ptr(pairs), E, max(E, 1), int(n_targets), _lib.ptr(row_idx), _lib.ptr(col_idx),
                   _lib.ptr(row_ptr), _lib.ptr(col_ptr), _lib.ptr(perm), _lib.ptr(status), _lib.ptr(ws), _lib.stream_ptr())
         if int(status.item()) != 0:

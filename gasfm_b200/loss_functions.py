@@ -18,7 +18,7 @@ class _EsfmLoss(torch.autograd.Function):
         E, n, dev = obs.shape[0], pts3D.shape[1], obs.device
         out = torch.empty(2, dtype=torch.float32, device=dev)
         ws = torch.empty(max(1, _lib.size_query("gasfm_esfm_loss_ws_bytes", E) // 4), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.call("gasfm_esfm_loss_fwd", _lib.ptr(Ps), _lib.ptr(pts3D), n, _lib.ptr(obs), _lib.ptr(index.row_idx),
                       _lib.ptr(index.col_idx), E, float(margin), int(hinge), float(hinge_weight), _lib.ptr(out), _lib.ptr(ws),
                       _lib.stream_ptr())
@@ -34,7 +34,7 @@ class _EsfmLoss(torch.autograd.Function):
         E, n, dev = obs.shape[0], pts3D.shape[1], obs.device
         G = torch.empty((E, 16), dtype=torch.float32, device=dev)
         up = d_loss.reshape(1).to(torch.float32).contiguous()
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.call("gasfm_esfm_loss_bwd", _lib.ptr(Ps), _lib.ptr(pts3D), n, _lib.ptr(obs), _lib.ptr(index.row_idx),
                       _lib.ptr(index.col_idx), E, margin, hinge, hinge_weight, _lib.ptr(up), _lib.ptr(stats), grad_mode,
                       _lib.ptr(G), _lib.stream_ptr())

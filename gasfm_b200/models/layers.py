@@ -18,7 +18,7 @@ from torch import nn
 from torch.nn import ReLU, Sequential, Module, Identity
 from torch.nn import functional as F
 
-from .. import ops
+from .. import _lib, ops
 from ..index import SegmentPlan, index_for, single_segment_chunk
 from ..utils.sparse_utils import SparseMat
 from ..utils import sparse_utils
@@ -110,7 +110,7 @@ def plan_for(graph_wrapper, proj_features=None):
             n_src = graph_wrapper.m if graph_wrapper.agg_dim == 0 else graph_wrapper.n
             seg_ptr = torch.tensor([0, k], dtype=torch.int32, device=dev)
             perm = None if k == n_src else ids.to(torch.int32).contiguous()
-            with torch.cuda.device(dev):
+            with _lib.device_guard(dev):
                 plan = SegmentPlan(seg_ptr, perm, 1, k, single_segment_chunk(k), dev)
             setattr(graph_wrapper, _PLAN_ATTR, plan)
         plan.shard = getattr(graph_wrapper, "shard", None)     # set for track-sharded scenes (gasfm_b200.dist)

@@ -52,7 +52,7 @@ class _GatEdge(torch.autograd.Function):
         ws = None
         if plan.chunk > 0:
             ws = plan.workspace(_lib.size_query("gasfm_gat_ws_bytes", plan.max_chunks, heads, head_dim), dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.call("gasfm_gat_edge_fwd", _lib.ptr(XL), ldxl, _lib.ptr(XR), ldxr, _lib.ptr(att_flat), _lib.ptr(bias),
                       *plan.abi_args(), heads, head_dim, LEAKY_SLOPE, 1,
                       _lib.ptr(out), _lib.ptr(seg_max), _lib.ptr(seg_sum), _lib.ptr(ws), _lib.stream_ptr())
@@ -75,7 +75,7 @@ class _GatEdge(torch.autograd.Function):
         datt = torch.empty(hc, dtype=torch.float32, device=dev)
         ws = plan.workspace(_lib.size_query("gasfm_gat_bwd_ws_bytes", XL.shape[0], plan.n_seg, plan.max_chunks,
                                             heads, head_dim), dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.call("gasfm_gat_edge_bwd", _lib.ptr(XL), XL.stride(0) if XL.shape[0] > 1 else hc, _lib.ptr(XR),
                       0 if ctx.bcast else hc, _lib.ptr(att_flat), _lib.ptr(out_nobias), _lib.ptr(seg_max),
                       _lib.ptr(seg_sum), _lib.ptr(d_out), *plan.abi_args(), heads, head_dim, LEAKY_SLOPE,
@@ -112,7 +112,7 @@ def gat_edge_partial(XL, XR, att, plan: SegmentPlan, heads: int):
     ws = None
     if plan.chunk > 0:
         ws = plan.workspace(_lib.size_query("gasfm_gat_ws_bytes", plan.max_chunks, heads, head_dim), dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gasfm_gat_edge_fwd", _lib.ptr(XL), ldxl, _lib.ptr(XR), 0 if bcast else hc, _lib.ptr(att_flat), None,
                   *plan.abi_args(), heads, head_dim, LEAKY_SLOPE, 0,
                   _lib.ptr(out), _lib.ptr(seg_max), _lib.ptr(seg_sum), _lib.ptr(ws), _lib.stream_ptr())
@@ -133,7 +133,7 @@ def gat_edge_backward_raw(XL, XR, att, out_nobias, seg_max, seg_sum, d_out, plan
     datt = torch.empty(hc, dtype=torch.float32, device=dev)
     ws = plan.workspace(_lib.size_query("gasfm_gat_bwd_ws_bytes", XL.shape[0], plan.n_seg, plan.max_chunks,
                                         heads, head_dim), dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gasfm_gat_edge_bwd", _lib.ptr(XL), ldxl, _lib.ptr(XR.contiguous()), 0 if bcast else hc,
                   _lib.ptr(att.reshape(-1).contiguous()), _lib.ptr(out_nobias.contiguous()),
                   _lib.ptr(seg_max.contiguous()), _lib.ptr(seg_sum.contiguous()), _lib.ptr(d_out.contiguous()),
@@ -160,7 +160,7 @@ class _LnRelu(torch.autograd.Function):
             gamma, beta = gamma.contiguous(), beta.contiguous()
             mean = torch.empty(E, dtype=torch.float32, device=dev)
             rstd = torch.empty(E, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.call("gasfm_ln_relu_fwd", _lib.ptr(x), E, w, _lib.ptr(gamma), _lib.ptr(beta), float(eps),
                       _lib.ptr(y), _lib.ptr(mean), _lib.ptr(rstd), _lib.stream_ptr())
         ctx.save_for_backward(x, y, mean, rstd, gamma)
@@ -179,7 +179,7 @@ class _LnRelu(torch.autograd.Function):
             dbeta = torch.empty(w, dtype=torch.float32, device=dev)
             ws = torch.empty(max(1, _lib.size_query("gasfm_ln_relu_bwd_ws_bytes", E, w) // 4),
                              dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.call("gasfm_ln_relu_bwd", _lib.ptr(dy), _lib.ptr(x), _lib.ptr(y), _lib.ptr(mean), _lib.ptr(rstd),
                       _lib.ptr(gamma), E, w, _lib.ptr(dx), _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(ws),
                       _lib.stream_ptr())
@@ -203,7 +203,7 @@ def seg_sum_raw(X, plan: SegmentPlan, scale=1.0, mean=False):
     ws = None
     if plan.chunk > 0:
         ws = plan.workspace(_lib.size_query("gasfm_seg_sum_ws_bytes", plan.max_chunks, w), dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gasfm_seg_sum", _lib.ptr(X), ldx, w, *plan.abi_args(), float(scale), int(mean),
                   _lib.ptr(out), _lib.ptr(ws), _lib.stream_ptr())
     return out
@@ -221,7 +221,7 @@ class _SegPool(torch.autograd.Function):
         w = d_out.shape[1]
         dev = d_out.device
         dX = torch.empty((ctx.n_rows, w), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.call("gasfm_seg_bcast", _lib.ptr(d_out), w, _lib.ptr(ctx.seg_of_edge), _lib.ptr(ctx.plan.seg_ptr),
                       ctx.n_rows, float(ctx.scale), int(ctx.mean), _lib.ptr(dX), _lib.stream_ptr())
         return dX, None, None, None, None
@@ -254,7 +254,7 @@ class _EdgeUpdate(torch.autograd.Function):
         V = None if V is None else V.contiguous()
         g = None if g is None else g.contiguous()
         out = torch.empty((E, w), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.call("gasfm_edge_update_fwd", _lib.ptr(P), ldp, _lib.ptr(x0), d0, _lib.ptr(W0), _lib.ptr(S), _lib.ptr(V),
                       _lib.ptr(g), _lib.ptr(skip), ldskip, _lib.ptr(index.row_idx), _lib.ptr(index.col_idx), E, w,
                       float(pscale), float(scale), _lib.ptr(out), _lib.stream_ptr())
@@ -283,7 +283,7 @@ class _EdgeUpdate(torch.autograd.Function):
                 dx0 = torch.empty((E, d0), dtype=torch.float32, device=d_out.device)
                 dW0 = torch.empty((w, d0), dtype=torch.float32, device=d_out.device)
                 ws = torch.empty(max(1, _lib.size_query("gasfm_x0_bwd_ws_bytes", E, w) // 4), dtype=torch.float32, device=d_out.device)
-                with torch.cuda.device(d_out.device):
+                with _lib.device_guard(d_out.device):
                     _lib.call("gasfm_x0_bwd", _lib.ptr(d_out), E, w, _lib.ptr(x0), _lib.ptr(W0), d0, float(scale),
                               _lib.ptr(dx0), _lib.ptr(dW0), _lib.ptr(ws), _lib.stream_ptr())
             else:
@@ -302,7 +302,7 @@ def edge_update(P, x0, W0, S, V, g, skip, index, pscale=1.0, scale=0.25):
 def _split_tf32(w):
     w = w.contiguous()
     hi, lo = torch.empty_like(w), torch.empty_like(w)
-    with torch.cuda.device(w.device):
+    with _lib.device_guard(w.device):
         _lib.call("gasfm_split_tf32", _lib.ptr(w), _lib.ptr(hi), _lib.ptr(lo), w.numel(), _lib.stream_ptr())
     return hi, lo
 
@@ -319,7 +319,7 @@ def gemm_tf32x3(a, b, bias=None, out=None, accumulate=False):
     N = b.shape[0]
     hi, lo = _split_tf32(b)
     c = torch.empty((M, N), dtype=torch.float32, device=a.device) if out is None else out
-    with torch.cuda.device(a.device):
+    with _lib.device_guard(a.device):
         _lib.call("gasfm_linear_tf32x3", _lib.ptr(a), lda, _lib.ptr(hi), _lib.ptr(lo),
                   _lib.ptr(None if bias is None else bias.contiguous()), _lib.ptr(c), N, M, N, K, int(bool(accumulate)),
                   _lib.stream_ptr())
@@ -346,7 +346,7 @@ def wgrad_tf32x3(dy, x, with_bias=False):
     small = _lib.load().gasfm_wgrad_small_supported(n_out, k_out, lddy, ldx)
     name = "gasfm_wgrad_small" if small else "gasfm_wgrad_tf32x3"
     ws = torch.empty(_lib.size_query(name + "_ws_bytes", n_out, k_out) // 4, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call(name, _lib.ptr(dy), lddy, _lib.ptr(x), ldx, E, n_out, k_out, _lib.ptr(dw), _lib.ptr(db), _lib.ptr(ws),
                   _lib.stream_ptr())
     return (dw, db) if with_bias else dw

@@ -27,7 +27,7 @@ def _valid_and_counts(M):
     cam_per_pts = torch.empty(n, dtype=torch.int64, device=dev)
     pts_per_cam = torch.empty(m, dtype=torch.int64, device=dev)
     n_obs = torch.empty(1, dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gasfm_m2sparse_count", _lib.ptr(Mg), m, n, MIN_N_VIEWS_PER_POINT, _lib.ptr(valid),
                   _lib.ptr(cam_per_pts), _lib.ptr(pts_per_cam), _lib.ptr(n_obs), _lib.stream_ptr())
     return Mg, valid, cam_per_pts, pts_per_cam, int(n_obs.item())
@@ -55,7 +55,7 @@ def M2sparse(M, normalize=False, Ns=None):
         assert Ns is not None
         Ng = Ns.to(device=dev, dtype=torch.float32).contiguous()
     ws = torch.empty(max(1, _lib.size_query("gasfm_m2sparse_ws_bytes", m, n) // 8), dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.device_guard(dev):
         _lib.call("gasfm_m2sparse_fill", _lib.ptr(Mg), _lib.ptr(Ng), _lib.ptr(valid), m, n, E, _lib.ptr(indices),
                   _lib.ptr(values), _lib.ptr(ws), _lib.stream_ptr())
     out = SparseMat(values, indices, cam_per_pts.unsqueeze(1), pts_per_cam.unsqueeze(1), (m, n, 2))
