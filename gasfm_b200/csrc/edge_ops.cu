@@ -444,6 +444,75 @@ __global__ void __launch_bounds__(256) edge_update_kernel(EdgeUpdArgs p) {
   V::st(p.out + e * p.width + c, a);
 }
 
+// Fast path (width % 4 == 0): LPR lanes per observation row, every lane owns NV float4 of the row; W0 columns
+// and the global term live in registers, row / col ids are read once per row, two rows are in flight per group.
+template <int LPR, int NV>
+__global__ void __launch_bounds__(256, 2) edge_update_rows_kernel(EdgeUpdArgs p) {
+  constexpr int RPW = 32 / LPR;
+  constexpr int U = 2;
+  const int lane = threadIdx.x & 31;
+  const int lir = lane % LPR, grp = lane / LPR;
+  const int nvec = p.width / 4;
+  float4 gl[NV], w0[NV][4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int vi = lir + LPR * v;
+    gl[v] = (p.g && vi < nvec) ? ld4(p.g + 4 * vi) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      w0[v][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < p.d0 && vi < nvec) {
+        const float* wp = p.W0 + (int64_t)(4 * vi) * p.d0 + q;
+        w0[v][q] = make_float4(wp[0], wp[p.d0], wp[2 * p.d0], wp[3 * p.d0]);
+      }
+    }
+  }
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t stride = ((int64_t)gridDim.x * blockDim.x >> 5) * RPW;
+  for (int64_t e0 = warp * RPW + grp; e0 < p.n_obs; e0 += stride * U) {
+    float4 pv[U][NV], sk[U][NV], sv[U][NV], vv[U][NV];
+    float x0v[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t e = e0 + u * stride;
+      const bool ok = e < p.n_obs;
+      const int64_t ec = ok ? e : e0;
+      const int col = p.S ? __ldg(p.col_idx + ec) : 0, row = p.V ? __ldg(p.row_idx + ec) : 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x0v[u][q] = (q < p.d0) ? __ldg(p.x0 + ec * p.d0 + q) : 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int vi = lir + LPR * v;
+        const bool on = vi < nvec;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        pv[u][v] = on ? ld_stream4(p.P + ec * p.ldp + 4 * vi) : z;
+        sk[u][v] = (on && p.skip) ? ld_stream4(p.skip + ec * p.ldskip + 4 * vi) : z;
+        sv[u][v] = (on && p.S) ? ld4(p.S + (int64_t)col * p.width + 4 * vi) : z;
+        vv[u][v] = (on && p.V) ? ld4(p.V + (int64_t)row * p.width + 4 * vi) : z;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t e = e0 + u * stride;
+      if (e >= p.n_obs) continue;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int vi = lir + LPR * v;
+        if (vi >= nvec) continue;
+        float4 a;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float t = comp(sv[u][v], k) + comp(vv[u][v], k) + comp(gl[v], k);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) t = fmaf(x0v[u][q], comp(w0[v][q], k), t);
+          comp(a, k) = fmaf(p.pscale, comp(pv[u][v], k), p.scale * t) + comp(sk[u][v], k);
+        }
+        st_stream4(p.out + e * p.width + 4 * vi, a);
+      }
+    }
+  }
+}
+
 }  // namespace gasfm
 
 using namespace gasfm;
@@ -559,9 +628,20 @@ extern "C" int gasfm_edge_update_fwd(const float* P, int64_t ldp, const float* x
   EdgeUpdArgs a{P, ldp, d0 > 0 ? x0 : nullptr, d0, W0, S, V, g, skip, ldskip, row_idx, col_idx, n_obs, width, pscale, scale, out};
   const bool vec4 = width % 4 == 0 && ldp % 4 == 0 && (!skip || ldskip % 4 == 0) &&
                     ((uintptr_t)P | (uintptr_t)S | (uintptr_t)V | (uintptr_t)g | (uintptr_t)skip | (uintptr_t)out) % 16 == 0;
-  if (vec4)
+  if (vec4 && width <= 1024) {
+    const int nvec = width / 4;
+    int64_t cap = (int64_t)kNumSMs * 16;
+#define CALL_EU(VEC, LPR, NV)                                                                          \
+    do {                                                                                               \
+      int64_t need = (n_obs + (32 / LPR) * 8 * 2 - 1) / ((32 / LPR) * 8 * 2);                          \
+      edge_update_rows_kernel<LPR, NV><<<(int)(need < cap ? (need < 1 ? 1 : need) : cap), 256, 0, st>>>(a); \
+    } while (0)
+    GASFM_ROW_DISPATCH(4, nvec, CALL_EU);
+#undef CALL_EU
+  } else if (vec4) {
     edge_update_kernel<4><<<ceil_div(n_obs * (width / 4), 256), 256, 0, st>>>(a);
-  else
+  } else {
     edge_update_kernel<1><<<ceil_div(n_obs * width, 256), 256, 0, st>>>(a);
+  }
   return check_launch("edge_update_fwd");
 }

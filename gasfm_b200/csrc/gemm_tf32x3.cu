@@ -553,8 +553,22 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
   }
 }
 
-// out[i] = sum_r ws[r, i] for i < width (width = Nout*Kout), deterministic
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int rows, int64_t width, float* __restrict__ out) {
+// out[i] = sum_r ws[r, i] for i < width (width = Nout*Kout), deterministic; the last blocks do the same for the
+// bias-gradient partials (ws2 / width2 / out2) so that dW and db need one launch
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int rows, int64_t width, float* __restrict__ out,
+                                                           const float* __restrict__ ws2, int64_t width2, float* __restrict__ out2,
+                                                           int blocks1) {
+  if ((int)blockIdx.x >= blocks1) {
+    const int64_t j = ((int64_t)(blockIdx.x - blocks1) * blockDim.x + threadIdx.x) * 4;
+    if (j >= width2) return;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < rows; ++r) {
+      const float4 v = *reinterpret_cast<const float4*>(ws2 + (int64_t)r * width2 + j);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out2 + j) = a;
+    return;
+  }
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= width) return;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -695,7 +709,7 @@ extern "C" int gasfm_wgrad_tf32x3(const float* dY, int64_t lddy, const float* X,
   int rc = check_launch("wgrad_tf32x3");
   if (rc) return rc;
   const int64_t width = (int64_t)Nout * Kout;
-  wgrad_reduce_kernel<<<ceil_div(width / 4, 256), 256, 0, st>>>((const float*)ws, grid, width, dW);
-  if (dbias) wgrad_reduce_kernel<<<ceil_div(Nout / 4, 256), 256, 0, st>>>(ws_db, grid, Nout, dbias);
+  const int blocks1 = ceil_div(width / 4, 256), blocks2 = dbias ? ceil_div(Nout / 4, 256) : 0;
+  wgrad_reduce_kernel<<<blocks1 + blocks2, 256, 0, st>>>((const float*)ws, grid, width, dW, ws_db, Nout, dbias, blocks1);
   return check_launch("wgrad_tf32x3(reduce)");
 }

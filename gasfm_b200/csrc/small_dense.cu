@@ -114,55 +114,69 @@ __global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restric
 
 // ---- x0 backward ------------------------------------------------------------------------------------
 constexpr int kX0Threads = 256;
-template <int LPR, int NV>
+template <int LPR, int NV, int D0>
 __global__ void __launch_bounds__(kX0Threads) x0_bwd_kernel(const float* __restrict__ dOut, int64_t E, int width,
-                                                            const float* __restrict__ x0, const float* __restrict__ W0, int d0,
+                                                            const float* __restrict__ x0, const float* __restrict__ W0,
                                                             float scale, float* __restrict__ dx0, float* __restrict__ ws) {
   constexpr int RPW = 32 / LPR;
   constexpr int NW = kX0Threads / 32;
+  constexpr int U = 2;                                        // rows in flight per lane group
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int lir = lane % LPR, grp = lane / LPR;
   const unsigned mask = group_mask<LPR>(lane);
   const int nvec = width / 4;
-  // W0 rows of this lane's channels, and the dW0 accumulators: [NV][4 channels][4 (d0 <= 4)]
-  float w[NV][4][4], dw[NV][4][4];
+  // W0 rows of this lane's channels, and the dW0 accumulators: [NV][4 channels][D0]
+  float w[NV][4][D0], dw[NV][4][D0];
 #pragma unroll
   for (int v = 0; v < NV; ++v)
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < D0; ++q) {
         const int c = 4 * (lir + LPR * v) + k;
-        w[v][k][q] = (lir + LPR * v < nvec && q < d0) ? W0[(int64_t)c * d0 + q] : 0.f;
+        w[v][k][q] = (lir + LPR * v < nvec) ? W0[(int64_t)c * D0 + q] : 0.f;
         dw[v][k][q] = 0.f;
       }
   const int64_t stride = (int64_t)gridDim.x * NW * RPW;
-  for (int64_t row = ((int64_t)blockIdx.x * NW + wid) * RPW + grp; row < E; row += stride) {
-    float xr[4], s[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t row0 = ((int64_t)blockIdx.x * NW + wid) * RPW + grp; row0 < E; row0 += stride * U) {
+    float4 g[U][NV];
+    float xr[U][D0];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) xr[q] = q < d0 ? __ldg(x0 + row * d0 + q) : 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + u * stride;
+      const bool ok = row < E;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      if (lir + LPR * v < nvec) {
-        const float4 g = ld_stream4(dOut + row * width + 4 * (lir + LPR * v));
+      for (int q = 0; q < D0; ++q) xr[u][q] = ok ? __ldg(x0 + row * D0 + q) : 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        g[u][v] = (ok && lir + LPR * v < nvec) ? ld_stream4(dOut + row * width + 4 * (lir + LPR * v)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float s[D0];
+#pragma unroll
+      for (int q = 0; q < D0; ++q) s[q] = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float gk = comp(g, k);
+          const float gk = comp(g[u][v], k);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < D0; ++q) {
             s[q] = fmaf(gk, w[v][k][q], s[q]);
-            dw[v][k][q] = fmaf(gk, xr[q], dw[v][k][q]);
+            dw[v][k][q] = fmaf(gk, xr[u][q], dw[v][k][q]);
           }
         }
+#pragma unroll
+      for (int q = 0; q < D0; ++q) {
+#pragma unroll
+        for (int off = LPR / 2; off > 0; off >>= 1) s[q] += __shfl_xor_sync(mask, s[q], off);
       }
-    }
+      const int64_t row = row0 + u * stride;
+      if (lir == 0 && row < E) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-#pragma unroll
-      for (int off = LPR / 2; off > 0; off >>= 1) s[q] += __shfl_xor_sync(mask, s[q], off);
-    }
-    if (lir == 0) {
-      for (int q = 0; q < d0; ++q) dx0[row * d0 + q] = scale * s[q];
+        for (int q = 0; q < D0; ++q) dx0[row * D0 + q] = scale * s[q];
+      }
     }
   }
   // dW0: groups -> warp -> CTA -> workspace row [width * 4]
@@ -175,10 +189,12 @@ __global__ void __launch_bounds__(kX0Threads) x0_bwd_kernel(const float* __restr
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) dw[v][k][q] += __shfl_xor_sync(0xffffffffu, dw[v][k][q], off);
+          for (int q = 0; q < D0; ++q) dw[v][k][q] += __shfl_xor_sync(0xffffffffu, dw[v][k][q], off);
   }
   extern __shared__ float sm[];   // [NW][width*4]
   const int W4 = width * 4;
+  for (int j = threadIdx.x; j < NW * W4; j += kX0Threads) sm[j] = 0.f;
+  __syncthreads();
   if (grp == 0) {
 #pragma unroll
     for (int v = 0; v < NV; ++v)
@@ -186,7 +202,7 @@ __global__ void __launch_bounds__(kX0Threads) x0_bwd_kernel(const float* __restr
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) sm[wid * W4 + (4 * (lir + LPR * v) + k) * 4 + q] = dw[v][k][q];
+          for (int q = 0; q < D0; ++q) sm[wid * W4 + (4 * (lir + LPR * v) + k) * 4 + q] = dw[v][k][q];
       }
   }
   __syncthreads();
@@ -210,7 +226,7 @@ __global__ void x0_bwd_reduce_kernel(const float* __restrict__ ws, int rows, int
 
 static int x0_blocks(int64_t E) {
   int64_t need = (E + 63) / 64;
-  int64_t cap = (int64_t)kNumSMs * 4;
+  int64_t cap = (int64_t)kNumSMs * 8;
   return (int)(need < 1 ? 1 : (need < cap ? need : cap));
 }
 
@@ -261,11 +277,20 @@ extern "C" int gasfm_x0_bwd(const float* dOut, int64_t E, int width, const float
   const int blocks = x0_blocks(E);
   const size_t smem = (size_t)(kX0Threads / 32) * width * 4 * sizeof(float);
   const int nvec = width / 4;
-#define CALL_X0(VEC, LPR, NV)                                                                                    \
-  do {                                                                                                           \
-    if (smem > 48 * 1024)                                                                                        \
-      cudaFuncSetAttribute(x0_bwd_kernel<LPR, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-    x0_bwd_kernel<LPR, NV><<<blocks, kX0Threads, smem, st>>>(dOut, E, width, x0, W0, d0, scale, dx0, (float*)ws); \
+#define CALL_X0D(LPR, NV, D0)                                                                                       \
+  do {                                                                                                              \
+    if (smem > 48 * 1024)                                                                                           \
+      cudaFuncSetAttribute(x0_bwd_kernel<LPR, NV, D0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    x0_bwd_kernel<LPR, NV, D0><<<blocks, kX0Threads, smem, st>>>(dOut, E, width, x0, W0, scale, dx0, (float*)ws);   \
+  } while (0)
+#define CALL_X0(VEC, LPR, NV)                          \
+  do {                                                 \
+    switch (d0) {                                      \
+      case 1: CALL_X0D(LPR, NV, 1); break;             \
+      case 2: CALL_X0D(LPR, NV, 2); break;             \
+      case 3: CALL_X0D(LPR, NV, 3); break;             \
+      default: CALL_X0D(LPR, NV, 4); break;            \
+    }                                                  \
   } while (0)
   if (nvec <= 1) CALL_X0(4, 1, 1);
   else if (nvec <= 2) CALL_X0(4, 2, 1);
@@ -276,6 +301,7 @@ extern "C" int gasfm_x0_bwd(const float* dOut, int64_t E, int width, const float
   else if (nvec <= 64) CALL_X0(4, 32, 2);
   else if (nvec <= 128) CALL_X0(4, 32, 4);
   else CALL_X0(4, 32, 8);
+#undef CALL_X0D
 #undef CALL_X0
   int rc = check_launch("x0_bwd");
   if (rc) return rc;
