@@ -146,9 +146,10 @@ def kernel_roofline(cfg, peaks, peak_kind):
     """The hot kernels alone at the workload's shapes (E observations, width d = n_feat_proj), CUDA events.
 
     Edge-attention kernels: HBM-bound; achieved = algorithmic bytes / time over the
-    measured copy bandwidth.  tcgen05 3xTF32 GEMMs: 3 tf32 MMAs per product, so the binding roof at
-    d = 256 is the tensor pipe: achieved = 3 * 2MNK / time over the tf32 rate, taken as half of the
-    measured dense bf16 rate (tf32 runs at half the bf16 MMA rate); their HBM fraction is listed too.
+    measured copy bandwidth.  Projection GEMMs (fwd + dX): the scaled 2 x FP16 split (three kind::f16 MMAs per
+    product at the bf16 rate) leaves them HBM-bound: achieved = (read A + write C) / time; the tensor share is
+    listed as ``tensor_frac``.  Weight gradients (and GASFM_GEMM=tf32x3): 3xTF32, tensor-bound: achieved =
+    3 * 2MNK / time over the tf32 rate, taken as half of the measured dense bf16 rate; HBM fraction listed too.
     Every E-sized operand (E x 256 fp32 = 507 MB) exceeds the 126 MB L2, so launches are cold.
     ``calls_per_step`` x time picks the dominant kernel of the step."""
     from gasfm_b200 import ops
@@ -180,13 +181,18 @@ def kernel_roofline(cfg, peaks, peak_kind):
         del XR, out, dO
     if ops.gemm_tf32x3_supported(E, HC, HC, HC, HC):
         W = torch.randn(HC, HC, device=dev) / HC ** 0.5
-        hi, lo = ops._split_tf32(W)
-        gemm_ms = timed_batches(lambda: ops.gemm_tf32x3(XL, W))
+        gemm_ms = timed_batches(lambda: ops.gemm_tc(XL, W))
         wg_ms = timed_batches(lambda: ops.wgrad_tf32x3(XL, XL))
         n_gemm = 3 * (L - 1) + 2                      # lin_l x2 + lin_proj per stateful block, lin_l x2 in the final update
-        flops = 3 * 2.0 * E * HC * HC
-        res["gemm_tf32x3 (fwd + dX)"] = dict(bound="tensor", ms=gemm_ms, work=flops, calls=2 * n_gemm, hbm_bytes=2 * E * HC * 4)
-        res["wgrad_tf32x3 (dW)"] = dict(bound="tensor", ms=wg_ms, work=flops, calls=n_gemm, hbm_bytes=2 * E * HC * 4)
+        flops = 3 * 2.0 * E * HC * HC                 # three split products
+        io_bytes = 2 * E * HC * 4                     # read A once, write C once (weights stay in L2)
+        if ops.GEMM_KIND == "f16x2" and ops.gemm_f16x2_supported(E, HC, HC, HC, HC):
+            # scaled 2 x FP16 split: the tensor time is half the 3xTF32 kernel's, the kernel is HBM-bound
+            res["gemm_f16x2 (fwd + dX)"] = dict(bound="hbm", ms=gemm_ms, work=io_bytes, calls=2 * n_gemm,
+                                                tensor_frac=flops / gemm_ms / 1e9 / (2.0 * peak_tf32))
+        else:
+            res["gemm_tf32x3 (fwd + dX)"] = dict(bound="tensor", ms=gemm_ms, work=flops, calls=2 * n_gemm, hbm_bytes=io_bytes)
+        res["wgrad_tf32x3 (dW)"] = dict(bound="tensor", ms=wg_ms, work=flops, calls=n_gemm, hbm_bytes=io_bytes)
     for v in res.values():
         if v["bound"] == "hbm":
             v["achieved"], v["peak"], v["unit"] = v["work"] / v["ms"] / 1e6, peak_gbs, "GB/s"
@@ -202,7 +208,9 @@ def kernel_roofline(cfg, peaks, peak_kind):
             "algorithmic_work_per_launch": d["work"], "ms_per_launch": round(d["ms"], 4),
             "all_kernels": {k: {"bound": v["bound"], "ms": round(v["ms"], 4), "calls_per_step": v["calls"],
                                 "achieved": round(v["achieved"], 1), "unit": v["unit"], "frac": round(v["frac"], 4),
-                                **({"hbm_frac": v["hbm_frac"]} if "hbm_frac" in v else {})} for k, v in res.items()}}
+                                **({"hbm_frac": v["hbm_frac"]} if "hbm_frac" in v else {}),
+                                **({"tensor_frac": round(v["tensor_frac"], 4)} if "tensor_frac" in v else {})}
+                            for k, v in res.items()}}
     return roof
 
 

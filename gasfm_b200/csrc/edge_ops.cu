@@ -1,6 +1,7 @@
 // Per-observation feature kernels: LayerNorm+ReLU, gather-add update, segment pooling (sm_100a).
 // All of them are single-pass, HBM-bound streams over [E, width] fp32 matrices.
 #include "common.cuh"
+#include "col_reduce.cuh"
 #include "../../include/gasfm_b200.h"
 
 namespace gasfm {
@@ -269,70 +270,102 @@ __global__ void __launch_bounds__(256) ln_relu_fwd_kernel(LnArgs p) {
 }
 
 struct LnBwdArgs {
-  const float* dy; const float* x; const float* y; const float* mean; const float* rstd; const float* gamma;
+  const float* dy; const float* x; const float* mean; const float* rstd; const float* gamma; const float* beta;
+  const float* add;   // optional [n_rows, width]: dx += add (gradient of a residual branch that also reads x)
   int64_t n_rows; int width; float* dx; float* ws;   // ws: [blocks, 2*width] partial dgamma | dbeta
 };
-constexpr int kLnBwdThreads = 256;
 
+constexpr int kLnBwdThreads = 256;
+// rows in flight per lane group (all their loads are issued before the first shuffle); wide rows already
+// carry enough loads per lane, and their accumulators need the registers
+constexpr int ln_bwd_unroll(int nv) { return nv <= 2 ? 2 : 1; }
+
+// The ReLU mask is recomputed from x (same expression as the forward kernel, so the same sign) instead of
+// reading y back: dy, x, [add] in, dx out.
 template <int VEC, int LPR, int NV>
-__global__ void __launch_bounds__(kLnBwdThreads) ln_relu_bwd_kernel(LnBwdArgs p) {
+__global__ void __launch_bounds__(kLnBwdThreads, NV <= 2 ? 2 : 1) ln_relu_bwd_kernel(LnBwdArgs p) {
   using V = VecT<VEC>;
   constexpr int RPW = 32 / LPR;
   constexpr int NW = kLnBwdThreads / 32;
+  constexpr int U = ln_bwd_unroll(NV);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int lir = lane % LPR, grp = lane / LPR;
   const unsigned mask = group_mask<LPR>(lane);
   const int nvec = p.width / VEC;
-  typename V::T dg[NV], db[NV], gam[NV];
+  const bool affine = p.gamma != nullptr;
+  typename V::T dg[NV], db[NV], gam[NV], bet[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     int vi = lir + LPR * v;
     dg[v] = V::zero(); db[v] = V::zero();
-    gam[v] = (p.gamma && vi < nvec) ? V::ld(p.gamma + VEC * vi) : V::zero();
+    gam[v] = (affine && vi < nvec) ? V::ld(p.gamma + VEC * vi) : V::zero();
+    bet[v] = (affine && vi < nvec) ? V::ld(p.beta + VEC * vi) : V::zero();
   }
-  const int64_t stride = (int64_t)gridDim.x * NW * RPW;
+  const int64_t rows_per_pass = (int64_t)gridDim.x * NW * RPW;
   const float invw = 1.f / (float)p.width;
-  for (int64_t row = ((int64_t)blockIdx.x * NW + wid) * RPW + grp; row < p.n_rows; row += stride) {
-    typename V::T g[NV], xh[NV];
-    float mean = 0.f, rstd = 1.f;
-    if (p.gamma) { mean = __ldg(p.mean + row); rstd = __ldg(p.rstd + row); }
-    float s1 = 0.f, s2 = 0.f;
+  for (int64_t row0 = ((int64_t)blockIdx.x * NW + wid) * RPW + grp; row0 < p.n_rows; row0 += U * rows_per_pass) {
+    typename V::T g[U][NV], xh[U][NV], extra[U][NV];
+    float mean[U], rstd[U];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      int vi = lir + LPR * v;
-      if (vi < nvec) {
-        typename V::T dy = V::ld_stream(p.dy + row * p.width + VEC * vi);
-        typename V::T y = V::ld_stream(p.y + row * p.width + VEC * vi);
-        xh[v] = p.gamma ? V::ld_stream(p.x + row * p.width + VEC * vi) : V::zero();
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + u * rows_per_pass;
+      const bool live = row < p.n_rows;
+      mean[u] = 0.f; rstd[u] = 1.f;
+      if (affine && live) { mean[u] = __ldg(p.mean + row); rstd[u] = __ldg(p.rstd + row); }
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-          float gk = get(y, k) > 0.f ? get(dy, k) : 0.f;
-          float xk = (get(xh[v], k) - mean) * rstd;
-          get(dg[v], k) = fmaf(gk, xk, get(dg[v], k));
-          get(db[v], k) += gk;
-          float gg = gk * get(gam[v], k);
-          get(g[v], k) = p.gamma ? gg : gk;
-          get(xh[v], k) = xk;
-          s1 += gg;
-          s2 = fmaf(gg, xk, s2);
-        }
-      } else {
-        g[v] = V::zero(); xh[v] = V::zero();
+      for (int v = 0; v < NV; ++v) {
+        int vi = lir + LPR * v;
+        const bool on = live && vi < nvec;
+        g[u][v] = on ? V::ld_stream(p.dy + row * p.width + VEC * vi) : V::zero();
+        xh[u][v] = on ? V::ld_stream(p.x + row * p.width + VEC * vi) : V::zero();
+        extra[u][v] = (on && p.add) ? V::ld_stream(p.add + row * p.width + VEC * vi) : V::zero();
       }
     }
-    if (p.gamma) {
-      s1 = group_sum<LPR>(s1, mask) * invw;
-      s2 = group_sum<LPR>(s2, mask) * invw;
+    float s1[U], s2[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      s1[u] = 0.f; s2[u] = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const float xraw = get(xh[u][v], k);
+          const float xk = (xraw - mean[u]) * rstd[u];
+          const float pre = affine ? fmaf(xk, get(gam[v], k), get(bet[v], k)) : xraw;
+          const float gk = pre > 0.f ? get(g[u][v], k) : 0.f;
+          get(dg[v], k) = fmaf(gk, xk, get(dg[v], k));
+          get(db[v], k) += gk;
+          const float gg = gk * get(gam[v], k);
+          get(g[u][v], k) = affine ? gg : gk;
+          get(xh[u][v], k) = xk;
+          s1[u] += gg;
+          s2[u] = fmaf(gg, xk, s2[u]);
+        }
+      }
+    }
+    if (affine) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        s1[u] = group_sum<LPR>(s1[u], mask) * invw;
+        s2[u] = group_sum<LPR>(s2[u], mask) * invw;
+      }
     }
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      int vi = lir + LPR * v;
-      if (vi < nvec) {
-        if (p.gamma) {
+    for (int u = 0; u < U; ++u) {
+      const int64_t row = row0 + u * rows_per_pass;
+      if (row >= p.n_rows) continue;
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) get(g[v], k) = rstd * (get(g[v], k) - s1 - get(xh[v], k) * s2);
+      for (int v = 0; v < NV; ++v) {
+        int vi = lir + LPR * v;
+        if (vi < nvec) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            float r = get(g[u][v], k);
+            if (affine) r = rstd[u] * (r - s1[u] - get(xh[u][v], k) * s2[u]);
+            get(g[u][v], k) = r + get(extra[u][v], k);
+          }
+          V::st(p.dx + row * p.width + VEC * vi, g[u][v]);
         }
-        V::st(p.dx + row * p.width + VEC * vi, g[v]);
       }
     }
   }
@@ -432,7 +465,7 @@ __global__ void __launch_bounds__(256) edge_update_kernel(EdgeUpdArgs p) {
     for (int k = 0; k < VEC; ++k) get(a, k) = fmaf(xv, __ldg(p.W0 + (int64_t)(c + k) * p.d0 + q), get(a, k));
   }
   {
-    typename V::T pv = V::ld_stream(p.P + e * p.ldp + c);
+    typename V::T pv = p.P ? V::ld_stream(p.P + e * p.ldp + c) : V::zero();
 #pragma unroll
     for (int k = 0; k < VEC; ++k) get(a, k) = fmaf(p.pscale, get(pv, k), p.scale * get(a, k));
   }
@@ -485,7 +518,7 @@ __global__ void __launch_bounds__(256, 2) edge_update_rows_kernel(EdgeUpdArgs p)
         const int vi = lir + LPR * v;
         const bool on = vi < nvec;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        pv[u][v] = on ? ld_stream4(p.P + ec * p.ldp + 4 * vi) : z;
+        pv[u][v] = (on && p.P) ? ld_stream4(p.P + ec * p.ldp + 4 * vi) : z;
         sk[u][v] = (on && p.skip) ? ld_stream4(p.skip + ec * p.ldskip + 4 * vi) : z;
         sv[u][v] = (on && p.S) ? ld4(p.S + (int64_t)col * p.width + 4 * vi) : z;
         vv[u][v] = (on && p.V) ? ld4(p.V + (int64_t)row * p.width + 4 * vi) : z;
@@ -580,9 +613,9 @@ extern "C" size_t gasfm_ln_relu_bwd_ws_bytes(int64_t n_rows, int width) {
   return (size_t)ln_bwd_blocks(n_rows) * 2 * width * sizeof(float);
 }
 
-extern "C" int gasfm_ln_relu_bwd(const float* dy, const float* x, const float* y, const float* mean, const float* rstd,
-                                 const float* gamma, int64_t n_rows, int width, float* dx, float* dgamma, float* dbeta,
-                                 void* ws, void* stream) {
+extern "C" int gasfm_ln_relu_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                                 const float* beta, const float* add, int64_t n_rows, int width, float* dx, float* dgamma,
+                                 float* dbeta, void* ws, void* stream) {
   GASFM_REQUIRE(width > 0 && width <= 1024, "ln_relu_bwd: unsupported width %d", width);
   cudaStream_t st = (cudaStream_t)stream;
   if (n_rows <= 0) {
@@ -592,11 +625,12 @@ extern "C" int gasfm_ln_relu_bwd(const float* dy, const float* x, const float* y
     }
     return check_launch("ln_relu_bwd(empty)");
   }
-  GASFM_REQUIRE(gamma == nullptr || ws != nullptr, "ln_relu_bwd: workspace required");
+  GASFM_REQUIRE(gamma == nullptr || (ws != nullptr && beta != nullptr && mean != nullptr && rstd != nullptr),
+                "ln_relu_bwd: the affine form needs beta, mean, rstd and a workspace");
   const int blocks = ln_bwd_blocks(n_rows);
-  LnBwdArgs a{dy, x, y, mean, rstd, gamma, n_rows, width, dx, (float*)ws};
+  LnBwdArgs a{dy, x, mean, rstd, gamma, beta, add, n_rows, width, dx, (float*)ws};
   const size_t smem = (size_t)(kLnBwdThreads / 32) * 2 * width * sizeof(float);
-  const bool vec4 = width % 4 == 0 && ((uintptr_t)x | (uintptr_t)y | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)gamma) % 16 == 0;
+  const bool vec4 = width % 4 == 0 && ((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)add) % 16 == 0;
 #define CALL_LNB(VEC, LPR, NV)                                                                       \
   do {                                                                                               \
     if (smem > 48 * 1024)                                                                            \
@@ -616,6 +650,37 @@ extern "C" int gasfm_ln_relu_bwd(const float* dy, const float* x, const float* y
   return check_launch("ln_relu_bwd(reduce)");
 }
 
+static int col_sum_slices(int64_t rows) {
+  int64_t s = rows / 256;
+  return (int)(s < 1 ? 1 : (s > 64 ? 64 : s));
+}
+
+extern "C" size_t gasfm_col_sum_ws_bytes(int64_t rows, int width) {
+  const int s = col_sum_slices(rows);
+  return s > 1 ? (size_t)s * width * sizeof(float) : 0;
+}
+
+extern "C" int gasfm_col_sum(const float* x, int64_t ld, int64_t rows, int width, float* out, void* ws, void* stream) {
+  GASFM_REQUIRE(width > 0 && ld >= width && rows < (int64_t)INT32_MAX, "col_sum: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows <= 0) {
+    cudaMemsetAsync(out, 0, (size_t)width * sizeof(float), st);
+    return check_launch("col_sum(empty)");
+  }
+  const int slices = col_sum_slices(rows);
+  if (slices == 1) {
+    launch_col_reduce(ColReduceJob{x, ld, width, out, 0, 0}, nullptr, (int)rows, 1.f, st);
+    return check_launch("col_sum");
+  }
+  GASFM_REQUIRE(ws != nullptr, "col_sum: workspace required");
+  const int per_slice = (int)((rows + slices - 1) / slices);
+  const int blocks = ceil_div(width, 32);
+  const ColReduceJob stage1{x, ld, width, (float*)ws, 0, 0};
+  col_reduce_kernel<<<dim3(blocks, slices), dim3(32, kColReduceGroups), 0, st>>>(stage1, stage1, blocks, (int)rows, per_slice, width, 1.f);
+  launch_col_reduce(ColReduceJob{(const float*)ws, width, width, out, 0, 0}, nullptr, slices, 1.f, st);
+  return check_launch("col_sum");
+}
+
 extern "C" int gasfm_edge_update_fwd(const float* P, int64_t ldp, const float* x0, int d0, const float* W0,
                                      const float* S, const float* V, const float* g, const float* skip, int64_t ldskip,
                                      const int32_t* row_idx, const int32_t* col_idx, int64_t n_obs, int width,
@@ -623,6 +688,7 @@ extern "C" int gasfm_edge_update_fwd(const float* P, int64_t ldp, const float* x
   GASFM_REQUIRE(width > 0, "edge_update_fwd: bad width");
   GASFM_REQUIRE(d0 >= 0 && d0 <= 4, "edge_update_fwd: init-feature width %d > 4 is not fused", d0);
   GASFM_REQUIRE((!S || col_idx) && (!V || row_idx), "edge_update_fwd: gather needs the index arrays");
+  GASFM_REQUIRE(P || d0 > 0, "edge_update_fwd: neither a projected term nor init features given");
   if (n_obs <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   EdgeUpdArgs a{P, ldp, d0 > 0 ? x0 : nullptr, d0, W0, S, V, g, skip, ldskip, row_idx, col_idx, n_obs, width, pscale, scale, out};

@@ -1,0 +1,389 @@
+// C[M,N] = A[M,K] * B[N,K]^T (+ bias), fp32 in / fp32 out, on the tcgen05 tensor cores with a SCALED 2 x FP16 split
+//     A*B ~= A_hi*B_hi + A_lo*B_hi + A_hi*B_lo,     x_hi = fp16(s x), x_lo = fp16(s x - x_hi)
+// kind::f16 runs at twice the kind::tf32 rate, and fp16 carries the same 11 significant bits as tf32, so the
+// three-product split keeps the ~2^-22 relative accuracy of the 3xTF32 kernel (gemm_tf32x3.cu) at half the tensor
+// time -- which moves these projections from tensor-bound to HBM-bound (read A once, write C once).
+//
+// fp16 has a 5-bit exponent, so every operand row is scaled by a power of two (exact) before the split:
+//   * A rows (observations):  s_m = 2^(14 - floor(log2 max_k |A[m,k]|)), computed by the producer warps from the
+//     row they hold in registers;  |s_m A[m,:]| < 2^15, the low part is >= 2^-24 (fp16 subnormal quantum), i.e. the
+//     split is exact to 2^-38 of the row maximum.
+//   * B rows (weights):       t_n likewise, by gasfm_split_f16 (once per weight and step).
+// The epilogue multiplies the accumulator by 1/(s_m t_n) (a power of two: exact) and adds the bias.
+//
+// Call sites: lin_l of the two GATv2 graphs, lin_r, lin_proj and the matching input gradients
+// (reference: code/models/layers.py:329,426,941 through torch.nn.functional.linear).
+//
+// Structure: CTA pairs (B halves multicast), persistent over M tiles, 16 warps in 4 warpgroups (128 registers per
+// thread at launch, redistributed with setmaxnreg):
+//   WG0  warp 0 TMA producer of B_hi/B_lo [N x 64] fp16 K-blocks, warp 1 TMEM allocation + MMA issue  (40 registers)
+//   WG1-2  A producers: the whole [128 x K] fp32 tile lives in registers (one LDG per element, no second pass
+//          for the row maximum); scaled, split and written as fp16 in the 128B-swizzled K-major layout; each
+//          K-block's registers are refilled with the NEXT tile as soon as they are consumed      (184 registers)
+//   WG3  epilogue: tcgen05.ld, descale, bias, swizzled staging tile, 256-bit global stores (+= C)     (96 registers)
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+#include "../../include/gasfm_b200.h"
+
+namespace gasfm {
+
+constexpr int kFBlockM = 128;
+constexpr int kFBlockK = 64;                          // 64 fp16 = 128 bytes = one SWIZZLE_128B atom row
+constexpr int kFUmmaK = 16;                           // fp16: 32 bytes per MMA along K
+constexpr int kFStages = 2;
+constexpr int kFThreads = 512;
+constexpr int kFATileBytes = kFBlockM * kFBlockK * 2;   // 16 KB per plane
+constexpr int kFScaleSlots = 8;                       // row-scale ring (tiles in flight between producers and epilogue)
+constexpr int kFCluster = 2;
+constexpr int kFTargetExp = 14;                       // scaled row maximum lies in [2^14, 2^15)
+
+struct GemmF16Args {
+  const float* A; int64_t lda; const float* b_scale; const float* bias; float* C; int64_t ldc; int64_t M; int N; int K;
+  int tmem_cols; int accumulate; int debug;   // debug: phase-isolation bits for profiling (GASFM_GEMM_DEBUG)
+  long long* trace;                           // optional [3 roles][kTraceTiles][16] SM-clock timestamps of CTA 0 (profiling)
+};
+
+constexpr int kTraceTiles = 16;
+#define GASFM_TRACE(role, it, slot)                                                                  \
+  do {                                                                                               \
+    if (p.trace && blockIdx.x == 0 && (it) < kTraceTiles) p.trace[((role) * kTraceTiles + (it)) * 16 + (slot)] = clock64(); \
+  } while (0)
+
+// 2^(kFTargetExp - floor(log2 amax)) and its inverse, from the exponent field (clamped so that both stay normal)
+__device__ __forceinline__ void row_scale_from_amax(float amax, float& scale, float& descale) {
+  int eb = (int)((__float_as_uint(amax) >> 23) & 0xffu);
+  eb = eb < 16 + kFTargetExp ? 16 + kFTargetExp : (eb > 254 - 16 ? 254 - 16 : eb);   // zero / tiny / inf rows: harmless scale
+  scale = __uint_as_float((uint32_t)(254 + kFTargetExp - eb) << 23);
+  descale = __uint_as_float((uint32_t)(eb - kFTargetExp) << 23);
+}
+
+template <int KB>   // number of 64-wide K blocks: K <= 64 * KB
+__global__ void __cluster_dims__(kFCluster, 1, 1) __launch_bounds__(kFThreads, 1)
+gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, GemmF16Args p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stage][A_hi 16K | A_lo 16K | B_hi N*128 | B_lo N*128] (1024-aligned), then the epilogue staging tiles
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_tile_bytes = p.N * kFBlockK * 2;
+  const int stage_bytes = 2 * kFATileBytes + 2 * b_tile_bytes;
+  uint8_t* c_stage = smem + (size_t)kFStages * stage_bytes;      // 4 epilogue warps x [32 rows x 128 B]
+  __shared__ uint64_t full_bar[kFStages], split_bar[kFStages], empty_bar[kFStages], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float bias_s[256], bscale_s[256];
+  __shared__ float row_descale[kFScaleSlots][kFBlockM];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t num_tiles = (p.M + kFBlockM - 1) / kFBlockM;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int64_t num_clusters = gridDim.x / kFCluster, cluster_id = blockIdx.x / kFCluster;
+  const int64_t num_pairs = (num_tiles + kFCluster - 1) / kFCluster;
+  // BOTH CTAs of a pair run every step (a CTA whose tile is past the end feeds zeros and stores nothing) so that
+  // the shared pipeline of multicast loads never deadlocks
+  const int64_t my_steps = cluster_id < num_pairs ? (num_pairs - cluster_id + num_clusters - 1) / num_clusters : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kFStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&split_bar[s], 256); mbar_init(&empty_bar[s], kFCluster); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int j = threadIdx.x; j < 256; j += kFThreads) {
+    bias_s[j] = (p.bias && j < p.N) ? p.bias[j] : 0.f;
+    bscale_s[j] = j < p.N ? p.b_scale[j] : 1.f;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();                            // the peer's barriers are initialised before any remote arrive / multicast
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+  const int acc_cols = p.tmem_cols / 2;     // column offset of the second accumulator
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0; uint32_t phase = 0;
+      const int half_rows = p.N / kFCluster;                       // B rows this CTA fetches and multicasts
+      const int half_bytes = half_rows * kFBlockK * 2;
+      for (int64_t it = 0; it < my_steps; ++it) {
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);                 // both CTAs have retired the MMAs of this stage
+          uint8_t* st = smem + (size_t)stage * stage_bytes;
+          if (p.debug & 4) { mbar_arrive(&full_bar[stage]); if (++stage == kFStages) { stage = 0; phase ^= 1; } continue; }
+          mbar_expect_tx(&full_bar[stage], 2 * b_tile_bytes);      // halves from both CTAs land here
+          tma_load_2d_mc(st + 2 * kFATileBytes + cta_rank * half_bytes, &map_bhi, &full_bar[stage], kb * kFBlockK,
+                         (int)cta_rank * half_rows, (uint16_t)((1u << kFCluster) - 1));
+          tma_load_2d_mc(st + 2 * kFATileBytes + b_tile_bytes + cta_rank * half_bytes, &map_blo, &full_bar[stage], kb * kFBlockK,
+                         (int)cta_rank * half_rows, (uint16_t)((1u << kFCluster) - 1));
+          if (++stage == kFStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ===================== MMA issuer =====================
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 (bit 4), A = B = f16 (format 0), K-major, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(kFBlockM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int64_t it = 0; it < my_steps; ++it) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        GASFM_TRACE(1, it, 0);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full_bar[stage], phase);       // B_hi / B_lo landed (TMA)
+          GASFM_TRACE(1, it, 1 + kb);
+          mbar_wait(&split_bar[stage], phase);      // A_hi / A_lo written by the producer warps
+          GASFM_TRACE(1, it, 5 + kb);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t a_lo = a_hi + kFATileBytes;
+          const uint32_t b_hi = a_hi + 2 * kFATileBytes;
+          const uint32_t b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+          for (int k = 0; k < kFBlockK / kFUmmaK; ++k) {
+            if (p.debug & 2) break;
+            const uint32_t koff = k * kFUmmaK * 2;   // bytes along K inside the 128-byte swizzle row
+            const uint32_t first = (kb == 0 && k == 0) ? 0u : 1u;
+            umma_f16(d_tmem, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, first);
+            umma_f16(d_tmem, make_desc(a_lo + koff), make_desc(b_hi + koff), idesc, 1u);
+            umma_f16(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), idesc, 1u);
+          }
+          umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << kFCluster) - 1));   // frees the stage in BOTH CTAs' eyes
+          if (kb == KB - 1) umma_commit(&tmem_full_bar[acc]);
+          GASFM_TRACE(1, it, 9 + kb);
+          if (++stage == kFStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp < 12) {
+    // ===================== A producers (256 threads, 2 warpgroups) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;" ::: "memory");
+    // thread -> float4 q (columns 4q..4q+3 of a 64-wide K block) of rows rg + 16 i: a warp-wide load covers
+    // two full 256-byte row segments.  buf holds this thread's share of the WHOLE tile.
+    const int t = threadIdx.x - 128;
+    const int q = t & 15, rg = t >> 4;
+    int stage = 0; uint32_t phase = 0;
+    float4 buf[KB][8];
+    auto load_block = [&](int64_t it, int kb, float4 (&v)[8]) {
+      const int64_t tile = (cluster_id + it * num_clusters) * kFCluster + cta_rank;
+      const int kcol = kb * kFBlockK + q * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t row = tile * kFBlockM + rg + 16 * i;
+        v[i] = (it < my_steps && row < p.M && kcol < p.K && !(p.debug & 8)) ? ld_stream4(p.A + row * p.lda + kcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) load_block(0, kb, buf[kb]);
+    for (int64_t it = 0; it < my_steps; ++it) {
+      // row maxima -> power-of-two scales (16 lanes share a row)
+      float scale[8];
+      float* descale_slot = row_descale[it & (kFScaleSlots - 1)];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float m = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+          m = fmaxf(m, fmaxf(fmaxf(fabsf(buf[kb][i].x), fabsf(buf[kb][i].y)), fmaxf(fabsf(buf[kb][i].z), fabsf(buf[kb][i].w))));
+#pragma unroll
+        for (int off = 1; off < 16; off <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        float descale;
+        row_scale_from_amax(m, scale[i], descale);
+        if (q == 0) descale_slot[rg + 16 * i] = descale;
+      }
+      if (t == 0) GASFM_TRACE(0, it, 0);
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (t == 0) GASFM_TRACE(0, it, 1 + kb);
+        uint8_t* a_hi = smem + (size_t)stage * stage_bytes;
+        uint8_t* a_lo = a_hi + kFATileBytes;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (p.debug & 16) break;
+          const int row = rg + 16 * i;
+          // 16-byte chunk q/2 of the row, swizzled (chunk ^= row % 8); this thread's 4 halves are its lower / upper 8 bytes
+          const int off = row * 128 + ((((q >> 1) ^ (row & 7))) << 4) + ((q & 1) << 3);
+          const float s = scale[i];
+          const float x0 = buf[kb][i].x * s, x1 = buf[kb][i].y * s, x2 = buf[kb][i].z * s, x3 = buf[kb][i].w * s;
+          const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+          uint2 hv, lv;
+          hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+          lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+          *reinterpret_cast<uint2*>(a_hi + off) = hv;
+          *reinterpret_cast<uint2*>(a_lo + off) = lv;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+        mbar_arrive(&split_bar[stage]);
+        if (t == 0) GASFM_TRACE(0, it, 5 + kb);
+        if (++stage == kFStages) { stage = 0; phase ^= 1; }
+        load_block(it + 1, kb, buf[kb]);        // refill the freed registers with the next tile's K block
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 12..15 -> TMEM lane quarters 0..3) =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");
+    const int quarter = warp & 3;
+    uint8_t* stg = c_stage + (warp - 12) * 4096;                   // [32 rows x 128 B], 128B-swizzled
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int64_t it = 0; it < my_steps; ++it) {
+      const int64_t tile = (cluster_id + it * num_clusters) * kFCluster + cta_rank;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (warp == 12 && lane == 0) GASFM_TRACE(2, it, 0);
+      const int row0 = (int)(tile * kFBlockM) + quarter * 32;       // first C row of this warp's 32-row slab
+      const float rs = row_descale[it & (kFScaleSlots - 1)][quarter * 32 + lane];   // lane = row of the slab
+      const uint32_t taddr0 = tmem_base + (uint32_t)(acc * acc_cols) + ((uint32_t)(quarter * 32) << 16);
+      // 32-column chunks: TMEM -> registers (lane = row) -> descale + bias -> swizzled staging tile -> registers
+      // (4 lanes = one 128-byte row segment) -> 256-bit global stores, 8 full lines per instruction.  All warp-local:
+      // no async proxy, no fences.  (Measured alternatives: TMA bulk stores of 4 KB / 2 KB tiles, 128-bit stores,
+      // stores straight from the lane = row registers, eight epilogue warps -- all slower or equal; the epilogue
+      // is paced by the memory system's write throughput under the concurrent A reads, see DESIGN.md.)
+      for (int c0 = 0; c0 < p.N; c0 += 32) {
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr0 + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        __syncwarp();                                  // the previous chunk's read-back is complete
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {              // lane = row; 16-byte chunk ^= row % 8: conflict-free
+          const float4 cs = *reinterpret_cast<const float4*>(&bscale_s[(c0 + j) & 255]);   // same address in every lane: broadcast
+          const float4 bs = *reinterpret_cast<const float4*>(&bias_s[(c0 + j) & 255]);
+          float4 v;
+          v.x = fmaf(__uint_as_float(r[j]), rs * cs.x, bs.x); v.y = fmaf(__uint_as_float(r[j + 1]), rs * cs.y, bs.y);
+          v.z = fmaf(__uint_as_float(r[j + 2]), rs * cs.z, bs.z); v.w = fmaf(__uint_as_float(r[j + 3]), rs * cs.w, bs.w);
+          *reinterpret_cast<float4*>(stg + lane * 128 + ((((j >> 2) ^ (lane & 7))) << 4)) = v;
+        }
+        __syncwarp();
+        const int pc = lane & 3, col = c0 + 8 * pc;    // this lane's 8 columns of rows (lane / 4) + 8 i
+        if (col >= p.N || (p.debug & 1)) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = 8 * i + (lane >> 2);
+          const int64_t grow = (int64_t)row0 + rr;
+          float4 v = *reinterpret_cast<const float4*>(stg + rr * 128 + (((2 * pc) ^ (rr & 7)) << 4));
+          float4 w = *reinterpret_cast<const float4*>(stg + rr * 128 + (((2 * pc + 1) ^ (rr & 7)) << 4));
+          if (grow < p.M) {
+            float* dst = p.C + grow * p.ldc + col;
+            if (p.accumulate) {
+              // C += : fire-and-forget vector reductions resolved in L2 (a read-add-write here would expose one
+              // memory round trip per chunk; every element has a single writer per launch, so the result is deterministic)
+              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+              asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 4), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w) : "memory");
+            } else {
+              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
+                           "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w)
+                           : "memory");
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&tmem_empty_bar[acc]);
+      if (warp == 12 && lane == 0) GASFM_TRACE(2, it, 1);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  __syncthreads();
+  cluster_sync();                            // no CTA leaves while its peer may still multicast into its shared memory
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// One warp per weight row n: t_n = 2^(14 - floor(log2 max_k |W[n,k]|)); hi = fp16(t W), lo = fp16(t W - hi); descale[n] = 1/t_n
+__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ w, int n_rows, int k, __half* __restrict__ hi,
+                                                        __half* __restrict__ lo, float* __restrict__ descale) {
+  const int row = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  const float* src = w + (int64_t)row * k;
+  float m = 0.f;
+  for (int j = lane; j < k; j += 32) m = fmaxf(m, fabsf(src[j]));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  float s, d;
+  row_scale_from_amax(m, s, d);
+  for (int j = lane; j < k; j += 32) {
+    const float x = src[j] * s;
+    const __half h = __float2half_rn(x);
+    hi[(int64_t)row * k + j] = h;
+    lo[(int64_t)row * k + j] = __float2half_rn(x - __half2float(h));
+  }
+  if (lane == 0) descale[row] = d;
+}
+
+}  // namespace gasfm
+
+using namespace gasfm;
+
+static long long* g_trace = nullptr;
+// profiling hook (tools/gemm_trace.py): device buffer of 3 * 16 * 16 int64 that the next launches fill with the
+// SM-clock timestamps of CTA 0's producer / MMA / epilogue milestones; NULL switches tracing off
+extern "C" int gasfm_debug_set_gemm_trace(void* dev_buffer) { g_trace = (long long*)dev_buffer; return 0; }
+
+extern "C" int gasfm_split_f16(const float* w, int n_rows, int k, void* hi, void* lo, float* descale, void* stream) {
+  GASFM_REQUIRE(n_rows >= 0 && k > 0, "split_f16: bad shape");
+  if (n_rows == 0) return 0;
+  split_f16_kernel<<<ceil_div((int64_t)n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(w, n_rows, k, (__half*)hi, (__half*)lo, descale);
+  return check_launch("split_f16");
+}
+
+extern "C" int gasfm_linear_f16x2_supported(int64_t M, int N, int K, int64_t lda, int64_t ldc) {
+  return (M > 0 && N >= 16 && N <= 256 && N % 16 == 0 && K >= 8 && K <= 256 && K % 8 == 0 && lda % 4 == 0 && ldc % 4 == 0) ? 1 : 0;
+}
+
+extern "C" int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi, const void* B_lo, const float* b_descale,
+                                  const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int accumulate, void* stream) {
+  GASFM_REQUIRE(gasfm_linear_f16x2_supported(M, N, K, lda, ldc), "linear_f16x2: unsupported shape M=%lld N=%d K=%d lda=%lld ldc=%lld",
+                (long long)M, N, K, (long long)lda, (long long)ldc);
+  GASFM_REQUIRE(b_descale != nullptr && ((uintptr_t)A | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C) % 16 == 0,
+                "linear_f16x2: pointers must be 16-byte aligned");
+  CUtensorMap mh, ml;
+  if (make_map_f16(&mh, B_hi, N, K, K, N / kFCluster, kFBlockK) || make_map_f16(&ml, B_lo, N, K, K, N / kFCluster, kFBlockK)) return 1;
+  int tmem_cols = 32;
+  while (tmem_cols < 2 * N) tmem_cols <<= 1;
+  const size_t smem = (size_t)kFStages * (2 * kFATileBytes + 2 * (size_t)N * kFBlockK * 2) + 4 * 4096 + 1024;
+  const int kb = (K + kFBlockK - 1) / kFBlockK;
+  const int64_t tiles = (M + kFBlockM - 1) / kFBlockM;
+  const int64_t pairs = (tiles + kFCluster - 1) / kFCluster;
+  const int grid = (int)(pairs < kNumSMs / kFCluster ? pairs : kNumSMs / kFCluster) * kFCluster;
+  static int debug = -1;
+  if (debug < 0) { const char* env = getenv("GASFM_GEMM_DEBUG"); debug = env ? atoi(env) : 0; }
+  GemmF16Args args{A, lda, b_descale, bias, C, ldc, M, N, K, tmem_cols, accumulate, debug, g_trace};
+#define LAUNCH_F16(KB)                                                                                                     \
+  do {                                                                                                                     \
+    static size_t allowed = 0; /* static smem (barriers, scales) also counts against the 227 KB per-CTA limit */          \
+    if (smem > allowed) {                                                                                                  \
+      cudaError_t e = cudaFuncSetAttribute(gemm_f16x2_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) {                                                                                              \
+        set_error("linear_f16x2: cannot reserve %zu bytes of shared memory (%s)", smem, cudaGetErrorString(e));            \
+        return (int)e;                                                                                                     \
+      }                                                                                                                    \
+      allowed = smem;                                                                                                      \
+    }                                                                                                                      \
+    gemm_f16x2_kernel<KB><<<grid, kFThreads, smem, (cudaStream_t)stream>>>(mh, ml, args);                             \
+  } while (0)
+  switch (kb) {
+    case 1: LAUNCH_F16(1); break;
+    case 2: LAUNCH_F16(2); break;
+    case 3: LAUNCH_F16(3); break;
+    default: LAUNCH_F16(4); break;
+  }
+#undef LAUNCH_F16
+  return check_launch("linear_f16x2");
+}

@@ -22,6 +22,8 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "col_reduce.cuh"
+#include "umma.cuh"
 #include "../../include/gasfm_b200.h"
 
 namespace gasfm {
@@ -33,92 +35,6 @@ constexpr int kStages = 2;
 constexpr int kGemmThreads = 448;          // TMA warp, MMA warp, 8 A-producer warps, 4 epilogue warps
 constexpr int kPrefetch = 4;               // K-blocks of A kept in flight per producer thread
 constexpr int kATileBytes = kBlockM * kBlockK * 4;   // 16 KB
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-// TMA load whose bytes (and complete_tx) land at the same shared-memory offsets in every CTA of ``mask``
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-// tcgen05.commit that arrives on the barrier at this offset in every CTA of ``mask``
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address and
-// offsets in 16-byte units, LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows x 128 B), version 1.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__device__ __forceinline__ float tf32_hi(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 
 struct GemmArgs {
   const float* A; int64_t lda; const float* bias; float* C; int64_t ldc; int64_t M; int N; int K; int tmem_cols; int accumulate; int debug;
@@ -553,32 +469,6 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_con
   }
 }
 
-// out[i] = sum_r ws[r, i] for i < width (width = Nout*Kout), deterministic; the last blocks do the same for the
-// bias-gradient partials (ws2 / width2 / out2) so that dW and db need one launch
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int rows, int64_t width, float* __restrict__ out,
-                                                           const float* __restrict__ ws2, int64_t width2, float* __restrict__ out2,
-                                                           int blocks1) {
-  if ((int)blockIdx.x >= blocks1) {
-    const int64_t j = ((int64_t)(blockIdx.x - blocks1) * blockDim.x + threadIdx.x) * 4;
-    if (j >= width2) return;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < rows; ++r) {
-      const float4 v = *reinterpret_cast<const float4*>(ws2 + (int64_t)r * width2 + j);
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-    }
-    *reinterpret_cast<float4*>(out2 + j) = a;
-    return;
-  }
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i >= width) return;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = 0; r < rows; ++r) {
-    const float4 v = *reinterpret_cast<const float4*>(ws + (int64_t)r * width + i);
-    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-  }
-  *reinterpret_cast<float4*>(out + i) = a;
-}
-
 __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -587,36 +477,6 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict
   lo[i] = x - h;
 }
 
-// ---- host: tensor maps via the driver entry point (no link-time dependency on libcuda) -----------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-// row-major [rows, cols] fp32 with row stride ld (elements); box = [box_rows x box_cols], SWIZZLE_128B
-static int make_map_box(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
-                        CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) { set_error("gemm_tf32x3: cuTensorMapEncodeTiled is unavailable"); return 1; }
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("gemm_tf32x3: cuTensorMapEncodeTiled failed (%d)", (int)r); return 1; }
-  return 0;
-}
 static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   return make_map_box(map, base, rows, cols, ld, box_rows, kBlockK);
 }
@@ -708,8 +568,9 @@ extern "C" int gasfm_wgrad_tf32x3(const float* dY, int64_t lddy, const float* X,
   wgrad_tf32x3_kernel<0><<<grid, kWgThreads, smem, st>>>(mdy, mx, a);
   int rc = check_launch("wgrad_tf32x3");
   if (rc) return rc;
+  // dW = sum of the per-CTA partials, db likewise, in one launch
   const int64_t width = (int64_t)Nout * Kout;
-  const int blocks1 = ceil_div(width / 4, 256), blocks2 = dbias ? ceil_div(Nout / 4, 256) : 0;
-  wgrad_reduce_kernel<<<blocks1 + blocks2, 256, 0, st>>>((const float*)ws, grid, width, dW, ws_db, Nout, dbias, blocks1);
+  const ColReduceJob jw{(const float*)ws, width, width, dW, 0, 0}, jb{ws_db, Nout, Nout, dbias, 0, 0};
+  launch_col_reduce(jw, dbias ? &jb : nullptr, grid, 1.f, st);
   return check_launch("wgrad_tf32x3(reduce)");
 }

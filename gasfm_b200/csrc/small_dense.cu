@@ -6,6 +6,7 @@
 // Both are single passes over E-sized inputs (HBM-bound) with fp32 round-to-nearest accumulation and a
 // deterministic two-stage reduction (per-CTA partials -> column sum).
 #include "common.cuh"
+#include "col_reduce.cuh"
 #include "../../include/gasfm_b200.h"
 
 namespace gasfm {
@@ -101,15 +102,6 @@ __global__ void __launch_bounds__(kWsWarps * 32) wgrad_small_kernel(const float*
     }
     for (int j = threadIdx.x; j < NOUT; j += blockDim.x) ws_db[(int64_t)blockIdx.x * NOUT + j] = s_acc[j];
   }
-}
-
-__global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restrict__ ws, int rows, int64_t width, float scale,
-                                                          float* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= width) return;
-  float a = 0.f;
-  for (int r = 0; r < rows; ++r) a += ws[(int64_t)r * width + i];
-  out[i] = a * scale;
 }
 
 // ---- x0 backward ------------------------------------------------------------------------------------
@@ -214,16 +206,6 @@ __global__ void __launch_bounds__(kX0Threads) x0_bwd_kernel(const float* __restr
   }
 }
 
-// dW0[c, q] = scale * sum_blocks ws[b][c*4 + q]
-__global__ void x0_bwd_reduce_kernel(const float* __restrict__ ws, int rows, int width, int d0, float scale, float* __restrict__ dW0) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= width * d0) return;
-  const int c = j / d0, q = j % d0;
-  float a = 0.f;
-  for (int r = 0; r < rows; ++r) a += ws[(int64_t)r * width * 4 + c * 4 + q];
-  dW0[j] = a * scale;
-}
-
 static int x0_blocks(int64_t E) {
   int64_t need = (E + 63) / 64;
   int64_t cap = (int64_t)kNumSMs * 8;
@@ -257,8 +239,8 @@ extern "C" int gasfm_wgrad_small(const float* dY, int64_t lddy, const float* X, 
   int rc = check_launch("wgrad_small");
   if (rc) return rc;
   const int64_t width = (int64_t)Nout * Kout;
-  partial_sum_kernel<<<ceil_div(width, 256), 256, 0, st>>>(w, blocks, width, 1.f, dW);
-  if (dbias) partial_sum_kernel<<<1, 256, 0, st>>>(wdb, blocks, Nout, 1.f, dbias);
+  const ColReduceJob jw{w, width, width, dW, 0, 0}, jb{wdb, Nout, Nout, dbias, 0, 0};
+  launch_col_reduce(jw, dbias ? &jb : nullptr, blocks, 1.f, st);
   return check_launch("wgrad_small(reduce)");
 }
 
@@ -305,6 +287,8 @@ extern "C" int gasfm_x0_bwd(const float* dOut, int64_t E, int width, const float
 #undef CALL_X0
   int rc = check_launch("x0_bwd");
   if (rc) return rc;
-  x0_bwd_reduce_kernel<<<ceil_div((int64_t)width * d0, 256), 256, 0, st>>>((const float*)ws, blocks, width, d0, scale, dW0);
+  // dW0[c, q] = scale * sum_blocks ws[b][c*4 + q], q < d0
+  const ColReduceJob jw{(const float*)ws, (int64_t)width * 4, (int64_t)width * 4, dW0, 4, d0};
+  launch_col_reduce(jw, nullptr, blocks, scale, st);
   return check_launch("x0_bwd(reduce)");
 }

@@ -141,8 +141,9 @@ class _ShardedGat(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
+        from . import ops
         XL, XR, att, out_nobias, M, L = ctx.saved_tensors
-        d_bias = d_out.sum(dim=0) if ctx.has_bias else None               # partial (sums to the true grad)
+        d_bias = ops.col_sum(d_out) if ctx.has_bias else None               # partial (sums to the true grad)
         d_full = d_out.contiguous().clone()
         dist.all_reduce(d_full, op=dist.ReduceOp.SUM, group=ctx.group)    # local edges need the full dOut
         dXL, dXR, datt = ctx.backend.backward(XL, XR, att, out_nobias, M, L, d_full, ctx.plan, ctx.heads)

@@ -56,7 +56,7 @@ class GATv2Conv(nn.Module):
             # the autograd graph so that it receives the same all-zero gradient it gets in the reference
             # (whose training loop concatenates every parameter's .grad, code/train.py:137).
             return (self.lin_r.bias + self.lin_r.weight.sum() * 0.0).unsqueeze(0)
-        return F.linear(x_agg, self.lin_r.weight, self.lin_r.bias)
+        return ops.linear(x_agg, self.lin_r.weight, self.lin_r.bias)
 
     def aggregate(self, x_elements, x_agg, plan, projected_sources=None):
         """[T, H*C] attention-aggregate of the element rows over ``plan``'s segments."""

@@ -266,7 +266,14 @@ class GraphAttnSfMLayer(Module):
     ):
         raw = prev_projection_features
         norm = self.prev_projfeat_norm_layer if self.use_norm_proj_update else None
-        x = relu_on_projection_features(None, _fused_norm=(raw, norm))
+        plain_residual = self.add_residual_skipconn_proj_update and self.skip_projection is None and norm is not None
+        if plain_residual:
+            # x_raw feeds LN+ReLU and the residual: one autograd node, so that the two gradients are summed
+            # inside the LN+ReLU backward kernel (ops.ln_relu_with_skip)
+            y, raw_vals = ops.ln_relu_with_skip(raw.values, norm.weight, norm.bias, norm.eps)
+            x, raw = raw.with_values(y), raw.with_values(raw_vals)
+        else:
+            x = relu_on_projection_features(None, _fused_norm=(raw, norm))
         if norm is None:
             # The reference's ReLU is in-place (layers.py:982-984): without a norm layer in front it
             # also rectifies the values the residual branch reads.

@@ -146,6 +146,12 @@ GASFM_API int gasfm_seg_bcast(const float* dOut, int width, const int32_t* seg_o
  * Per-observation feature ops
  * ------------------------------------------------------------------------------------- */
 
+/* out[width] = column sums of the row-major x[rows, ld>=width] (bias gradients: the reference gets them from
+ * autograd's sum over the target rows, e.g. GATv2Conv.bias at models/layers.py:329-335).  Deterministic
+ * two-stage reduction; ws: gasfm_col_sum_ws_bytes(rows, width) bytes (may be 0 -> NULL allowed). */
+GASFM_API size_t gasfm_col_sum_ws_bytes(int64_t rows, int width);
+GASFM_API int gasfm_col_sum(const float* x, int64_t ld, int64_t rows, int width, float* out, void* ws, void* stream);
+
 /* y = relu(layer_norm(x) * gamma + beta)  (normalize_projection_features +
  * relu_on_projection_features, models/layers.py:232-234, 972-984).  gamma == NULL skips the
  * normalisation (use_norm_proj_update = false): y = relu(x).  mean/rstd[E] saved for backward. */
@@ -153,14 +159,18 @@ GASFM_API int gasfm_ln_relu_fwd(const float* x, int64_t n_rows, int width, const
                       const float* beta, float eps, float* y, float* mean, float* rstd,
                       void* stream);
 GASFM_API size_t gasfm_ln_relu_bwd_ws_bytes(int64_t n_rows, int width);
-GASFM_API int gasfm_ln_relu_bwd(const float* dy, const float* x, const float* y, const float* mean,
-                      const float* rstd, const float* gamma, int64_t n_rows, int width,
-                      float* dx, float* dgamma, float* dbeta, void* ws, void* stream);
+/* Backward.  The ReLU mask is recomputed from x, mean, rstd, gamma, beta (y is not read).  add: optional
+ * [n_rows,width] tensor added to dx -- the gradient of a residual branch that reads the same x. */
+GASFM_API int gasfm_ln_relu_bwd(const float* dy, const float* x, const float* mean, const float* rstd,
+                      const float* gamma, const float* beta, const float* add,
+                      int64_t n_rows, int width, float* dx, float* dgamma, float* dbeta, void* ws, void* stream);
 
 /* out[e] = pscale * P[e] + scale * (sum_k x0[e,k] * W0[:,k] + S[col[e]] + V[row[e]] + g) + skip[e]
  * (GraphAttnSfMProjectionFeatureUpdate.forward + the residual of GraphAttnSfMLayer.forward,
  * models/layers.py:941-945, 254-261; also SetOfSetProjectionFeatureUpdate, :141-143).
- * x0 / W0 (width x d0, row-major, d0 <= 4), g and skip may be NULL.  ``pscale`` lets the caller fold
+ * x0 / W0 (width x d0, row-major, d0 <= 4), g and skip may be NULL; P may be NULL when d0 > 0 -- with
+ * g = bias and scale = 1 that is the write-bound linear layer of the first block, whose input is only
+ * d0 = 2 wide (lin_l / lin_proj / skip_projection of block 0).  ``pscale`` lets the caller fold
  * the 1/4 into lin_proj's weights so that dP == dOut in backward (no extra pass over [E,width]). */
 GASFM_API int gasfm_edge_update_fwd(const float* P, int64_t ldp, const float* x0, int d0, const float* W0,
                           const float* S, const float* V, const float* g, const float* skip,
@@ -179,6 +189,21 @@ GASFM_API int gasfm_linear_tf32x3_supported(int64_t M, int N, int K, int64_t lda
 GASFM_API int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo,
                                   const float* bias, float* C, int64_t ldc, int64_t M, int N, int K,
                                   int accumulate /* 1: C += A B^T + bias */, void* stream);
+
+/* Same product on the fp16 tensor-core path (twice the tf32 MMA rate) with a SCALED 2 x FP16 split:
+ * every row of A and of B is multiplied by a power of two that puts its largest magnitude in [2^14, 2^15)
+ * (exact), split into fp16 hi + lo, multiplied as A_hi B_hi + A_lo B_hi + A_hi B_lo with fp32 accumulation and
+ * descaled in the epilogue.  Accuracy ~2^-22 relative to |A_row| |B_row| like the 3xTF32 form; the kernel is
+ * HBM-bound (reads A once, writes C once) instead of tensor-bound.  K <= 256, K % 8 == 0, N as above.
+ * gasfm_split_f16 prepares B: hi/lo are [n_rows, k] fp16 (2-byte) matrices, descale[n_rows] fp32. */
+GASFM_API int gasfm_split_f16(const float* w, int n_rows, int k, void* hi, void* lo, float* descale, void* stream);
+/* Profiling hook: dev_buffer = 3*16*16 int64 on the device; the following gasfm_linear_f16x2 launches record
+ * SM-clock timestamps of CTA 0's producer / MMA / epilogue milestones there.  NULL switches it off. */
+GASFM_API int gasfm_debug_set_gemm_trace(void* dev_buffer);
+GASFM_API int gasfm_linear_f16x2_supported(int64_t M, int N, int K, int64_t lda, int64_t ldc);
+GASFM_API int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi, const void* B_lo,
+                       const float* b_descale, const float* bias, float* C, int64_t ldc,
+                       int64_t M, int N, int K, int accumulate, void* stream);
 
 /* Weight gradient of the same projections: dW[Nout,Kout] = dY[E,Nout]^T * X[E,Kout], 3xTF32 on tcgen05,
  * deterministic split-K over the SMs.  ``ws`` needs gasfm_wgrad_tf32x3_ws_bytes(Nout,Kout) bytes. */

@@ -283,6 +283,76 @@ def test_ln_relu_forward_backward(w, affine):
         assert rel_err(bg.grad, beta.grad.numpy()) < GRAD_TOL
 
 
+@pytest.mark.parametrize("w", [32, 256, 34])
+@pytest.mark.parametrize("use", ["both", "skip_only", "main_only"])
+def test_ln_relu_with_skip_sums_both_gradients_in_the_kernel(w, use):
+    torch.manual_seed(w)
+    E = 1501
+    x = torch.randn(E, w, dtype=torch.float64)
+    gamma = (torch.randn(w, dtype=torch.float64) * 0.5 + 1).requires_grad_(True)
+    beta = (torch.randn(w, dtype=torch.float64) * 0.2).requires_grad_(True)
+    c1, c2 = torch.randn(E, w, dtype=torch.float64), torch.randn(E, w, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    y_ref = torch.relu(torch.nn.functional.layer_norm(xr, (w,), gamma, beta, 1e-5))
+    loss_ref = ((y_ref * c1).sum() if use != "skip_only" else 0) + ((xr * xr * c2).sum() if use != "main_only" else 0)
+    loss_ref.backward()
+    xg = x.float().to(DEV).requires_grad_(True)
+    gg, bg = (t.detach().float().to(DEV).requires_grad_(True) for t in (gamma, beta))
+    y, skip = ops.ln_relu_with_skip(xg, gg, bg, 1e-5)
+    assert skip.data_ptr() == xg.data_ptr()
+    c1g, c2g = c1.float().to(DEV), c2.float().to(DEV)
+    loss = ((y * c1g).sum() if use != "skip_only" else 0) + ((skip * skip * c2g).sum() if use != "main_only" else 0)
+    loss.backward()
+    assert rel_err(y, y_ref.detach().numpy()) < FP32_TOL
+    assert rel_err(xg.grad, xr.grad.numpy()) < GRAD_TOL
+    if use != "skip_only":
+        assert rel_err(gg.grad, gamma.grad.numpy()) < GRAD_TOL
+        assert rel_err(bg.grad, beta.grad.numpy()) < GRAD_TOL
+
+
+@pytest.mark.parametrize("rows,w,strided", [(1, 7, False), (1500, 256, False), (50000, 256, False), (20011, 33, True),
+                                            (300, 64, False), (70000, 4, False)])
+def test_col_sum_matches_fp64_sum(rows, w, strided):
+    torch.manual_seed(rows + w)
+    base = torch.randn(rows, w + (5 if strided else 0), dtype=torch.float32)
+    x = base[:, :w]
+    want = x.double().sum(dim=0).numpy()
+    old = ops.COL_SUM_MIN_ROWS
+    ops.COL_SUM_MIN_ROWS = 0          # force the kernel for the small cases too
+    try:
+        got = ops.col_sum(base.to(DEV)[:, :w])
+        got_keep = ops.col_sum(base.to(DEV)[:, :w], keepdim=True)
+    finally:
+        ops.COL_SUM_MIN_ROWS = old
+    scale = np.abs(x.double().numpy()).sum(axis=0).max()
+    assert np.abs(got.cpu().numpy() - want).max() < 1e-6 * scale
+    assert got_keep.shape == (1, w) and torch.equal(got_keep[0], got)
+
+
+@pytest.mark.parametrize("K,N,bias", [(2, 256, True), (1, 32, True), (4, 64, False), (3, 1024, True), (2, 36, True)])
+def test_linear_with_tiny_input_width_uses_the_write_bound_kernel(K, N, bias):
+    """first block: the observations are 2 wide, so lin_l / lin_proj / skip_projection are [E,2] x [2,N]"""
+    torch.manual_seed(K * N)
+    E = 5003
+    x = torch.randn(E, K, dtype=torch.float64, requires_grad=True)
+    W = torch.randn(N, K, dtype=torch.float64, requires_grad=True)
+    b = torch.randn(N, dtype=torch.float64, requires_grad=True) if bias else None
+    dy = torch.randn(E, N, dtype=torch.float64)
+    torch.nn.functional.linear(x, W, b).backward(dy)
+    xg, Wg = (t.detach().float().to(DEV).requires_grad_(True) for t in (x, W))
+    bg = b.detach().float().to(DEV).requires_grad_(True) if bias else None
+    before = _lib.launch_count
+    y = ops.linear(xg, Wg, bg)
+    if K < 4:      # K = 4 is also a valid tensor-core shape (weight split + GEMM)
+        assert _lib.launch_count == before + 1, "expected exactly one gasfm kernel call (no cuBLAS fallback)"
+    y.backward(dy.float().to(DEV))
+    assert rel_err(y, torch.nn.functional.linear(x, W, b).detach().numpy()) < FP32_TOL
+    assert rel_err(xg.grad, x.grad.numpy()) < GRAD_TOL
+    assert rel_err(Wg.grad, W.grad.numpy()) < GRAD_TOL
+    if bias:
+        assert rel_err(bg.grad, b.grad.numpy()) < GRAD_TOL
+
+
 @pytest.mark.parametrize("w", [6, 32, 256, 3, 100])
 def test_row_col_pooling_matches_reference_golden_and_oracle(w):
     g = load_golden("pooling")
@@ -372,6 +442,40 @@ def test_gemm_tf32x3_has_fp32_accuracy(M, N, K):
     got2 = ops.gemm_tf32x3(wide[:, 4:4 + K], w)
     ref2 = wide[:, 4:4 + K].double() @ w.double().t()
     assert ((got2.double() - ref2).abs().max() / ref2.abs().max()).item() < max(5 * err32, 4e-6)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 16, 32), (1000, 256, 256), (4097, 32, 32), (300, 64, 104), (20000, 256, 256),
+                                   (5000, 48, 40), (129, 256, 8), (70000, 128, 64), (70000, 64, 256), (33000, 256, 192)])
+def test_gemm_f16x2_has_fp32_accuracy_for_any_row_scale(M, N, K):
+    """The scaled 2 x FP16 split must keep fp32-level accuracy whatever the magnitude of a row: rows of A spanning
+    1e-12 .. 1e+12 (gradients are tiny, pre-norm features can be large), weights rows likewise, zero rows, and a
+    row whose entries span 7 decades.  Error is measured per ROW against that row's own largest output."""
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device=DEV)
+    a *= 10.0 ** torch.randint(-12, 13, (M, 1), device=DEV).float()        # per-row magnitude
+    a[::97] = 0.0
+    a[1] = torch.randn(K, device=DEV) * 10.0 ** torch.linspace(-7, 0, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) / K ** 0.5
+    w *= 10.0 ** torch.randint(-3, 4, (N, 1), device=DEV).float()
+    b = None
+    ref = a.double() @ w.double().t()
+    assert ops.gemm_f16x2_supported(M, N, K, K, N)
+    got = ops.gemm_f16x2(a, w, b)
+    # per-row, per-column normalisation: |err[m,n]| <= tol * |a_m| |w_n|
+    bound = a.double().norm(dim=1, keepdim=True) * w.double().norm(dim=1).unsqueeze(0) + 1e-300
+    err = ((got.double() - ref).abs() / bound).max().item()
+    err32 = ((torch.nn.functional.linear(a, w).double() - ref).abs() / bound).max().item()
+    assert err < max(5 * err32, 2e-6), (err, err32)
+    assert torch.isfinite(got).all()
+    # bias, strided A, accumulate mode
+    bias = torch.randn(N, device=DEV)
+    wide = torch.randn(M, K + 8, device=DEV)
+    base = torch.randn(M, N, device=DEV)
+    out = base.clone()
+    got2 = ops.gemm_f16x2(wide[:, 4:4 + K], w, bias, out=out, accumulate=True)
+    assert got2.data_ptr() == out.data_ptr()
+    ref2 = base.double() + wide[:, 4:4 + K].double() @ w.double().t() + bias.double()
+    assert ((got2.double() - ref2).abs().max() / ref2.abs().max()).item() < 4e-6
 
 
 def test_linear_autograd_matches_fp64():
