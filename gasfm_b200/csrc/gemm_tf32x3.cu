@@ -36,8 +36,12 @@ constexpr int kGemmThreads = 448;          // TMA warp, MMA warp, 8 A-producer w
 constexpr int kPrefetch = 4;               // K-blocks of A kept in flight per producer thread
 constexpr int kATileBytes = kBlockM * kBlockK * 4;   // 16 KB
 
+constexpr int kMaxASegments = 4;
+// A may be the column-wise concatenation [A_0 | A_1 | ...] of up to kMaxASegments matrices of seg_k columns each
+// (input gradient of several projections of the same input: dX = sum_i dY_i W_i = [dY_0 | dY_1 | ..] [W_0; W_1; ..])
 struct GemmArgs {
-  const float* A; int64_t lda; const float* bias; float* C; int64_t ldc; int64_t M; int N; int K; int tmem_cols; int accumulate; int debug;
+  const float* A[kMaxASegments]; int64_t lda[kMaxASegments]; int seg_k;
+  const float* bias; float* C; int64_t ldc; int64_t M; int N; int K; int tmem_cols; int accumulate; int debug;
 };
 
 // CTA pairs (cluster of 2): the weight tiles B_hi / B_lo are identical for every M tile, and re-streaming them
@@ -154,10 +158,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_con
     auto load_block = [&](int64_t g, float4 (&v)[4]) {
       const int64_t tile = (cluster_id + (g / num_k_blocks) * num_clusters) * kCluster + cta_rank;
       const int kcol = (int)(g % num_k_blocks) * kBlockK + q * 4;
+      const int seg = kcol < p.K ? kcol / p.seg_k : 0, kloc = kcol - seg * p.seg_k;   // seg_k % 4 == 0: a float4 never straddles
+      const float* a_seg = p.A[seg];
+      const int64_t lda_seg = p.lda[seg];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int64_t row = tile * kBlockM + rg + 32 * i;
-        v[i] = (g < total && row < p.M && kcol < p.K && !(p.debug & 8)) ? ld_stream4(p.A + row * p.lda + kcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = (g < total && row < p.M && kcol < p.K && !(p.debug & 8)) ? ld_stream4(a_seg + row * lda_seg + kloc) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
 #pragma unroll
@@ -495,11 +502,8 @@ extern "C" int gasfm_linear_tf32x3_supported(int64_t M, int N, int K, int64_t ld
   return (M > 0 && N >= 16 && N <= 256 && N % 16 == 0 && K >= 4 && K % 4 == 0 && lda % 4 == 0 && ldc % 4 == 0) ? 1 : 0;
 }
 
-extern "C" int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo, const float* bias,
-                                   float* C, int64_t ldc, int64_t M, int N, int K, int accumulate, void* stream) {
-  GASFM_REQUIRE(gasfm_linear_tf32x3_supported(M, N, K, lda, ldc), "linear_tf32x3: unsupported shape M=%lld N=%d K=%d lda=%lld ldc=%lld",
-                (long long)M, N, K, (long long)lda, (long long)ldc);
-  GASFM_REQUIRE(((uintptr_t)A | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C) % 16 == 0, "linear_tf32x3: pointers must be 16-byte aligned");
+static int launch_linear_tf32x3(const float* const* A, const int64_t* lda, int n_seg, int seg_k, const float* B_hi, const float* B_lo,
+                                const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int accumulate, void* stream) {
   CUtensorMap mh, ml, mc;
   if (make_map(&mh, B_hi, N, K, K, N / kCluster) || make_map(&ml, B_lo, N, K, K, N / kCluster) ||
       make_map_box(&mc, C, M, N, ldc, 32, 32)) return 1;
@@ -520,9 +524,36 @@ extern "C" int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_h
   const int grid = (int)(pairs < kNumSMs / kCluster ? pairs : kNumSMs / kCluster) * kCluster;
   static int debug = -1;
   if (debug < 0) { const char* env = getenv("GASFM_GEMM_DEBUG"); debug = env ? atoi(env) : 0; }   // phase-isolation knob for profiling
-  GemmArgs args{A, lda, bias, C, ldc, M, N, K, tmem_cols, accumulate, debug};
+  GemmArgs args{};
+  for (int i = 0; i < n_seg; ++i) { args.A[i] = A[i]; args.lda[i] = lda[i]; }
+  args.seg_k = seg_k; args.bias = bias; args.C = C; args.ldc = ldc; args.M = M; args.N = N; args.K = K;
+  args.tmem_cols = tmem_cols; args.accumulate = accumulate; args.debug = debug;
   gemm_tf32x3_kernel<0><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(mh, ml, mc, args);
   return check_launch("linear_tf32x3");
+}
+
+extern "C" int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_hi, const float* B_lo, const float* bias,
+                                   float* C, int64_t ldc, int64_t M, int N, int K, int accumulate, void* stream) {
+  GASFM_REQUIRE(gasfm_linear_tf32x3_supported(M, N, K, lda, ldc), "linear_tf32x3: unsupported shape M=%lld N=%d K=%d lda=%lld ldc=%lld",
+                (long long)M, N, K, (long long)lda, (long long)ldc);
+  GASFM_REQUIRE(((uintptr_t)A | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C) % 16 == 0, "linear_tf32x3: pointers must be 16-byte aligned");
+  return launch_linear_tf32x3(&A, &lda, 1, K, B_hi, B_lo, bias, C, ldc, M, N, K, accumulate, stream);
+}
+
+extern "C" int gasfm_linear_tf32x3_cat(const float* const* A, const int64_t* lda, int n_seg, int seg_k, const float* B_hi,
+                                       const float* B_lo, const float* bias, float* C, int64_t ldc, int64_t M, int N,
+                                       int accumulate, void* stream) {
+  GASFM_REQUIRE(A && lda && n_seg >= 1 && n_seg <= kMaxASegments && seg_k >= 4 && seg_k % 4 == 0,
+                "linear_tf32x3_cat: 1..%d segments of a multiple of 4 columns", kMaxASegments);
+  const int K = n_seg * seg_k;
+  uintptr_t bits = (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C;
+  for (int i = 0; i < n_seg; ++i) {
+    GASFM_REQUIRE(gasfm_linear_tf32x3_supported(M, N, K, lda[i], ldc), "linear_tf32x3_cat: unsupported shape M=%lld N=%d K=%d lda=%lld",
+                  (long long)M, N, K, (long long)lda[i]);
+    bits |= (uintptr_t)A[i];
+  }
+  GASFM_REQUIRE(bits % 16 == 0, "linear_tf32x3_cat: pointers must be 16-byte aligned");
+  return launch_linear_tf32x3(A, lda, n_seg, seg_k, B_hi, B_lo, bias, C, ldc, M, N, K, accumulate, stream);
 }
 
 extern "C" int gasfm_wgrad_tf32x3_supported(int64_t E, int Nout, int Kout, int64_t lddy, int64_t ldx) {

@@ -407,6 +407,26 @@ def gemm_tf32x3(a, b, bias=None, out=None, accumulate=False):
     return gemm_tc(a, b, bias, out, accumulate, kind="tf32x3")
 
 
+def gemm_tf32x3_cat(a_list, b, bias=None):
+    """[A_0 | A_1 | ..] b^T for 1..4 matrices A_i [M, seg_k] that live in separate buffers; b is [N, n * seg_k].
+    One pass over every A_i and one write of the result (3xTF32: no per-row scale to agree on across the A_i)."""
+    import ctypes
+
+    rows = [_rows(a) for a in a_list]
+    M, seg_k = rows[0][0].shape
+    N = b.shape[0]
+    n = len(rows)
+    assert b.shape[1] == n * seg_k and all(r[0].shape == (M, seg_k) for r in rows)
+    hi, lo = _split_tf32(b)
+    c = torch.empty((M, N), dtype=torch.float32, device=b.device)
+    ptrs = (ctypes.c_void_p * n)(*[r[0].data_ptr() for r in rows])
+    lds = (ctypes.c_int64 * n)(*[r[1] for r in rows])
+    with _lib.device_guard(b.device):
+        _lib.call("gasfm_linear_tf32x3_cat", ptrs, lds, n, seg_k, _lib.ptr(hi), _lib.ptr(lo),
+                  _lib.ptr(None if bias is None else bias.contiguous()), _lib.ptr(c), N, M, N, 0, _lib.stream_ptr())
+    return c
+
+
 def gemm_f16x2(a, b, bias=None, out=None, accumulate=False):
     return gemm_tc(a, b, bias, out, accumulate, kind="f16x2")
 
@@ -492,10 +512,19 @@ class _LinearMulti(torch.autograd.Function):
         grads = []
         dx = None
         need_x = ctx.needs_input_grad[0]
+        M, K = x.shape
+        n_out = weights[0].shape[0]
+        fused_dx = (need_x and 2 <= len(weights) <= 4 and all(dy is not None for dy in dys)
+                    and all(w.shape[0] == n_out for w in weights) and n_out % 4 == 0
+                    and gemm_tf32x3_supported(M, K, len(weights) * n_out, n_out, K))
+        if fused_dx:
+            # dX = [dY_0 | dY_1 | ..] [W_0; W_1; ..]: one pass over every dY_i, one write of dX
+            dys = [dy.contiguous() for dy in dys]
+            dx = gemm_tf32x3_cat(dys, torch.cat([w.t() for w in weights], dim=1))
         for i, (w, dy) in enumerate(zip(weights, dys)):
-            g, dw, db = _linear_backward(x, w, dy, need_x, ctx.needs_input_grad[1 + 2 * i], ctx.needs_input_grad[2 + 2 * i],
-                                         dx_out=dx)
-            if need_x:
+            g, dw, db = _linear_backward(x, w, dy, need_x and not fused_dx, ctx.needs_input_grad[1 + 2 * i],
+                                         ctx.needs_input_grad[2 + 2 * i], dx_out=None if fused_dx else dx)
+            if need_x and not fused_dx:
                 dx = g
             grads += [dw, db]
         return (dx, *grads)

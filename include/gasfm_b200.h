@@ -190,6 +190,14 @@ GASFM_API int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_hi
                                   const float* bias, float* C, int64_t ldc, int64_t M, int N, int K,
                                   int accumulate /* 1: C += A B^T + bias */, void* stream);
 
+/* The same with A given as the column-wise concatenation [A_0 | .. | A_{n_seg-1}] of n_seg <= 4 matrices of seg_k
+ * columns each (host arrays of device pointers / row strides); B is [N, n_seg * seg_k].  Input gradient of
+ * several projections of one input in ONE pass: dX = sum_i dY_i W_i (GraphAttnSfMLayer: lin_l x 2 + lin_proj,
+ * models/layers.py:329,426,941) instead of one GEMM plus two read-modify-write accumulations. */
+GASFM_API int gasfm_linear_tf32x3_cat(const float* const* A, const int64_t* lda, int n_seg, int seg_k,
+                            const float* B_hi, const float* B_lo, const float* bias, float* C, int64_t ldc,
+                            int64_t M, int N, int accumulate, void* stream);
+
 /* Same product on the fp16 tensor-core path (twice the tf32 MMA rate) with a SCALED 2 x FP16 split:
  * every row of A and of B is multiplied by a power of two that puts its largest magnitude in [2^14, 2^15)
  * (exact), split into fp16 hi + lo, multiplied as A_hi B_hi + A_lo B_hi + A_hi B_lo with fp32 accumulation and

@@ -550,14 +550,16 @@ def test_full_size_edge_kernels_cfg3():
     assert torch.equal(oi.csc_perm.long(), torch.argsort(torch.from_numpy(idx_np[1]).to(DEV), stable=True))
 
 
-def test_linear_multi_sums_input_gradients_in_the_epilogue():
-    """three projections of one input (lin_l x2 + lin_proj): outputs, dX (accumulated in the GEMM epilogue),
-    dW and the fused bias gradients against fp64"""
+@pytest.mark.parametrize("M,K,widths", [(9000, 64, (64, 32, 48)), (9000, 64, (32, 32, 32)), (70000, 256, (256, 256, 256)),
+                                        (5000, 32, (64, 64))])
+def test_linear_multi_sums_input_gradients_in_one_pass(M, K, widths):
+    """several projections of one input (lin_l x2 + lin_proj): outputs, dX (equal widths: ONE GEMM over the
+    concatenated [dY_0 | dY_1 | ..]; otherwise accumulated in the GEMM epilogues), dW and the fused bias gradients
+    against fp64"""
     torch.manual_seed(5)
-    M, K = 9000, 64
     x = torch.randn(M, K, device=DEV, requires_grad=True)
-    ws = [(torch.randn(n, K, device=DEV) / K ** 0.5).requires_grad_(True) for n in (64, 32, 48)]
-    bs = [torch.randn(n, device=DEV, requires_grad=True) for n in (64, 32, 48)]
+    ws = [(torch.randn(n, K, device=DEV) / K ** 0.5).requires_grad_(True) for n in widths]
+    bs = [torch.randn(n, device=DEV, requires_grad=True) for n in widths]
     ys = ops.linear_multi(x, list(zip(ws, bs)))
     assert type(ys[0].grad_fn).__name__.startswith("_LinearMulti")
     dys = [torch.randn_like(y) for y in ys]
