@@ -45,7 +45,7 @@ SIGNATURES = {
     "gasfm_split_f16": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "gasfm_debug_set_gemm_trace": (_I, [_P]),
     "gasfm_linear_f16x2_supported": (_I, [_L, _I, _I, _L, _L]),
-    "gasfm_linear_f16x2": (_I, [_P, _L, _P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _P]),
+    "gasfm_linear_f16x2": (_I, [_P, _L, _P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _I, _P]),
     "gasfm_linear_tf32x3_supported": (_I, [_L, _I, _I, _L, _L]),
     "gasfm_linear_tf32x3": (_I, [_P, _L, _P, _P, _P, _P, _L, _L, _I, _I, _I, _P]),
     "gasfm_wgrad_tf32x3_supported": (_I, [_L, _I, _I, _L, _L]),

@@ -39,10 +39,12 @@ constexpr int kFThreads = 512;
 constexpr int kFATileBytes = kFBlockM * kFBlockK * 2;   // 16 KB per plane
 constexpr int kFScaleSlots = 8;                       // row-scale ring (tiles in flight between producers and epilogue)
 constexpr int kFCluster = 2;
+constexpr int kFMaxGroups = 3;                        // projections of the same A computed per M tile
 constexpr int kFTargetExp = 14;                       // scaled row maximum lies in [2^14, 2^15)
 
 struct GemmF16Args {
   const float* A; int64_t lda; const float* b_scale; const float* bias; float* C; int64_t ldc; int64_t M; int N; int K;
+  int groups;                                 // B = [groups * N, K] stacked weights, C column offset g * N: one pass over A
   int tmem_cols; int accumulate; int debug;   // debug: phase-isolation bits for profiling (GASFM_GEMM_DEBUG)
   long long* trace;                           // optional [3 roles][kTraceTiles][16] SM-clock timestamps of CTA 0 (profiling)
 };
@@ -72,7 +74,7 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
   uint8_t* c_stage = smem + (size_t)kFStages * stage_bytes;      // 4 epilogue warps x [32 rows x 128 B]
   __shared__ uint64_t full_bar[kFStages], split_bar[kFStages], empty_bar[kFStages], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(16) float bias_s[256], bscale_s[256];
+  __shared__ __align__(16) float bias_s[kFMaxGroups * 256], bscale_s[kFMaxGroups * 256];   // [group][256]
   __shared__ float row_descale[kFScaleSlots][kFBlockM];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,9 +91,10 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int j = threadIdx.x; j < 256; j += kFThreads) {
-    bias_s[j] = (p.bias && j < p.N) ? p.bias[j] : 0.f;
-    bscale_s[j] = j < p.N ? p.b_scale[j] : 1.f;
+  for (int j = threadIdx.x; j < p.groups * 256; j += kFThreads) {
+    const int g = j >> 8, c = j & 255;
+    bias_s[j] = (p.bias && c < p.N) ? p.bias[g * p.N + c] : 0.f;
+    bscale_s[j] = c < p.N ? p.b_scale[g * p.N + c] : 1.f;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols) : "memory");
@@ -111,16 +114,17 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
       int stage = 0; uint32_t phase = 0;
       const int half_rows = p.N / kFCluster;                       // B rows this CTA fetches and multicasts
       const int half_bytes = half_rows * kFBlockK * 2;
-      for (int64_t it = 0; it < my_steps; ++it) {
+      for (int64_t vt = 0; vt < my_steps * p.groups; ++vt) {       // virtual tile = (M tile, group)
+        const int b_row0 = (int)(vt % p.groups) * p.N + (int)cta_rank * half_rows;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);                 // both CTAs have retired the MMAs of this stage
           uint8_t* st = smem + (size_t)stage * stage_bytes;
           if (p.debug & 4) { mbar_arrive(&full_bar[stage]); if (++stage == kFStages) { stage = 0; phase ^= 1; } continue; }
           mbar_expect_tx(&full_bar[stage], 2 * b_tile_bytes);      // halves from both CTAs land here
-          tma_load_2d_mc(st + 2 * kFATileBytes + cta_rank * half_bytes, &map_bhi, &full_bar[stage], kb * kFBlockK,
-                         (int)cta_rank * half_rows, (uint16_t)((1u << kFCluster) - 1));
+          tma_load_2d_mc(st + 2 * kFATileBytes + cta_rank * half_bytes, &map_bhi, &full_bar[stage], kb * kFBlockK, b_row0,
+                         (uint16_t)((1u << kFCluster) - 1));
           tma_load_2d_mc(st + 2 * kFATileBytes + b_tile_bytes + cta_rank * half_bytes, &map_blo, &full_bar[stage], kb * kFBlockK,
-                         (int)cta_rank * half_rows, (uint16_t)((1u << kFCluster) - 1));
+                         b_row0, (uint16_t)((1u << kFCluster) - 1));
           if (++stage == kFStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -130,7 +134,7 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(kFBlockM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int64_t it = 0; it < my_steps; ++it) {
+      for (int64_t it = 0; it < my_steps * p.groups; ++it) {       // virtual tiles
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         GASFM_TRACE(1, it, 0);
@@ -199,6 +203,8 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
         if (q == 0) descale_slot[rg + 16 * i] = descale;
       }
       if (t == 0) GASFM_TRACE(0, it, 0);
+      for (int g = 0; g < p.groups; ++g) {            // the same A tile feeds every group: converted again, loaded once
+      const bool last_group = g == p.groups - 1;
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -226,7 +232,8 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
         mbar_arrive(&split_bar[stage]);
         if (t == 0) GASFM_TRACE(0, it, 5 + kb);
         if (++stage == kFStages) { stage = 0; phase ^= 1; }
-        load_block(it + 1, kb, buf[kb]);        // refill the freed registers with the next tile's K block
+        if (last_group) load_block(it + 1, kb, buf[kb]);   // refill the freed registers with the next tile's K block
+      }
       }
     }
   } else {
@@ -235,11 +242,16 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
     const int quarter = warp & 3;
     uint8_t* stg = c_stage + (warp - 12) * 4096;                   // [32 rows x 128 B], 128B-swizzled
     int acc = 0; uint32_t acc_phase = 0;
-    for (int64_t it = 0; it < my_steps; ++it) {
+    for (int64_t vt = 0; vt < my_steps * p.groups; ++vt) {
+      const int64_t it = vt / p.groups;
+      const int grp = (int)(vt % p.groups);
+      const float* bias_g = bias_s + grp * 256;
+      const float* bscale_g = bscale_s + grp * 256;
+      float* c_grp = p.C + (int64_t)grp * p.N;
       const int64_t tile = (cluster_id + it * num_clusters) * kFCluster + cta_rank;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (warp == 12 && lane == 0) GASFM_TRACE(2, it, 0);
+      if (warp == 12 && lane == 0) GASFM_TRACE(2, vt, 0);
       const int row0 = (int)(tile * kFBlockM) + quarter * 32;       // first C row of this warp's 32-row slab
       const float rs = row_descale[it & (kFScaleSlots - 1)][quarter * 32 + lane];   // lane = row of the slab
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * acc_cols) + ((uint32_t)(quarter * 32) << 16);
@@ -262,8 +274,8 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
         __syncwarp();                                  // the previous chunk's read-back is complete
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {              // lane = row; 16-byte chunk ^= row % 8: conflict-free
-          const float4 cs = *reinterpret_cast<const float4*>(&bscale_s[(c0 + j) & 255]);   // same address in every lane: broadcast
-          const float4 bs = *reinterpret_cast<const float4*>(&bias_s[(c0 + j) & 255]);
+          const float4 cs = *reinterpret_cast<const float4*>(&bscale_g[(c0 + j) & 255]);   // same address in every lane: broadcast
+          const float4 bs = *reinterpret_cast<const float4*>(&bias_g[(c0 + j) & 255]);
           float4 v;
           v.x = fmaf(__uint_as_float(r[j]), rs * cs.x, bs.x); v.y = fmaf(__uint_as_float(r[j + 1]), rs * cs.y, bs.y);
           v.z = fmaf(__uint_as_float(r[j + 2]), rs * cs.z, bs.z); v.w = fmaf(__uint_as_float(r[j + 3]), rs * cs.w, bs.w);
@@ -279,7 +291,7 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
           float4 v = *reinterpret_cast<const float4*>(stg + rr * 128 + (((2 * pc) ^ (rr & 7)) << 4));
           float4 w = *reinterpret_cast<const float4*>(stg + rr * 128 + (((2 * pc + 1) ^ (rr & 7)) << 4));
           if (grow < p.M) {
-            float* dst = p.C + grow * p.ldc + col;
+            float* dst = c_grp + grow * p.ldc + col;
             if (p.accumulate) {
               // C += : fire-and-forget vector reductions resolved in L2 (a read-add-write here would expose one
               // memory round trip per chunk; every element has a single writer per launch, so the result is deterministic)
@@ -295,7 +307,7 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&tmem_empty_bar[acc]);
-      if (warp == 12 && lane == 0) GASFM_TRACE(2, it, 1);
+      if (warp == 12 && lane == 0) GASFM_TRACE(2, vt, 1);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -344,17 +356,22 @@ extern "C" int gasfm_split_f16(const float* w, int n_rows, int k, void* hi, void
 }
 
 extern "C" int gasfm_linear_f16x2_supported(int64_t M, int N, int K, int64_t lda, int64_t ldc) {
-  return (M > 0 && N >= 16 && N <= 256 && N % 16 == 0 && K >= 8 && K <= 256 && K % 8 == 0 && lda % 4 == 0 && ldc % 4 == 0) ? 1 : 0;
+  // K < 64 would leave half of every 64-wide K block (and of the producer lanes) empty: the 3xTF32 kernel with its
+  // 32-wide blocks is the better fit there
+  return (M > 0 && N >= 16 && N <= 256 && N % 16 == 0 && K >= 64 && K <= 256 && K % 8 == 0 && lda % 4 == 0 && ldc % 4 == 0) ? 1 : 0;
 }
 
 extern "C" int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi, const void* B_lo, const float* b_descale,
-                                  const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int accumulate, void* stream) {
+                                  const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int groups, int accumulate,
+                                  void* stream) {
   GASFM_REQUIRE(gasfm_linear_f16x2_supported(M, N, K, lda, ldc), "linear_f16x2: unsupported shape M=%lld N=%d K=%d lda=%lld ldc=%lld",
                 (long long)M, N, K, (long long)lda, (long long)ldc);
+  GASFM_REQUIRE(groups >= 1 && groups <= kFMaxGroups && ldc >= (int64_t)groups * N, "linear_f16x2: 1..%d groups, ldc >= groups * N", kFMaxGroups);
   GASFM_REQUIRE(b_descale != nullptr && ((uintptr_t)A | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C) % 16 == 0,
                 "linear_f16x2: pointers must be 16-byte aligned");
   CUtensorMap mh, ml;
-  if (make_map_f16(&mh, B_hi, N, K, K, N / kFCluster, kFBlockK) || make_map_f16(&ml, B_lo, N, K, K, N / kFCluster, kFBlockK)) return 1;
+  if (make_map_f16(&mh, B_hi, (int64_t)groups * N, K, K, N / kFCluster, kFBlockK) ||
+      make_map_f16(&ml, B_lo, (int64_t)groups * N, K, K, N / kFCluster, kFBlockK)) return 1;
   int tmem_cols = 32;
   while (tmem_cols < 2 * N) tmem_cols <<= 1;
   const size_t smem = (size_t)kFStages * (2 * kFATileBytes + 2 * (size_t)N * kFBlockK * 2) + 4 * 4096 + 1024;
@@ -364,7 +381,7 @@ extern "C" int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi,
   const int grid = (int)(pairs < kNumSMs / kFCluster ? pairs : kNumSMs / kFCluster) * kFCluster;
   static int debug = -1;
   if (debug < 0) { const char* env = getenv("GASFM_GEMM_DEBUG"); debug = env ? atoi(env) : 0; }
-  GemmF16Args args{A, lda, b_descale, bias, C, ldc, M, N, K, tmem_cols, accumulate, debug, g_trace};
+  GemmF16Args args{A, lda, b_descale, bias, C, ldc, M, N, K, groups, tmem_cols, accumulate, debug, g_trace};
 #define LAUNCH_F16(KB)                                                                                                     \
   do {                                                                                                                     \
     static size_t allowed = 0; /* static smem (barriers, scales) also counts against the 227 KB per-CTA limit */          \

@@ -394,12 +394,30 @@ def gemm_tc(a, b, bias=None, out=None, accumulate=False, kind=None):
         hi, lo, descale = _split_f16(b)
         with _lib.device_guard(a.device):
             _lib.call("gasfm_linear_f16x2", _lib.ptr(a), lda, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(descale), bias_ptr,
-                      _lib.ptr(c), N, M, N, K, int(bool(accumulate)), _lib.stream_ptr())
+                      _lib.ptr(c), N, M, N, K, 1, int(bool(accumulate)), _lib.stream_ptr())
         return c
     hi, lo = _split_tf32(b)
     with _lib.device_guard(a.device):
         _lib.call("gasfm_linear_tf32x3", _lib.ptr(a), lda, _lib.ptr(hi), _lib.ptr(lo), bias_ptr, _lib.ptr(c), N, M, N, K,
                   int(bool(accumulate)), _lib.stream_ptr())
+    return c
+
+
+F16X2_MAX_GROUPS = 3
+
+
+def gemm_f16x2_groups(a, weights, biases):
+    """Several projections y_g = a W_g^T + b_g of the SAME a (equal output widths) in one kernel: a is read from
+    HBM once.  Returns the [M, G*N] buffer; y_g = out[:, g*N:(g+1)*N]."""
+    a, lda = _rows(a)
+    M, K = a.shape
+    G, N = len(weights), weights[0].shape[0]
+    hi, lo, descale = _split_f16(torch.cat(list(weights), dim=0))
+    bias = torch.cat([b if b is not None else torch.zeros(N, dtype=torch.float32, device=a.device) for b in biases])
+    c = torch.empty((M, G * N), dtype=torch.float32, device=a.device)
+    with _lib.device_guard(a.device):
+        _lib.call("gasfm_linear_f16x2", _lib.ptr(a), lda, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(descale), _lib.ptr(bias),
+                  _lib.ptr(c), G * N, M, N, K, G, 0, _lib.stream_ptr())
     return c
 
 
@@ -504,6 +522,13 @@ class _LinearMulti(torch.autograd.Function):
         weights, biases = wb[0::2], wb[1::2]
         ctx.save_for_backward(x, *weights)
         ctx.n = len(weights)
+        M, K = x.shape
+        N = weights[0].shape[0]
+        lda = x.stride(0) if x.stride(1) == 1 else K
+        if (GEMM_KIND == "f16x2" and 2 <= len(weights) <= F16X2_MAX_GROUPS and all(w.shape[0] == N for w in weights)
+                and gemm_f16x2_supported(M, N, K, lda, len(weights) * N)):
+            out = gemm_f16x2_groups(x, weights, biases)          # x is read once for all projections
+            return tuple(out[:, g * N:(g + 1) * N] for g in range(len(weights)))
         return tuple(gemm_tc(x, w, b) for w, b in zip(weights, biases))
 
     @staticmethod

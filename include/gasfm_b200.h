@@ -209,9 +209,11 @@ GASFM_API int gasfm_split_f16(const float* w, int n_rows, int k, void* hi, void*
  * SM-clock timestamps of CTA 0's producer / MMA / epilogue milestones there.  NULL switches it off. */
 GASFM_API int gasfm_debug_set_gemm_trace(void* dev_buffer);
 GASFM_API int gasfm_linear_f16x2_supported(int64_t M, int N, int K, int64_t lda, int64_t ldc);
+/* groups (1..3): B_hi/B_lo/b_descale/bias hold ``groups`` stacked [N, K] weights; group g is written to columns
+ * [g*N, (g+1)*N) of C (ldc >= groups*N).  Several projections of the same input read A from HBM once. */
 GASFM_API int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi, const void* B_lo,
                        const float* b_descale, const float* bias, float* C, int64_t ldc,
-                       int64_t M, int N, int K, int accumulate, void* stream);
+                       int64_t M, int N, int K, int groups, int accumulate, void* stream);
 
 /* Weight gradient of the same projections: dW[Nout,Kout] = dY[E,Nout]^T * X[E,Kout], 3xTF32 on tcgen05,
  * deterministic split-K over the SMs.  ``ws`` needs gasfm_wgrad_tf32x3_ws_bytes(Nout,Kout) bytes. */

@@ -444,8 +444,8 @@ def test_gemm_tf32x3_has_fp32_accuracy(M, N, K):
     assert ((got2.double() - ref2).abs().max() / ref2.abs().max()).item() < max(5 * err32, 4e-6)
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 16, 32), (1000, 256, 256), (4097, 32, 32), (300, 64, 104), (20000, 256, 256),
-                                   (5000, 48, 40), (129, 256, 8), (70000, 128, 64), (70000, 64, 256), (33000, 256, 192)])
+@pytest.mark.parametrize("M,N,K", [(128, 16, 64), (1000, 256, 256), (4097, 32, 72), (300, 64, 104), (20000, 256, 256),
+                                   (5000, 48, 80), (129, 256, 128), (70000, 128, 64), (70000, 64, 256), (33000, 256, 192)])
 def test_gemm_f16x2_has_fp32_accuracy_for_any_row_scale(M, N, K):
     """The scaled 2 x FP16 split must keep fp32-level accuracy whatever the magnitude of a row: rows of A spanning
     1e-12 .. 1e+12 (gradients are tiny, pre-norm features can be large), weights rows likewise, zero rows, and a
@@ -476,6 +476,20 @@ def test_gemm_f16x2_has_fp32_accuracy_for_any_row_scale(M, N, K):
     assert got2.data_ptr() == out.data_ptr()
     ref2 = base.double() + wide[:, 4:4 + K].double() @ w.double().t() + bias.double()
     assert ((got2.double() - ref2).abs().max() / ref2.abs().max()).item() < 4e-6
+
+
+def test_gemm_f16x2_groups_read_the_input_once():
+    """three projections of one input in one launch == three separate GEMMs, bit for bit"""
+    torch.manual_seed(11)
+    M, K, N = 30011, 256, 256
+    a = torch.randn(M, K, device=DEV) * 10.0 ** torch.randint(-4, 5, (M, 1), device=DEV).float()
+    ws = [torch.randn(N, K, device=DEV) / K ** 0.5 for _ in range(3)]
+    bs = [torch.randn(N, device=DEV), None, torch.randn(N, device=DEV)]
+    out = ops.gemm_f16x2_groups(a, ws, bs)
+    assert out.shape == (M, 3 * N)
+    for g in range(3):
+        assert torch.equal(out[:, g * N:(g + 1) * N], ops.gemm_f16x2(a, ws[g], bs[g]))
+    assert not ops.gemm_f16x2_supported(M, N, 32, 32, N)      # narrow K stays on the 3xTF32 kernel
 
 
 def test_linear_autograd_matches_fp64():
