@@ -181,17 +181,27 @@ def kernel_roofline(cfg, peaks, peak_kind):
         del XR, out, dO
     if ops.gemm_tf32x3_supported(E, HC, HC, HC, HC):
         W = torch.randn(HC, HC, device=dev) / HC ** 0.5
-        gemm_ms = timed_batches(lambda: ops.gemm_tc(XL, W))
-        wg_ms = timed_batches(lambda: ops.wgrad_tf32x3(XL, XL))
-        n_gemm = 3 * (L - 1) + 2                      # lin_l x2 + lin_proj per stateful block, lin_l x2 in the final update
+        n_blocks3 = L - 1                             # stateful blocks: lin_l x2 + lin_proj of the same x
+        n_gemm = 3 * n_blocks3 + 2                    # + lin_l x2 in the final update
         flops = 3 * 2.0 * E * HC * HC                 # three split products
         io_bytes = 2 * E * HC * 4                     # read A once, write C once (weights stay in L2)
-        if ops.GEMM_KIND == "f16x2" and ops.gemm_f16x2_supported(E, HC, HC, HC, HC):
-            # scaled 2 x FP16 split: the tensor time is half the 3xTF32 kernel's, the kernel is HBM-bound
-            res["gemm_f16x2 (fwd + dX)"] = dict(bound="hbm", ms=gemm_ms, work=io_bytes, calls=2 * n_gemm,
-                                                tensor_frac=flops / gemm_ms / 1e9 / (2.0 * peak_tf32))
+        f16 = ops.GEMM_KIND == "f16x2" and ops.gemm_f16x2_supported(E, HC, HC, HC, HC)
+        gemm_ms = timed_batches(lambda: ops.gemm_tc(XL, W))
+        if f16:
+            # scaled 2 x FP16 split: the tensor time is half the 3xTF32 kernel's, the kernel is HBM-bound.
+            # Forward: the three projections of a block in one launch (A read once, three outputs written).
+            grp_ms = timed_batches(lambda: ops.gemm_f16x2_groups(XL, [W, W, W], [None, None, None]))
+            res["gemm_f16x2 x3 groups (forward projections)"] = dict(
+                bound="hbm", ms=grp_ms, work=4 * E * HC * 4, calls=n_blocks3, tensor_frac=3 * flops / grp_ms / 1e9 / (2.0 * peak_tf32))
+            res["gemm_f16x2 (single projection)"] = dict(bound="hbm", ms=gemm_ms, work=io_bytes, calls=2,
+                                                         tensor_frac=flops / gemm_ms / 1e9 / (2.0 * peak_tf32))
         else:
-            res["gemm_tf32x3 (fwd + dX)"] = dict(bound="tensor", ms=gemm_ms, work=flops, calls=2 * n_gemm, hbm_bytes=io_bytes)
+            res["gemm_tf32x3 (forward projections)"] = dict(bound="tensor", ms=gemm_ms, work=flops, calls=n_gemm, hbm_bytes=io_bytes)
+        # input gradient of a block's three projections: one 3xTF32 GEMM over [dY0 | dY1 | dY2] (K = 3 HC)
+        Wcat = torch.cat([W, W, W], dim=1)
+        dx_ms = timed_batches(lambda: ops.gemm_tf32x3_cat([XL, XL, XL], Wcat))
+        res["gemm_tf32x3_cat (dX over 3 dY)"] = dict(bound="tensor", ms=dx_ms, work=3 * flops, calls=n_blocks3, hbm_bytes=4 * E * HC * 4)
+        wg_ms = timed_batches(lambda: ops.wgrad_tf32x3(XL, XL))
         res["wgrad_tf32x3 (dW)"] = dict(bound="tensor", ms=wg_ms, work=flops, calls=n_gemm, hbm_bytes=io_bytes)
     for v in res.values():
         if v["bound"] == "hbm":

@@ -652,8 +652,57 @@ extern "C" int gasfm_ln_relu_bwd(const float* dy, const float* x, const float* m
 
 static int col_sum_slices(int64_t rows) {
   int64_t s = rows / 256;
-  return (int)(s < 1 ? 1 : (s > 64 ? 64 : s));
+  return (int)(s < 1 ? 1 : (s > 2 * kNumSMs ? 2 * kNumSMs : s));
 }
+
+namespace gasfm {
+// Stage 1 of the column sum for 16-byte aligned rows: a warp reads whole rows (row-contiguous, 4 rows in flight),
+// every lane keeps NV float4 column accumulators; the CTA's 8 warps are combined through shared memory and one
+// partial row per CTA goes to the workspace.  (Reading 32-column strips of every row instead left most of each
+// DRAM page unused: 86 us for a [50k, 256] matrix, cold.)
+template <int NV>
+__global__ void __launch_bounds__(256) col_sum_rows_kernel(const float* __restrict__ x, int64_t ld, int64_t rows, int width,
+                                                           int64_t rows_per_cta, float* __restrict__ ws) {
+  extern __shared__ float part[];                      // [8 warps][width]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nvec = width / 4;
+  float4 acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r_end = r_begin + rows_per_cta < rows ? r_begin + rows_per_cta : rows;
+  for (int64_t r0 = r_begin + wid; r0 < r_end; r0 += 8 * 4) {
+    float4 v4[4][NV];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = r0 + 8 * u;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int vi = lane + 32 * v;
+        v4[u][v] = (r < r_end && vi < nvec) ? ld_stream4(x + r * ld + 4 * vi) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        acc[v].x += v4[u][v].x; acc[v].y += v4[u][v].y; acc[v].z += v4[u][v].z; acc[v].w += v4[u][v].w;
+      }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int vi = lane + 32 * v;
+    if (vi < nvec) *reinterpret_cast<float4*>(part + wid * width + 4 * vi) = acc[v];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < width; c += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w * width + c];
+    ws[(int64_t)blockIdx.x * width + c] = t;
+  }
+}
+}  // namespace gasfm
 
 extern "C" size_t gasfm_col_sum_ws_bytes(int64_t rows, int width) {
   const int s = col_sum_slices(rows);
@@ -673,10 +722,20 @@ extern "C" int gasfm_col_sum(const float* x, int64_t ld, int64_t rows, int width
     return check_launch("col_sum");
   }
   GASFM_REQUIRE(ws != nullptr, "col_sum: workspace required");
-  const int per_slice = (int)((rows + slices - 1) / slices);
-  const int blocks = ceil_div(width, 32);
-  const ColReduceJob stage1{x, ld, width, (float*)ws, 0, 0};
-  col_reduce_kernel<<<dim3(blocks, slices), dim3(32, kColReduceGroups), 0, st>>>(stage1, stage1, blocks, (int)rows, per_slice, width, 1.f);
+  const int64_t per_slice = (rows + slices - 1) / slices;
+  const bool vec4 = width % 4 == 0 && ld % 4 == 0 && width <= 1024 && (uintptr_t)x % 16 == 0;
+  if (vec4) {
+    const size_t smem = (size_t)8 * width * sizeof(float);
+    const int nv = (width / 4 + 31) / 32;
+    if (nv <= 1) col_sum_rows_kernel<1><<<slices, 256, smem, st>>>(x, ld, rows, width, per_slice, (float*)ws);
+    else if (nv <= 2) col_sum_rows_kernel<2><<<slices, 256, smem, st>>>(x, ld, rows, width, per_slice, (float*)ws);
+    else if (nv <= 4) col_sum_rows_kernel<4><<<slices, 256, smem, st>>>(x, ld, rows, width, per_slice, (float*)ws);
+    else col_sum_rows_kernel<8><<<slices, 256, smem, st>>>(x, ld, rows, width, per_slice, (float*)ws);
+  } else {
+    const int blocks = ceil_div(width, 32);
+    const ColReduceJob stage1{x, ld, width, (float*)ws, 0, 0};
+    col_reduce_kernel<<<dim3(blocks, slices), dim3(32, kColReduceGroups), 0, st>>>(stage1, stage1, blocks, (int)rows, (int)per_slice, width, 1.f);
+  }
   launch_col_reduce(ColReduceJob{(const float*)ws, width, width, out, 0, 0}, nullptr, slices, 1.f, st);
   return check_launch("col_sum");
 }
