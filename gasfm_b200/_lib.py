@@ -41,11 +41,14 @@ SIGNATURES = {
     "gasfm_ln_relu_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P, _P, _P]),
     "gasfm_edge_update_fwd": (_I, [_P, _L, _P, _I, _P, _P, _P, _P, _P, _L, _P, _P, _L, _I, _F, _F, _P, _P]),
     "gasfm_split_tf32": (_I, [_P, _P, _P, _L, _P]),
-    "gasfm_linear_tf32x3_cat": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _L, _L, _I, _I, _P]),
+    "gasfm_linear_tf32x3_cat": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _L, _L, _I, _I, _P, _P]),
     "gasfm_split_f16": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "gasfm_debug_set_gemm_trace": (_I, [_P]),
     "gasfm_linear_f16x2_supported": (_I, [_L, _I, _I, _L, _L]),
-    "gasfm_linear_f16x2": (_I, [_P, _L, _P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _I, _P]),
+    "gasfm_linear_f16x2": (_I, [_P, _L, _P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _I, _P, _P]),
+    "gasfm_wgrad_f16x2_supported": (_I, [_L, _I, _I, _L, _L]),
+    "gasfm_wgrad_f16x2_ws_bytes": (_SZ, [_I, _I]),
+    "gasfm_wgrad_f16x2": (_I, [_P, _L, _P, _L, _P, _P, _L, _I, _I, _P, _P, _P, _P]),
     "gasfm_linear_tf32x3_supported": (_I, [_L, _I, _I, _L, _L]),
     "gasfm_linear_tf32x3": (_I, [_P, _L, _P, _P, _P, _P, _L, _L, _I, _I, _I, _P]),
     "gasfm_wgrad_tf32x3_supported": (_I, [_L, _I, _I, _L, _L]),

@@ -40,12 +40,12 @@ constexpr int kFATileBytes = kFBlockM * kFBlockK * 2;   // 16 KB per plane
 constexpr int kFScaleSlots = 8;                       // row-scale ring (tiles in flight between producers and epilogue)
 constexpr int kFCluster = 2;
 constexpr int kFMaxGroups = 3;                        // projections of the same A computed per M tile
-constexpr int kFTargetExp = 14;                       // scaled row maximum lies in [2^14, 2^15)
 
 struct GemmF16Args {
   const float* A; int64_t lda; const float* b_scale; const float* bias; float* C; int64_t ldc; int64_t M; int N; int K;
   int groups;                                 // B = [groups * N, K] stacked weights, C column offset g * N: one pass over A
   int tmem_cols; int accumulate; int debug;   // debug: phase-isolation bits for profiling (GASFM_GEMM_DEBUG)
+  float* a_amax;                              // optional: max |A| over the whole matrix (atomicMax; zeroed by the launcher)
   long long* trace;                           // optional [3 roles][kTraceTiles][16] SM-clock timestamps of CTA 0 (profiling)
 };
 
@@ -54,14 +54,6 @@ constexpr int kTraceTiles = 16;
   do {                                                                                               \
     if (p.trace && blockIdx.x == 0 && (it) < kTraceTiles) p.trace[((role) * kTraceTiles + (it)) * 16 + (slot)] = clock64(); \
   } while (0)
-
-// 2^(kFTargetExp - floor(log2 amax)) and its inverse, from the exponent field (clamped so that both stay normal)
-__device__ __forceinline__ void row_scale_from_amax(float amax, float& scale, float& descale) {
-  int eb = (int)((__float_as_uint(amax) >> 23) & 0xffu);
-  eb = eb < 16 + kFTargetExp ? 16 + kFTargetExp : (eb > 254 - 16 ? 254 - 16 : eb);   // zero / tiny / inf rows: harmless scale
-  scale = __uint_as_float((uint32_t)(254 + kFTargetExp - eb) << 23);
-  descale = __uint_as_float((uint32_t)(eb - kFTargetExp) << 23);
-}
 
 template <int KB>   // number of 64-wide K blocks: K <= 64 * KB
 __global__ void __cluster_dims__(kFCluster, 1, 1) __launch_bounds__(kFThreads, 1)
@@ -186,6 +178,7 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
     };
 #pragma unroll
     for (int kb = 0; kb < KB; ++kb) load_block(0, kb, buf[kb]);
+    float seen_max = 0.f;
     for (int64_t it = 0; it < my_steps; ++it) {
       // row maxima -> power-of-two scales (16 lanes share a row)
       float scale[8];
@@ -199,6 +192,7 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
 #pragma unroll
         for (int off = 1; off < 16; off <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
         float descale;
+        seen_max = fmaxf(seen_max, m);
         row_scale_from_amax(m, scale[i], descale);
         if (q == 0) descale_slot[rg + 16 * i] = descale;
       }
@@ -236,6 +230,7 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
       }
       }
     }
+    if (p.a_amax != nullptr) warp_amax_to_global(seen_max, p.a_amax);
   } else {
     // ===================== epilogue (warps 12..15 -> TMEM lane quarters 0..3) =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");
@@ -363,7 +358,7 @@ extern "C" int gasfm_linear_f16x2_supported(int64_t M, int N, int K, int64_t lda
 
 extern "C" int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi, const void* B_lo, const float* b_descale,
                                   const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int groups, int accumulate,
-                                  void* stream) {
+                                  float* a_amax, void* stream) {
   GASFM_REQUIRE(gasfm_linear_f16x2_supported(M, N, K, lda, ldc), "linear_f16x2: unsupported shape M=%lld N=%d K=%d lda=%lld ldc=%lld",
                 (long long)M, N, K, (long long)lda, (long long)ldc);
   GASFM_REQUIRE(groups >= 1 && groups <= kFMaxGroups && ldc >= (int64_t)groups * N, "linear_f16x2: 1..%d groups, ldc >= groups * N", kFMaxGroups);
@@ -381,7 +376,8 @@ extern "C" int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi,
   const int grid = (int)(pairs < kNumSMs / kFCluster ? pairs : kNumSMs / kFCluster) * kFCluster;
   static int debug = -1;
   if (debug < 0) { const char* env = getenv("GASFM_GEMM_DEBUG"); debug = env ? atoi(env) : 0; }
-  GemmF16Args args{A, lda, b_descale, bias, C, ldc, M, N, K, groups, tmem_cols, accumulate, debug, g_trace};
+  if (a_amax != nullptr) cudaMemsetAsync(a_amax, 0, sizeof(float), (cudaStream_t)stream);
+  GemmF16Args args{A, lda, b_descale, bias, C, ldc, M, N, K, groups, tmem_cols, accumulate, debug, a_amax, g_trace};
 #define LAUNCH_F16(KB)                                                                                                     \
   do {                                                                                                                     \
     static size_t allowed = 0; /* static smem (barriers, scales) also counts against the 227 KB per-CTA limit */          \

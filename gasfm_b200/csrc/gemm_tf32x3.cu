@@ -42,6 +42,7 @@ constexpr int kMaxASegments = 4;
 struct GemmArgs {
   const float* A[kMaxASegments]; int64_t lda[kMaxASegments]; int seg_k;
   const float* bias; float* C; int64_t ldc; int64_t M; int N; int K; int tmem_cols; int accumulate; int debug;
+  float* a_amax;   // optional [segments]: max |A_i| (atomicMax; zeroed by the launcher) -- scales for wgrad_f16x2
 };
 
 // CTA pairs (cluster of 2): the weight tiles B_hi / B_lo are identical for every M tile, and re-streaming them
@@ -155,6 +156,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_con
     int stage = 0; uint32_t phase = 0;
     const int64_t total = my_steps * num_k_blocks;           // K-blocks this CTA produces
     float4 buf[kPrefetch][4];
+    float seg_max[kMaxASegments] = {0.f, 0.f, 0.f, 0.f};
     auto load_block = [&](int64_t g, float4 (&v)[4]) {
       const int64_t tile = (cluster_id + (g / num_k_blocks) * num_clusters) * kCluster + cta_rank;
       const int kcol = (int)(g % num_k_blocks) * kBlockK + q * 4;
@@ -178,6 +180,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_con
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_hi = smem + (size_t)stage * stage_bytes;
           uint8_t* a_lo = a_hi + kATileBytes;
+          if (p.a_amax != nullptr) {
+            const int kc = (int)(g % num_k_blocks) * kBlockK + q * 4;
+            const int sg = kc < p.K ? kc / p.seg_k : 0;
+            float m = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              m = fmaxf(m, fmaxf(fmaxf(fabsf(buf[u][i].x), fabsf(buf[u][i].y)), fmaxf(fabsf(buf[u][i].z), fabsf(buf[u][i].w))));
+#pragma unroll
+            for (int j = 0; j < kMaxASegments; ++j) seg_max[j] = (j == sg) ? fmaxf(seg_max[j], m) : seg_max[j];
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int row = rg + 32 * i;
@@ -193,6 +205,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_con
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+    }
+    if (p.a_amax != nullptr) {
+#pragma unroll
+      for (int j = 0; j < kMaxASegments; ++j)
+        if (j * p.seg_k < p.K) warp_amax_to_global(seg_max[j], p.a_amax + j);
     }
   } else {
     // ===================== epilogue (warps 10..13 -> TMEM lane quarters 2,3,0,1) =====================
@@ -503,7 +520,8 @@ extern "C" int gasfm_linear_tf32x3_supported(int64_t M, int N, int K, int64_t ld
 }
 
 static int launch_linear_tf32x3(const float* const* A, const int64_t* lda, int n_seg, int seg_k, const float* B_hi, const float* B_lo,
-                                const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int accumulate, void* stream) {
+                                const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int accumulate, float* a_amax,
+                                void* stream) {
   CUtensorMap mh, ml, mc;
   if (make_map(&mh, B_hi, N, K, K, N / kCluster) || make_map(&ml, B_lo, N, K, K, N / kCluster) ||
       make_map_box(&mc, C, M, N, ldc, 32, 32)) return 1;
@@ -527,7 +545,8 @@ static int launch_linear_tf32x3(const float* const* A, const int64_t* lda, int n
   GemmArgs args{};
   for (int i = 0; i < n_seg; ++i) { args.A[i] = A[i]; args.lda[i] = lda[i]; }
   args.seg_k = seg_k; args.bias = bias; args.C = C; args.ldc = ldc; args.M = M; args.N = N; args.K = K;
-  args.tmem_cols = tmem_cols; args.accumulate = accumulate; args.debug = debug;
+  args.tmem_cols = tmem_cols; args.accumulate = accumulate; args.debug = debug; args.a_amax = a_amax;
+  if (a_amax != nullptr) cudaMemsetAsync(a_amax, 0, (size_t)n_seg * sizeof(float), (cudaStream_t)stream);
   gemm_tf32x3_kernel<0><<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(mh, ml, mc, args);
   return check_launch("linear_tf32x3");
 }
@@ -537,12 +556,12 @@ extern "C" int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_h
   GASFM_REQUIRE(gasfm_linear_tf32x3_supported(M, N, K, lda, ldc), "linear_tf32x3: unsupported shape M=%lld N=%d K=%d lda=%lld ldc=%lld",
                 (long long)M, N, K, (long long)lda, (long long)ldc);
   GASFM_REQUIRE(((uintptr_t)A | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C) % 16 == 0, "linear_tf32x3: pointers must be 16-byte aligned");
-  return launch_linear_tf32x3(&A, &lda, 1, K, B_hi, B_lo, bias, C, ldc, M, N, K, accumulate, stream);
+  return launch_linear_tf32x3(&A, &lda, 1, K, B_hi, B_lo, bias, C, ldc, M, N, K, accumulate, nullptr, stream);
 }
 
 extern "C" int gasfm_linear_tf32x3_cat(const float* const* A, const int64_t* lda, int n_seg, int seg_k, const float* B_hi,
                                        const float* B_lo, const float* bias, float* C, int64_t ldc, int64_t M, int N,
-                                       int accumulate, void* stream) {
+                                       int accumulate, float* a_amax, void* stream) {
   GASFM_REQUIRE(A && lda && n_seg >= 1 && n_seg <= kMaxASegments && seg_k >= 4 && seg_k % 4 == 0,
                 "linear_tf32x3_cat: 1..%d segments of a multiple of 4 columns", kMaxASegments);
   const int K = n_seg * seg_k;
@@ -553,7 +572,7 @@ extern "C" int gasfm_linear_tf32x3_cat(const float* const* A, const int64_t* lda
     bits |= (uintptr_t)A[i];
   }
   GASFM_REQUIRE(bits % 16 == 0, "linear_tf32x3_cat: pointers must be 16-byte aligned");
-  return launch_linear_tf32x3(A, lda, n_seg, seg_k, B_hi, B_lo, bias, C, ldc, M, N, K, accumulate, stream);
+  return launch_linear_tf32x3(A, lda, n_seg, seg_k, B_hi, B_lo, bias, C, ldc, M, N, K, accumulate, a_amax, stream);
 }
 
 extern "C" int gasfm_wgrad_tf32x3_supported(int64_t E, int Nout, int Kout, int64_t lddy, int64_t ldx) {

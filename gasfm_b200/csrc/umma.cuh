@@ -104,6 +104,23 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       : "memory");
 }
 
+constexpr int kFTargetExp = 14;                       // fp16 split: the scaled maximum lies in [2^14, 2^15)
+
+// 2^(kFTargetExp - floor(log2 amax)) and its inverse, from the exponent field (clamped so that both stay normal)
+__device__ __forceinline__ void row_scale_from_amax(float amax, float& scale, float& descale) {
+  int eb = (int)((__float_as_uint(amax) >> 23) & 0xffu);
+  eb = eb < 16 + kFTargetExp ? 16 + kFTargetExp : (eb > 254 - 16 ? 254 - 16 : eb);   // zero / tiny / inf rows: harmless scale
+  scale = __uint_as_float((uint32_t)(254 + kFTargetExp - eb) << 23);
+  descale = __uint_as_float((uint32_t)(eb - kFTargetExp) << 23);
+}
+
+// largest |value| seen by a warp -> one atomicMax on the bit pattern (non-negative floats order like unsigned ints)
+__device__ __forceinline__ void warp_amax_to_global(float m, float* dst) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && dst != nullptr) atomicMax(reinterpret_cast<unsigned int*>(dst), __float_as_uint(m));
+}
+
 // ---- host: tensor maps via the driver entry point (no link-time dependency on libcuda) -----------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -394,7 +394,7 @@ def gemm_tc(a, b, bias=None, out=None, accumulate=False, kind=None):
         hi, lo, descale = _split_f16(b)
         with _lib.device_guard(a.device):
             _lib.call("gasfm_linear_f16x2", _lib.ptr(a), lda, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(descale), bias_ptr,
-                      _lib.ptr(c), N, M, N, K, 1, int(bool(accumulate)), _lib.stream_ptr())
+                      _lib.ptr(c), N, M, N, K, 1, int(bool(accumulate)), None, _lib.stream_ptr())
         return c
     hi, lo = _split_tf32(b)
     with _lib.device_guard(a.device):
@@ -406,28 +406,31 @@ def gemm_tc(a, b, bias=None, out=None, accumulate=False, kind=None):
 F16X2_MAX_GROUPS = 3
 
 
-def gemm_f16x2_groups(a, weights, biases):
+def gemm_f16x2_groups(a, weights, biases, want_amax=False):
     """Several projections y_g = a W_g^T + b_g of the SAME a (equal output widths) in one kernel: a is read from
-    HBM once.  Returns the [M, G*N] buffer; y_g = out[:, g*N:(g+1)*N]."""
+    HBM once.  Returns the [M, G*N] buffer; y_g = out[:, g*N:(g+1)*N].  ``want_amax``: also return max|a| as a
+    1-element device tensor (the producers see every row maximum anyway; it scales the fp16 weight gradient)."""
     a, lda = _rows(a)
     M, K = a.shape
     G, N = len(weights), weights[0].shape[0]
     hi, lo, descale = _split_f16(torch.cat(list(weights), dim=0))
     bias = torch.cat([b if b is not None else torch.zeros(N, dtype=torch.float32, device=a.device) for b in biases])
     c = torch.empty((M, G * N), dtype=torch.float32, device=a.device)
+    amax = torch.empty(1, dtype=torch.float32, device=a.device) if want_amax else None
     with _lib.device_guard(a.device):
         _lib.call("gasfm_linear_f16x2", _lib.ptr(a), lda, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(descale), _lib.ptr(bias),
-                  _lib.ptr(c), G * N, M, N, K, G, 0, _lib.stream_ptr())
-    return c
+                  _lib.ptr(c), G * N, M, N, K, G, 0, _lib.ptr(amax), _lib.stream_ptr())
+    return (c, amax) if want_amax else c
 
 
 def gemm_tf32x3(a, b, bias=None, out=None, accumulate=False):
     return gemm_tc(a, b, bias, out, accumulate, kind="tf32x3")
 
 
-def gemm_tf32x3_cat(a_list, b, bias=None):
+def gemm_tf32x3_cat(a_list, b, bias=None, want_amax=False):
     """[A_0 | A_1 | ..] b^T for 1..4 matrices A_i [M, seg_k] that live in separate buffers; b is [N, n * seg_k].
-    One pass over every A_i and one write of the result (3xTF32: no per-row scale to agree on across the A_i)."""
+    One pass over every A_i and one write of the result (3xTF32: no per-row scale to agree on across the A_i).
+    ``want_amax``: also return max|A_i| per segment as an n-element device tensor."""
     import ctypes
 
     rows = [_rows(a) for a in a_list]
@@ -439,10 +442,12 @@ def gemm_tf32x3_cat(a_list, b, bias=None):
     c = torch.empty((M, N), dtype=torch.float32, device=b.device)
     ptrs = (ctypes.c_void_p * n)(*[r[0].data_ptr() for r in rows])
     lds = (ctypes.c_int64 * n)(*[r[1] for r in rows])
+    amax = torch.empty(n, dtype=torch.float32, device=b.device) if want_amax else None
     with _lib.device_guard(b.device):
         _lib.call("gasfm_linear_tf32x3_cat", ptrs, lds, n, seg_k, _lib.ptr(hi), _lib.ptr(lo),
-                  _lib.ptr(None if bias is None else bias.contiguous()), _lib.ptr(c), N, M, N, 0, _lib.stream_ptr())
-    return c
+                  _lib.ptr(None if bias is None else bias.contiguous()), _lib.ptr(c), N, M, N, 0, _lib.ptr(amax),
+                  _lib.stream_ptr())
+    return (c, amax) if want_amax else c
 
 
 def gemm_f16x2(a, b, bias=None, out=None, accumulate=False):
@@ -475,7 +480,32 @@ def wgrad_tf32x3(dy, x, with_bias=False):
     return (dw, db) if with_bias else dw
 
 
-def _linear_backward(x, weight, dy, need_x, need_w, need_b, dx_out=None):
+# "f16x2": fp16 weight gradient where both operand maxima are at hand (grouped projections), 3xTF32 otherwise
+WGRAD_KIND = os.environ.get("GASFM_WGRAD", "f16x2")
+
+
+def wgrad_f16x2_supported(E, n_out, k_out, lddy, ldx):
+    return bool(_lib.load().gasfm_wgrad_f16x2_supported(int(E), int(n_out), int(k_out), int(lddy), int(ldx)))
+
+
+def wgrad_f16x2(dy, x, amax_dy, amax_x, with_bias=False):
+    """dW = dy^T x (and db) on the fp16 tensor-core path; amax_dy / amax_x: 1-element DEVICE tensors holding max|dy|,
+    max|x| (any upper bound within a few binades works), as returned by gemm_tf32x3_cat / gemm_f16x2_groups."""
+    dy, lddy = _rows(dy)
+    x, ldx = _rows(x)
+    E, n_out = dy.shape
+    k_out = x.shape[1]
+    dev = dy.device
+    dw = torch.empty((n_out, k_out), dtype=torch.float32, device=dev)
+    db = torch.empty(n_out, dtype=torch.float32, device=dev) if with_bias else None
+    ws = torch.empty(_lib.size_query("gasfm_wgrad_f16x2_ws_bytes", n_out, k_out) // 4, dtype=torch.float32, device=dev)
+    with _lib.device_guard(dev):
+        _lib.call("gasfm_wgrad_f16x2", _lib.ptr(dy), lddy, _lib.ptr(x), ldx, _lib.ptr(amax_dy), _lib.ptr(amax_x), E, n_out, k_out,
+                  _lib.ptr(dw), _lib.ptr(db), _lib.ptr(ws), _lib.stream_ptr())
+    return (dw, db) if with_bias else dw
+
+
+def _linear_backward(x, weight, dy, need_x, need_w, need_b, dx_out=None, amax=None):
     """Gradients of y = x W^T + b on the tensor-core kernels; ``dx_out``: accumulate dX into this buffer."""
     dy = dy.contiguous()
     dx = dw = db = None
@@ -490,7 +520,9 @@ def _linear_backward(x, weight, dy, need_x, need_w, need_b, dx_out=None):
             dx = dy @ weight
     if need_w or need_b:
         ldx = x.stride(0) if x.stride(1) == 1 else K
-        if wgrad_tf32x3_supported(M, N, K, N, ldx):
+        if amax is not None and WGRAD_KIND == "f16x2" and wgrad_f16x2_supported(M, N, K, N, ldx):
+            dw, db = wgrad_f16x2(dy, x, amax[0], amax[1], with_bias=True)
+        elif wgrad_tf32x3_supported(M, N, K, N, ldx):
             dw, db = wgrad_tf32x3(dy, x, with_bias=True)
         else:
             dw = dy.t() @ x
@@ -527,8 +559,9 @@ class _LinearMulti(torch.autograd.Function):
         lda = x.stride(0) if x.stride(1) == 1 else K
         if (GEMM_KIND == "f16x2" and 2 <= len(weights) <= F16X2_MAX_GROUPS and all(w.shape[0] == N for w in weights)
                 and gemm_f16x2_supported(M, N, K, lda, len(weights) * N)):
-            out = gemm_f16x2_groups(x, weights, biases)          # x is read once for all projections
+            out, ctx.x_amax = gemm_f16x2_groups(x, weights, biases, want_amax=True)   # x is read once for all projections
             return tuple(out[:, g * N:(g + 1) * N] for g in range(len(weights)))
+        ctx.x_amax = None
         return tuple(gemm_tc(x, w, b) for w, b in zip(weights, biases))
 
     @staticmethod
@@ -545,10 +578,12 @@ class _LinearMulti(torch.autograd.Function):
         if fused_dx:
             # dX = [dY_0 | dY_1 | ..] [W_0; W_1; ..]: one pass over every dY_i, one write of dX
             dys = [dy.contiguous() for dy in dys]
-            dx = gemm_tf32x3_cat(dys, torch.cat([w.t() for w in weights], dim=1))
+            dx, dy_amax = gemm_tf32x3_cat(dys, torch.cat([w.t() for w in weights], dim=1), want_amax=True)
         for i, (w, dy) in enumerate(zip(weights, dys)):
+            # both operand maxima are known (x from the forward GEMM, dY_i from the GEMM above): fp16 weight gradient
+            amax = (dy_amax[i:i + 1], ctx.x_amax) if (fused_dx and ctx.x_amax is not None) else None
             g, dw, db = _linear_backward(x, w, dy, need_x and not fused_dx, ctx.needs_input_grad[1 + 2 * i],
-                                         ctx.needs_input_grad[2 + 2 * i], dx_out=None if fused_dx else dx)
+                                         ctx.needs_input_grad[2 + 2 * i], dx_out=None if fused_dx else dx, amax=amax)
             if need_x and not fused_dx:
                 dx = g
             grads += [dw, db]

@@ -196,7 +196,9 @@ GASFM_API int gasfm_linear_tf32x3(const float* A, int64_t lda, const float* B_hi
  * models/layers.py:329,426,941) instead of one GEMM plus two read-modify-write accumulations. */
 GASFM_API int gasfm_linear_tf32x3_cat(const float* const* A, const int64_t* lda, int n_seg, int seg_k,
                             const float* B_hi, const float* B_lo, const float* bias, float* C, int64_t ldc,
-                            int64_t M, int N, int accumulate, void* stream);
+                            int64_t M, int N, int accumulate,
+                            float* a_amax /* optional [n_seg]: receives max |A_i| (for gasfm_wgrad_f16x2) */,
+                            void* stream);
 
 /* Same product on the fp16 tensor-core path (twice the tf32 MMA rate) with a SCALED 2 x FP16 split:
  * every row of A and of B is multiplied by a power of two that puts its largest magnitude in [2^14, 2^15)
@@ -213,7 +215,17 @@ GASFM_API int gasfm_linear_f16x2_supported(int64_t M, int N, int K, int64_t lda,
  * [g*N, (g+1)*N) of C (ldc >= groups*N).  Several projections of the same input read A from HBM once. */
 GASFM_API int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi, const void* B_lo,
                        const float* b_descale, const float* bias, float* C, int64_t ldc,
-                       int64_t M, int N, int K, int groups, int accumulate, void* stream);
+                       int64_t M, int N, int K, int groups, int accumulate,
+                       float* a_amax /* optional [1]: receives max |A| (for gasfm_wgrad_f16x2) */, void* stream);
+
+/* Weight gradient on the fp16 path: dW = dY^T X (+ db), each operand scaled by ONE power of two derived from its largest
+ * magnitude (amax_dy[1], amax_x[1]: DEVICE scalars, as left behind by the GEMMs above that read the same matrices).
+ * Nout in {128, 256}, Kout in {64, 128, 192, 256}; ws: gasfm_wgrad_f16x2_ws_bytes.  Error ~1e-6 of max|dW|. */
+GASFM_API int gasfm_wgrad_f16x2_supported(int64_t E, int Nout, int Kout, int64_t lddy, int64_t ldx);
+GASFM_API size_t gasfm_wgrad_f16x2_ws_bytes(int Nout, int Kout);
+GASFM_API int gasfm_wgrad_f16x2(const float* dY, int64_t lddy, const float* X, int64_t ldx,
+                      const float* amax_dy, const float* amax_x, int64_t E, int Nout, int Kout,
+                      float* dW, float* dbias, void* ws, void* stream);
 
 /* Weight gradient of the same projections: dW[Nout,Kout] = dY[E,Nout]^T * X[E,Kout], 3xTF32 on tcgen05,
  * deterministic split-K over the SMs.  ``ws`` needs gasfm_wgrad_tf32x3_ws_bytes(Nout,Kout) bytes. */

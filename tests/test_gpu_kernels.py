@@ -592,6 +592,30 @@ def test_linear_multi_sums_input_gradients_in_one_pass(M, K, widths):
         assert rel_err(b.grad, r.grad.cpu().numpy()) < GRAD_TOL
 
 
+@pytest.mark.parametrize("E,Nout,Kout", [(64, 128, 64), (1000, 256, 256), (4099, 128, 192), (70001, 256, 64), (200003, 256, 256)])
+@pytest.mark.parametrize("slack", [1.0, 37.0])
+def test_wgrad_f16x2_has_fp32_accuracy(E, Nout, Kout, slack):
+    """dW = dY^T X on the fp16 tensor-core path (MN-major operands written by the producer warps, one power-of-two scale
+    per operand from the matrix maximum): error against fp64 no worse than the 3xTF32 kernel's bound (1e-5 of the
+    largest entry), with rows of dY spanning 5 decades and the maxima overestimated by ``slack`` (any bound works)."""
+    torch.manual_seed(E + Nout)
+    dy = torch.randn(E, Nout, device=DEV) * 10.0 ** torch.randint(-5, 1, (E, 1), device=DEV).float() * 1e-3
+    x = torch.relu(torch.randn(E, Kout, device=DEV) * 3)
+    assert ops.wgrad_f16x2_supported(E, Nout, Kout, Nout, Kout)
+    ady, ax = (dy.abs().max() * slack).reshape(1), (x.abs().max() * slack).reshape(1)
+    dw, db = ops.wgrad_f16x2(dy, x, ady, ax, with_bias=True)
+    ref = dy.double().t() @ x.double()
+    assert ((dw.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+    refb = dy.double().sum(0)
+    assert ((db.double() - refb).abs().max() / refb.abs().max()).item() < 2e-6
+    # the maxima the GEMMs leave behind are the true ones
+    w = torch.randn(64, Kout, device=DEV)
+    _, amax_x = ops.gemm_f16x2_groups(x, [w, w], [None, None], want_amax=True) if Kout >= 64 else (None, ax)
+    assert torch.equal(amax_x, x.abs().max().reshape(1))
+    _, amax_cat = ops.gemm_tf32x3_cat([dy, 2 * dy], torch.randn(32, 2 * Nout, device=DEV), want_amax=True)
+    assert torch.equal(amax_cat, torch.stack([dy.abs().max(), (2 * dy).abs().max()]))
+
+
 @pytest.mark.parametrize("E,Nout,Kout", [(70001, 256, 256), (5000, 48, 80), (30000, 64, 64), (999, 32, 32)])
 def test_wgrad_fused_bias_gradient(E, Nout, Kout):
     torch.manual_seed(E)
