@@ -148,7 +148,8 @@ def kernel_roofline(cfg, peaks, peak_kind):
     Edge-attention kernels: HBM-bound; achieved = algorithmic bytes / time over the
     measured copy bandwidth.  Projection GEMMs (fwd + dX): the scaled 2 x FP16 split (three kind::f16 MMAs per
     product at the bf16 rate) leaves them HBM-bound: achieved = (read A + write C) / time; the tensor share is
-    listed as ``tensor_frac``.  Weight gradients (and GASFM_GEMM=tf32x3): 3xTF32, tensor-bound: achieved =
+    listed as ``tensor_frac``; the fp16 weight gradient likewise.  Concatenated input gradient (and GASFM_GEMM=tf32x3):
+    3xTF32, tensor-bound: achieved =
     3 * 2MNK / time over the tf32 rate, taken as half of the measured dense bf16 rate; HBM fraction listed too.
     Every E-sized operand (E x 256 fp32 = 507 MB) exceeds the 126 MB L2, so launches are cold.
     ``calls_per_step`` x time picks the dominant kernel of the step."""
@@ -201,8 +202,15 @@ def kernel_roofline(cfg, peaks, peak_kind):
         Wcat = torch.cat([W, W, W], dim=1)
         dx_ms = timed_batches(lambda: ops.gemm_tf32x3_cat([XL, XL, XL], Wcat))
         res["gemm_tf32x3_cat (dX over 3 dY)"] = dict(bound="tensor", ms=dx_ms, work=3 * flops, calls=n_blocks3, hbm_bytes=4 * E * HC * 4)
-        wg_ms = timed_batches(lambda: ops.wgrad_tf32x3(XL, XL))
-        res["wgrad_tf32x3 (dW)"] = dict(bound="tensor", ms=wg_ms, work=flops, calls=n_gemm, hbm_bytes=io_bytes)
+        if f16 and ops.WGRAD_KIND == "f16x2" and ops.wgrad_f16x2_supported(E, HC, HC, HC, HC):
+            # fp16 weight gradient (operand maxima come from the GEMMs above): HBM-bound like the forward projections
+            amax = XL.abs().max().reshape(1)
+            wg_ms = timed_batches(lambda: ops.wgrad_f16x2(XL, XL, amax, amax))
+            res["wgrad_f16x2 (dW)"] = dict(bound="hbm", ms=wg_ms, work=io_bytes, calls=n_gemm,
+                                           tensor_frac=flops / wg_ms / 1e9 / (2.0 * peak_tf32))
+        else:
+            wg_ms = timed_batches(lambda: ops.wgrad_tf32x3(XL, XL))
+            res["wgrad_tf32x3 (dW)"] = dict(bound="tensor", ms=wg_ms, work=flops, calls=n_gemm, hbm_bytes=io_bytes)
     for v in res.values():
         if v["bound"] == "hbm":
             v["achieved"], v["peak"], v["unit"] = v["work"] / v["ms"] / 1e6, peak_gbs, "GB/s"
