@@ -33,6 +33,32 @@ def test_library_exports_every_declared_symbol():
     assert lib.gasfm_abi_version() == 1
 
 
+def test_tensor_core_kernel_shape_predicates():
+    """Host-only shape predicates that steer the dispatch in gasfm_b200.ops (no kernel is launched): the scaled 2xFP16
+    GEMM takes 64 <= K <= 256, everything else stays on 3xTF32; the fp16 weight gradient takes Nout in {128, 256} and
+    Kout a multiple of 64; row strides must keep rows 16-byte aligned."""
+    lib = _lib.load()
+    E = 495592
+    assert lib.gasfm_linear_f16x2_supported(E, 256, 256, 256, 256) == 1
+    assert lib.gasfm_linear_f16x2_supported(E, 256, 64, 64, 768) == 1           # grouped output, ldc = 3 N
+    assert lib.gasfm_linear_f16x2_supported(E, 32, 32, 32, 32) == 0             # shipped d = 32: narrow K
+    assert lib.gasfm_linear_f16x2_supported(E, 256, 512, 512, 256) == 0         # K > 256: tile does not fit the registers
+    assert lib.gasfm_linear_f16x2_supported(E, 40, 256, 256, 40) == 0           # N % 16
+    assert lib.gasfm_linear_tf32x3_supported(E, 32, 32, 32, 32) == 1
+    assert lib.gasfm_linear_tf32x3_supported(E, 256, 768, 256, 256) == 1        # concatenated dY (K = 3 d)
+    assert lib.gasfm_linear_tf32x3_supported(E, 256, 2, 2, 256) == 0            # first block (K = 2): write-bound kernel instead
+    assert lib.gasfm_linear_tf32x3_supported(E, 256, 256, 255, 256) == 0        # misaligned rows
+    assert lib.gasfm_wgrad_f16x2_supported(E, 256, 256, 256, 256) == 1
+    assert lib.gasfm_wgrad_f16x2_supported(E, 256, 64, 256, 64) == 1
+    assert lib.gasfm_wgrad_f16x2_supported(E, 64, 64, 64, 64) == 0              # -> wgrad_small / 3xTF32
+    assert lib.gasfm_wgrad_f16x2_supported(E, 256, 32, 256, 32) == 0
+    assert lib.gasfm_wgrad_tf32x3_supported(E, 256, 32, 256, 32) == 1
+    assert lib.gasfm_wgrad_small_supported(64, 64, 64, 64) == 1
+    # workspace queries are pure host arithmetic too
+    assert lib.gasfm_wgrad_f16x2_ws_bytes(256, 256) == (148 * 256 * 256 + 148 * 256) * 4
+    assert lib.gasfm_col_sum_ws_bytes(100, 256) == 0 and lib.gasfm_col_sum_ws_bytes(50000, 256) == 195 * 256 * 4
+
+
 def test_header_cites_the_reference_for_each_entry_point():
     text = open(os.path.join(ROOT, "include", "gasfm_b200.h")).read()
     for cite in ("utils/dataset_utils.py:86-113", "utils/sparse_utils.py:436-449", "models/layers.py:329-335",
