@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """Benchmark of the GASFM graph-attention hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3_d256|cfg3|cfg2]
+    torchrun --nproc-per-node N bench.py --gpus N ...        (N > 1: one rank per GPU)
 
-A "step" is one forward+backward of the full GASFM model over one synthetic scene.  At N=1 the
-workload is BASELINE.json configs[1]: 300 views x 50k points, ~500k observations, n_feat_proj=256,
-4 heads, 12 layers (other widths as shipped).  Prints ONE JSON line (see the task contract):
-  value  GAT-layer edges/s fwd+bwd with the scene resident in HBM  (E x 26 edge-level GATs / step)
-  e2e    same metric through the public API with the scene in pinned HOST memory: H2D copy of the
-         observations, index build, forward+backward, D2H of the predictions -- every step
-  roofline      the dominant edge-attention kernel timed alone with CUDA events (achieved GB/s of
-                algorithmic bytes over the measured HBM peak)
-  cpu_baseline  the CPU oracle (port of the reference's PyTorch path) on the host cores, bounded sample
+A "step" is one forward+backward of the full GASFM model over one synthetic scene.  The default workload is the
+configuration BASELINE.json's target sentence names -- configs[2]: 1,000 views x 300k points, ~5M observations -- at
+n_feat_proj=256, 4 heads, 12 layers (other widths as shipped).  With N > 1 the SAME scene is track-sharded over the
+GPUs (strong scaling; --scaling weak grows the scene with N instead).  Prints ONE JSON line (see the task contract):
+  value   GAT-layer edges/s fwd+bwd with the scene resident in HBM (E x 26 edge-level GATs / step), CUDA-graph replay
+  e2e     same metric through the public API with the scene in pinned HOST memory: H2D copy of the observations,
+          index build, forward+backward, D2H of the predictions -- every step
+  roofline       the dominant hot kernel timed alone with CUDA events (algorithmic bytes / time over the measured HBM
+                 peak), the other hot kernels under ``all_kernels``, and the layer-level floor under ``layer``
+  cpu_baseline   the CPU oracle (port of the reference's PyTorch path) on the host cores, bounded sample   (N = 1)
+  parity         N = 1: GPU vs that CPU run on the same sample scene and weights;  N > 1: the track-sharded model vs
+                 the single-GPU model on a small scene (outputs and every parameter gradient)
+  cfg2           N = 1: the same measurements on configs[1] (300 x 50k, ~500k observations), the round-1 headline
 """
 import argparse
 import json
@@ -32,7 +37,9 @@ CFG2 = dict(name="cfg2", m=300, n=50_000, n_obs=500_000, n_feat_proj=256, num_la
 CFG3 = dict(name="cfg3", m=1000, n=300_000, n_obs=5_000_000, n_feat_proj=32, num_layers=12, seed=0)
 CFG3_WIDE = dict(CFG3, name="cfg3_d256", n_feat_proj=256)
 WORKLOADS = {"cfg2": CFG2, "cfg3": CFG3, "cfg3_d256": CFG3_WIDE}
+DEFAULT_WORKLOAD = "cfg3_d256"
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
+METRIC = "gat_layer_edges_per_sec_fwd_bwd"
 
 
 def measured_peaks():
@@ -84,31 +91,24 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_workload(cfg):
+_SCENES = {}
+
+
+def observations(m, n, n_obs, seed):
+    from gasfm_b200.synthetic import synthetic_observations
+
+    key = (m, n, n_obs, seed)
+    if key not in _SCENES:
+        _SCENES[key] = synthetic_observations(m, n, n_obs, seed)
+    return _SCENES[key]
+
+
+def make_model(cfg, layers=None):
     from gasfm_b200.config import gasfm_conf
     from gasfm_b200.models.graph_attn_sfm import GraphAttnSfMNet
-    from gasfm_b200.scene import Scene
-    from oracle import gasfm_cpu  # synthetic scene generator only (shared with the tests)
 
-    idx, vals = gasfm_cpu.synthetic_observations(cfg["m"], cfg["n"], cfg["n_obs"], cfg["seed"])
-    scene = Scene.from_observations(idx, vals, cfg["m"], cfg["n"])
-    conf = gasfm_conf(n_feat_proj=cfg["n_feat_proj"], num_layers=cfg["num_layers"])
     torch.manual_seed(cfg["seed"])
-    model = GraphAttnSfMNet(conf)
-    return conf, model, scene
-
-
-def surrogate_loss(out):
-    """Scalar touching both predictions (the reprojection loss is outside the hot path)."""
-    return out["Ps_norm"].square().mean() + out["pts3D"].square().mean()
-
-
-def step_device(model, scene):
-    model.zero_grad(set_to_none=True)
-    out = model(scene)
-    loss = surrogate_loss(out)
-    loss.backward()
-    return loss
+    return GraphAttnSfMNet(gasfm_conf(n_feat_proj=cfg["n_feat_proj"], num_layers=layers or cfg["num_layers"]))
 
 
 def timed(fn, steps, warmup, sync_dist=False):
@@ -142,26 +142,25 @@ def timed_batches(fn, batches=5, per_batch=5, warmup=5):
     return float(np.mean(kept))
 
 
-def kernel_roofline(cfg, peaks, peak_kind):
+# ---------------------------------------------------------------------------------------------
+# roofline of the hot kernels, each timed alone
+# ---------------------------------------------------------------------------------------------
+def kernel_roofline(cfg, peaks, peak_kind, forward_ms=None):
     """The hot kernels alone at the workload's shapes (E observations, width d = n_feat_proj), CUDA events.
 
-    Edge-attention kernels: HBM-bound; achieved = algorithmic bytes / time over the
-    measured copy bandwidth.  Projection GEMMs (fwd + dX): the scaled 2 x FP16 split (three kind::f16 MMAs per
-    product at the bf16 rate) leaves them HBM-bound: achieved = (read A + write C) / time; the tensor share is
-    listed as ``tensor_frac``; the fp16 weight gradient likewise.  Concatenated input gradient (and GASFM_GEMM=tf32x3):
-    3xTF32, tensor-bound: achieved =
-    3 * 2MNK / time over the tf32 rate, taken as half of the measured dense bf16 rate; HBM fraction listed too.
-    Every E-sized operand (E x 256 fp32 = 507 MB) exceeds the 126 MB L2, so launches are cold.
-    ``calls_per_step`` x time picks the dominant kernel of the step."""
+    Edge-attention kernels, the scaled 2 x FP16 projections and the fp16 weight gradient are HBM-bound: achieved =
+    algorithmic bytes (GEMMs: read A once + write C once) / time over the measured copy bandwidth.  The
+    concatenated input gradient (3xTF32) is tensor-bound: achieved = ALGORITHMIC 2 M N K / time over the tf32 MMA rate
+    (half the measured dense bf16 rate); the three split products it actually issues are listed as ``pipe_util``.
+    Every E-sized operand exceeds the 126 MB L2, so launches are cold.  ``calls_per_step`` x time picks the dominant one."""
     from gasfm_b200 import ops
     from gasfm_b200.index import ObservationIndex
-    from oracle import gasfm_cpu
 
     peak_gbs = float(peaks["hbm_gbs"])
     peak_tf32 = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
     dev = torch.device("cuda")
     H, HC, L = 4, cfg["n_feat_proj"], cfg["num_layers"]
-    idx, _ = gasfm_cpu.synthetic_observations(cfg["m"], cfg["n"], cfg["n_obs"], cfg["seed"])
+    idx, _ = observations(cfg["m"], cfg["n"], cfg["n_obs"], cfg["seed"])
     E = idx.shape[1]
     oi = ObservationIndex(torch.from_numpy(idx).to(dev), cfg["m"], cfg["n"])
     torch.manual_seed(0)
@@ -184,33 +183,33 @@ def kernel_roofline(cfg, peaks, peak_kind):
         W = torch.randn(HC, HC, device=dev) / HC ** 0.5
         n_blocks3 = L - 1                             # stateful blocks: lin_l x2 + lin_proj of the same x
         n_gemm = 3 * n_blocks3 + 2                    # + lin_l x2 in the final update
-        flops = 3 * 2.0 * E * HC * HC                 # three split products
+        flops = 2.0 * E * HC * HC                     # algorithmic flops of one projection
         io_bytes = 2 * E * HC * 4                     # read A once, write C once (weights stay in L2)
         f16 = ops.GEMM_KIND == "f16x2" and ops.gemm_f16x2_supported(E, HC, HC, HC, HC)
         gemm_ms = timed_batches(lambda: ops.gemm_tc(XL, W))
         if f16:
-            # scaled 2 x FP16 split: the tensor time is half the 3xTF32 kernel's, the kernel is HBM-bound.
-            # Forward: the three projections of a block in one launch (A read once, three outputs written).
             grp_ms = timed_batches(lambda: ops.gemm_f16x2_groups(XL, [W, W, W], [None, None, None]))
             res["gemm_f16x2 x3 groups (forward projections)"] = dict(
-                bound="hbm", ms=grp_ms, work=4 * E * HC * 4, calls=n_blocks3, tensor_frac=3 * flops / grp_ms / 1e9 / (2.0 * peak_tf32))
+                bound="hbm", ms=grp_ms, work=4 * E * HC * 4, calls=n_blocks3, pipe_util=9 * flops / grp_ms / 1e9 / (2.0 * peak_tf32))
             res["gemm_f16x2 (single projection)"] = dict(bound="hbm", ms=gemm_ms, work=io_bytes, calls=2,
-                                                         tensor_frac=flops / gemm_ms / 1e9 / (2.0 * peak_tf32))
+                                                         pipe_util=3 * flops / gemm_ms / 1e9 / (2.0 * peak_tf32))
         else:
-            res["gemm_tf32x3 (forward projections)"] = dict(bound="tensor", ms=gemm_ms, work=flops, calls=n_gemm, hbm_bytes=io_bytes)
+            res["gemm_tf32x3 (forward projections)"] = dict(bound="tensor", ms=gemm_ms, work=flops, calls=n_gemm, hbm_bytes=io_bytes,
+                                                            pipe_util=3 * flops / gemm_ms / 1e9 / peak_tf32)
         # input gradient of a block's three projections: one 3xTF32 GEMM over [dY0 | dY1 | dY2] (K = 3 HC)
         Wcat = torch.cat([W, W, W], dim=1)
         dx_ms = timed_batches(lambda: ops.gemm_tf32x3_cat([XL, XL, XL], Wcat))
-        res["gemm_tf32x3_cat (dX over 3 dY)"] = dict(bound="tensor", ms=dx_ms, work=3 * flops, calls=n_blocks3, hbm_bytes=4 * E * HC * 4)
+        res["gemm_tf32x3_cat (dX over 3 dY)"] = dict(bound="tensor", ms=dx_ms, work=3 * flops, calls=n_blocks3, hbm_bytes=4 * E * HC * 4,
+                                                     pipe_util=9 * flops / dx_ms / 1e9 / peak_tf32)
         if f16 and ops.WGRAD_KIND == "f16x2" and ops.wgrad_f16x2_supported(E, HC, HC, HC, HC):
-            # fp16 weight gradient (operand maxima come from the GEMMs above): HBM-bound like the forward projections
             amax = XL.abs().max().reshape(1)
             wg_ms = timed_batches(lambda: ops.wgrad_f16x2(XL, XL, amax, amax))
             res["wgrad_f16x2 (dW)"] = dict(bound="hbm", ms=wg_ms, work=io_bytes, calls=n_gemm,
-                                           tensor_frac=flops / wg_ms / 1e9 / (2.0 * peak_tf32))
+                                           pipe_util=3 * flops / wg_ms / 1e9 / (2.0 * peak_tf32))
         else:
             wg_ms = timed_batches(lambda: ops.wgrad_tf32x3(XL, XL))
-            res["wgrad_tf32x3 (dW)"] = dict(bound="tensor", ms=wg_ms, work=flops, calls=n_gemm, hbm_bytes=io_bytes)
+            res["wgrad_tf32x3 (dW)"] = dict(bound="tensor", ms=wg_ms, work=flops, calls=n_gemm, hbm_bytes=io_bytes,
+                                            pipe_util=3 * flops / wg_ms / 1e9 / peak_tf32)
     for v in res.values():
         if v["bound"] == "hbm":
             v["achieved"], v["peak"], v["unit"] = v["work"] / v["ms"] / 1e6, peak_gbs, "GB/s"
@@ -227,70 +226,340 @@ def kernel_roofline(cfg, peaks, peak_kind):
             "all_kernels": {k: {"bound": v["bound"], "ms": round(v["ms"], 4), "calls_per_step": v["calls"],
                                 "achieved": round(v["achieved"], 1), "unit": v["unit"], "frac": round(v["frac"], 4),
                                 **({"hbm_frac": v["hbm_frac"]} if "hbm_frac" in v else {}),
-                                **({"tensor_frac": round(v["tensor_frac"], 4)} if "tensor_frac" in v else {})}
+                                **({"pipe_util": round(v["pipe_util"], 4)} if "pipe_util" in v else {})}
                             for k, v in res.items()}}
+    if forward_ms:
+        # fused-layer floor of SURVEY.md 8d: x read once, x_out written once, the per-edge index once -- per block
+        floor_bytes = E * ((HC + HC) * 4 + 8) * L
+        floor_ms = floor_bytes / peak_gbs / 1e6
+        roof["layer"] = {"floor_bytes_forward": floor_bytes, "floor_ms_forward": round(floor_ms, 3),
+                         "forward_ms_per_scene": round(forward_ms, 3), "frac": round(floor_ms / forward_ms, 4)}
     return roof
 
 
-def cpu_baseline(cfg, layers=1, repeats=1):
-    """The oracle (= port of the reference's PyTorch path, materialising what the reference
-    materialises) forward+backward on the host cores.  Bounded sample: the same scene and widths
-    but ``layers`` GASFM blocks instead of 12 (the reference's memory use grows by ~10 GB per
-    block at this size); edges/s counts the 2*(layers+1) edge-level GATs run."""
-    from gasfm_b200.config import gasfm_conf
-    from gasfm_b200.models.graph_attn_sfm import GraphAttnSfMNet
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the reference's PyTorch path) on the host cores, bounded sample
+# ---------------------------------------------------------------------------------------------
+CPU_SAMPLE_LAYERS = 2          # blocks 0 (width 2 -> d) and 1 (d -> d) + the final update: 6 edge-level GATs, 4 at full width
+CPU_SAMPLE_OBS = 500_000       # the reference's materialise-everything style needs ~10 GB per full-width block at this size
+
+
+def cpu_sample_cfg(cfg):
+    """Bounded sample of a workload for the CPU arm: the same views, density, widths and weights-init seed, but
+    ``CPU_SAMPLE_OBS`` observations (a proportional subset of the tracks) and ``CPU_SAMPLE_LAYERS`` of the blocks."""
+    frac = min(1.0, CPU_SAMPLE_OBS / cfg["n_obs"])
+    return dict(cfg, n=max(1000, int(round(cfg["n"] * frac))), n_obs=int(round(cfg["n_obs"] * frac)), num_layers=CPU_SAMPLE_LAYERS)
+
+
+def sample_loss(out):
+    return out["Ps_norm"].square().mean() + out["pts3D"].square().mean()
+
+
+def cpu_baseline(cfg, repeats=1):
+    """-> (cpu_baseline dict, seconds, reference outputs / gradients for the parity check)."""
     from oracle import gasfm_cpu
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    idx, vals = gasfm_cpu.synthetic_observations(cfg["m"], cfg["n"], cfg["n_obs"], cfg["seed"])
-    scene = gasfm_cpu.scene_from_sparse(torch.from_numpy(idx), torch.from_numpy(vals), cfg["m"], cfg["n"])
-    torch.manual_seed(cfg["seed"])
-    model = GraphAttnSfMNet(gasfm_conf(n_feat_proj=cfg["n_feat_proj"], num_layers=layers))
+    s = cpu_sample_cfg(cfg)
+    idx, vals = observations(s["m"], s["n"], s["n_obs"], s["seed"])
+    scene = gasfm_cpu.scene_from_sparse(torch.from_numpy(idx), torch.from_numpy(vals), s["m"], s["n"])
+    model = make_model(s)
     params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
     E = idx.shape[1]
-    best = float("inf")
+    best, out = float("inf"), None
     for _ in range(repeats):
         for p in params.values():
             p.grad = None
         t0 = time.perf_counter()
         out = gasfm_cpu.gasfm_forward(params, scene)
-        surrogate_loss(out).backward()
+        sample_loss(out).backward()
         best = min(best, time.perf_counter() - t0)
-    n_gat = 2 * (layers + 1)
-    return {"value": E * n_gat / best, "unit": "edges/s", "cores": cores, "kind": "port",
-            "sample": f"same scene (E={E}), same widths, {layers} of {cfg['num_layers']} blocks "
-                      f"({n_gat} edge-level GATs), fwd+bwd, best of {repeats}, {best:.2f} s"}, best
+    n_gat = 2 * (s["num_layers"] + 1)
+    ref = {"out": {k: out[k].detach() for k in ("Ps_norm", "pts3D")},
+           "grads": {k: p.grad.detach() for k, p in params.items() if p.grad is not None}}
+    info = {"value": E * n_gat / best, "unit": "edges/s", "cores": cores, "kind": "port",
+            "sample": f"{s['m']} views x {s['n']} points (E={E}: the workload's density on a subset of its tracks), same widths, "
+                      f"{s['num_layers']} of {cfg['num_layers']} blocks ({n_gat} edge-level GATs, {n_gat - 2} at full width), "
+                      f"fwd+bwd, best of {repeats}, {best:.2f} s"}
+    return info, best, ref
+
+
+def _grad_error(got, want):
+    """Worst per-parameter gradient error, each scaled by max(|g_param|, 1e-3 * largest gradient) (tests/conftest.py)."""
+    gscale = 1e-3 * max(float(v.abs().max()) for v in want.values())
+    worst, key = 0.0, None
+    for k, w in want.items():
+        err = float((got[k] - w).abs().max()) / max(gscale, float(w.abs().max()))
+        if err > worst:
+            worst, key = err, k
+    return worst, key
+
+
+def parity_vs_cpu(cfg, ref, dev):
+    """The GPU model on the CPU arm's sample scene with the same weights: outputs and all gradients vs the oracle."""
+    from gasfm_b200.scene import Scene
+
+    s = cpu_sample_cfg(cfg)
+    idx, vals = observations(s["m"], s["n"], s["n_obs"], s["seed"])
+    model = make_model(s).to(dev)
+    out = model(Scene.from_observations(idx, vals, s["m"], s["n"]).to(dev))
+    sample_loss(out).backward()
+    errs = {k: float((out[k].detach().cpu() - ref["out"][k]).abs().max() / max(1.0, float(ref["out"][k].abs().max())))
+            for k in ("Ps_norm", "pts3D")}
+    got = {k: p.grad.detach().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    worst, key = _grad_error(got, ref["grads"])
+    return {"against": "CPU oracle (fp32) on the cpu_baseline sample scene, same weights", "E": int(idx.shape[1]),
+            "max_err_outputs": errs, "tolerance_outputs": 1e-4, "worst_grad_err": worst, "worst_grad_param": key,
+            "tolerance_grads": 2e-3, "ok": bool(max(errs.values()) < 1e-4 and worst < 2e-3)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = dict(CFG2)
+    cfg = dict(WORKLOADS[args.workload])
     times, base = [], None
     for i in range(args.warmup + args.steps):
-        base, t = cpu_baseline(cfg, layers=1, repeats=1)
+        base, t, _ = cpu_baseline(cfg, repeats=1)
         if i >= args.warmup:
             times.append(t)
-    E = int(base["sample"].split("E=")[1].split(")")[0])
+    s = cpu_sample_cfg(cfg)
+    E = observations(s["m"], s["n"], s["n_obs"], s["seed"])[0].shape[1]
     ms = 1e3 * float(np.mean(times))
-    value = E * 4 / (ms / 1e3)
+    value = E * 2 * (s["num_layers"] + 1) / (ms / 1e3)
     base["value"] = value
-    line = {"impl": "reference", "metric": "gat_layer_edges_per_sec_fwd_bwd", "value": value, "unit": "edges/s",
+    E_full = observations(cfg["m"], cfg["n"], cfg["n_obs"], cfg["seed"])[0].shape[1] if cfg["n_obs"] <= 1_000_000 else cfg["n_obs"]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "edges/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(cfg, E, 1), "cpu_baseline": base,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(cfg, E_full, 1, "strong"), "cpu_baseline": base,
             "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(cfg, E, n_gpus):
-    return {"workload": f"{cfg['name']}: GASFM fwd+bwd, {cfg['m']} views x {cfg['n']} points, E={E} observations, "
+def workload_config(cfg, E, n_gpus, scaling):
+    return {"workload": f"{cfg['name']}: GASFM fwd+bwd, {cfg['m']} views x {cfg['n']} points, E~{E} observations, "
                         f"n_feat_proj={cfg['n_feat_proj']}, 4 heads, {cfg['num_layers']} layers, shipped other widths",
             "edge_level_gats_per_step": 2 * (cfg["num_layers"] + 1),
-            "cache": f"inputs larger than L2 (one [E,{cfg['n_feat_proj']}] fp32 tensor = {E * cfg['n_feat_proj'] * 4 / 1e6:.0f} MB vs 126 MB L2)",
-            "parallelism": "single GPU" if n_gpus == 1 else f"tracks sharded over {n_gpus} GPUs"}
+            "cache": f"inputs larger than L2 (one [E,{cfg['n_feat_proj']}] fp32 tensor = {E * cfg['n_feat_proj'] * 4 / 1e6 / n_gpus:.0f} MB per GPU vs 126 MB L2)",
+            "parallelism": "single GPU" if n_gpus == 1 else
+                           f"tracks sharded over {n_gpus} GPUs ({scaling} scaling), per-view softmax partials merged by peer-memory kernels over NVLink"}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def measure_workload(cfg, args, dev, rank, world, exchange, scaling):
+    """Device-resident step (graph replay), forward only, and the end-to-end step of one workload."""
+    from gasfm_b200 import _lib
+    from gasfm_b200 import dist as gdist
+    from gasfm_b200.graphs import GraphedStep
+    from gasfm_b200.scene import Scene
+
+    sync = world > 1
+    weak = sync and scaling == "weak"
+    m = cfg["m"]
+    n_total, obs_total = (cfg["n"] * world, cfg["n_obs"] * world) if weak else (cfg["n"], cfg["n_obs"])
+    idx, vals = observations(m, n_total, obs_total, cfg["seed"])
+    E_total = idx.shape[1]
+    if sync:
+        scene_host = gdist.shard_scene(idx, vals, m, n_total, rank, world, exchange).pin_memory()
+    else:
+        scene_host = Scene.from_observations(idx, vals, m, n_total).pin_memory()
+    model = make_model(cfg).to(dev)
+    n_gat = 2 * (cfg["num_layers"] + 1)
+    scene_dev = scene_host.to(dev).prepare()
+    bucket = gdist.LocalGradBucket(model, exchange) if sync else None
+
+    def loss_fn(out):
+        # replicated term (every rank evaluates it) + rank-local term (its own tracks); N = 1: the plain mean over all points
+        return out["Ps_norm"].square().mean() + out["pts3D"].square().sum() / (4 * n_total)
+
+    def step(scene):
+        if bucket is not None:
+            bucket.prepare()
+        else:
+            model.zero_grad(set_to_none=True)
+        out = model(scene)
+        loss = loss_fn(out)
+        loss.backward()
+        if bucket is not None:
+            bucket.allreduce()
+        return out, loss
+
+    step(scene_dev)
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count
+    n_eager = 3
+    eager_ms = timed(lambda: step(scene_dev), n_eager, 1, sync_dist=sync)
+    launches = (_lib.launch_count - l0) // (n_eager + 1)
+    recompute = bool(__import__("gasfm_b200.ops", fromlist=["ops"]).activation_recompute_enabled())
+
+    # the device-resident step is replayed as ONE CUDA graph (same kernels, no per-launch host overhead); sharded steps too:
+    # their exchanges are peer-memory kernels, not NCCL calls
+    step_fn, graphed, gstep = (lambda: step(scene_dev)), False, None
+    if not args.no_graph and (not sync or isinstance(exchange, gdist.PeerExchange)):
+        ok = 1
+        try:
+            torch.cuda.empty_cache()
+            gstep = GraphedStep(model, scene_dev, loss_fn, warmup=2,
+                                before_forward=bucket.prepare if bucket else None,
+                                after_backward=bucket.allreduce if bucket else None)
+        except Exception as exc:  # capture is an optimisation; report and fall back to eager timing
+            print(f"[bench] rank {rank}: CUDA graph capture failed, timing eagerly: {exc}", file=sys.stderr)
+            ok = 0
+        if sync:
+            flag = torch.tensor([ok], device=dev)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+            ok = int(flag.item())
+        if ok:
+            step_fn, graphed = gstep, True
+        else:
+            gstep = None
+            torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    ms = timed(step_fn, args.steps, args.warmup, sync_dist=sync)
+    clocks = sampler.stop()
+    del gstep, step_fn
+    torch.cuda.empty_cache()
+
+    def fwd_only():
+        with torch.no_grad():
+            model(scene_dev)
+    fwd_ms = timed(fwd_only, max(3, args.steps // 2), 2, sync_dist=sync)
+
+    # ---- end to end: host scene -> device -> index build -> fwd+bwd -> predictions back on the host ----
+    holder = {}
+
+    def step_e2e():
+        out, loss = step(scene_host.to(dev, non_blocking=True))
+        holder["Ps"] = out["Ps_norm"].detach().cpu()
+        holder["pts"] = out["pts3D"].detach().cpu()
+        holder["loss"] = float(loss.detach())
+    del scene_dev
+    torch.cuda.empty_cache()
+    e2e_ms = timed(step_e2e, max(3, args.steps // 2), 2, sync_dist=sync)
+    h2d = (scene_host.x.values.numel() * 4 + scene_host.x.indices.numel() * 8 +
+           scene_host.x.cam_per_pts.numel() * 8 + scene_host.x.pts_per_cam.numel() * 8 +
+           sum(w.valid_indices.numel() * 8 for k, w in scene_host.graph_wrappers.items() if k.endswith("2global")))
+    d2h = holder["Ps"].numel() * 4 + holder["pts"].numel() * 4 + 4
+    if sync:
+        t = torch.tensor([h2d, d2h], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t)
+        h2d, d2h = int(t[0].item()), int(t[1].item())
+    if exchange is not None:
+        exchange.check()
+    return {"E": E_total, "n_total": n_total, "ms": ms, "value": E_total * n_gat / (ms / 1e3), "eager_ms": eager_ms,
+            "forward_ms": fwd_ms, "e2e_ms": e2e_ms, "e2e_value": E_total * n_gat / (e2e_ms / 1e3), "h2d": int(h2d), "d2h": int(d2h),
+            "launches": int(launches), "graphed": graphed, "clocks": clocks, "recompute": recompute}
+
+
+def parity_sharded_vs_single(dev, rank, world, exchange):
+    """A small scene through the track-sharded model on all ranks and through the single-GPU model on rank 0: outputs
+    and every parameter gradient must agree (the driver's pytest box has one GPU; this is the NCCL-free multi-GPU path's
+    driver-side parity record)."""
+    from gasfm_b200 import dist as gdist
+    from gasfm_b200.scene import Scene
+
+    cfg = dict(CFG2, n=20_000, n_obs=200_000, num_layers=2, seed=1)
+    idx, vals = observations(cfg["m"], cfg["n"], cfg["n_obs"], cfg["seed"])
+    model = make_model(cfg).to(dev)
+    g = torch.Generator().manual_seed(1)
+    wP = torch.rand(cfg["m"], 3, 4, generator=g).to(dev)
+    wX = torch.rand(4, cfg["n"], generator=g).to(dev)
+    sh = gdist.shard_scene(idx, vals, cfg["m"], cfg["n"], rank, world, exchange).to(dev)
+    lo, hi = sh.shard.col_begin, sh.shard.col_end
+    bucket = gdist.LocalGradBucket(model, exchange)
+    bucket.prepare()
+    o = model(sh)
+    ((o["Ps_norm"] * wP).sum() + (o["pts3D"] * wX[:, lo:hi]).sum()).backward()
+    bucket.allreduce()
+    got = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    got_out = {"Ps_norm": o["Ps_norm"].detach().clone(), "pts3D": o["pts3D"].detach().clone()}
+    exchange.check()
+    res = None
+    if rank == 0:
+        model.zero_grad(set_to_none=True)
+        o1 = model(Scene.from_observations(idx, vals, cfg["m"], cfg["n"]).to(dev))
+        ((o1["Ps_norm"] * wP).sum() + (o1["pts3D"] * wX).sum()).backward()
+        want = {k: p.grad.detach() for k, p in model.named_parameters() if p.grad is not None}
+        worst, key = _grad_error(got, want)
+        e_ps = float((got_out["Ps_norm"] - o1["Ps_norm"]).abs().max() / max(1.0, float(o1["Ps_norm"].abs().max())))
+        e_pts = float((got_out["pts3D"] - o1["pts3D"][:, lo:hi]).abs().max() / max(1.0, float(o1["pts3D"].abs().max())))
+        res = {"against": f"single-GPU model on rank 0, {cfg['m']} x {cfg['n']} scene (E={idx.shape[1]}), d=256, 2 blocks",
+               "max_err_outputs": {"Ps_norm": e_ps, "pts3D(rank 0 tracks)": e_pts}, "tolerance_outputs": 1e-4,
+               "worst_grad_err": worst, "worst_grad_param": key, "tolerance_grads": 2e-3,
+               "ok": bool(max(e_ps, e_pts) < 1e-4 and worst < 2e-3)}
+    torch.distributed.barrier()
+    return res
+
+
+def run_ours(args):
+    from gasfm_b200 import _lib
+    from gasfm_b200 import dist as gdist
+
+    _lib.load()   # fail loudly if the CUDA library is missing
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    cfg = dict(WORKLOADS[args.workload])
+    peaks, peak_kind = measured_peaks()
+    exchange, exchange_kind = None, None
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+        if args.exchange == "peer":
+            try:
+                exchange, exchange_kind = gdist.PeerExchange(dev), "peer-memory kernels (cudaIpc over NVLink), CUDA-graph replay"
+            except Exception as exc:
+                print(f"[bench] rank {rank}: peer-memory exchange unavailable ({exc}); using NCCL all_gather", file=sys.stderr)
+        flag = torch.tensor([0 if exchange is None else 1], device=dev)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            exchange, exchange_kind = gdist.CollectiveExchange(dev), "NCCL all_gather + merge kernels, eager"
+
+    r = measure_workload(cfg, args, dev, rank, world, exchange, args.scaling)
+    parity = parity_sharded_vs_single(dev, rank, world, exchange) if world > 1 else None
+    if rank != 0:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+        return
+    scaling = args.scaling if world > 1 else "strong"
+    wc = workload_config(dict(cfg, n=r["n_total"]), r["E"], world, scaling)
+    if exchange_kind:
+        wc["exchange"] = exchange_kind
+    wc["activation_recompute"] = r["recompute"]
+    line = {"metric": METRIC, "value": r["value"], "unit": "edges/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True,
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wc,
+            "forward_ms_per_scene": r["forward_ms"], "cuda_graph": r["graphed"], "eager_ms_per_step": r["eager_ms"],
+            "e2e": {"value": r["e2e_value"], "unit": "edges/s", "ms_per_step": r["e2e_ms"],
+                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+            "gpu_launches": r["launches"] * args.steps, "gpu_launches_per_step": r["launches"],
+            "clocks": r["clocks"], "roofline": None, "cpu_baseline": None, "parity": parity}
+    if world == 1:
+        if not args.no_roofline:
+            line["roofline"] = kernel_roofline(cfg, peaks, peak_kind, r["forward_ms"])
+            torch.cuda.empty_cache()
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"], _, ref = cpu_baseline(cfg, repeats=1)
+            line["parity"] = parity_vs_cpu(cfg, ref, dev)
+            del ref
+        if args.workload != "cfg2" and not args.no_cfg2:
+            torch.cuda.empty_cache()
+            r2 = measure_workload(dict(CFG2), args, dev, rank, 1, None, "strong")
+            line["cfg2"] = {"workload": workload_config(CFG2, r2["E"], 1, "strong")["workload"], "value": r2["value"], "unit": "edges/s",
+                            "ms_per_step": r2["ms"], "eager_ms_per_step": r2["eager_ms"], "forward_ms_per_scene": r2["forward_ms"],
+                            "e2e": {"value": r2["e2e_value"], "ms_per_step": r2["e2e_ms"], "h2d_bytes_per_step": r2["h2d"],
+                                    "d2h_bytes_per_step": r2["d2h"]},
+                            "gpu_launches_per_step": r2["launches"], "cuda_graph": r2["graphed"], "activation_recompute": r2["recompute"]}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 def main():
@@ -299,101 +568,21 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS),
+                    help="default cfg3_d256 = BASELINE.json's target scene (1,000 x 300k, ~5M observations) at d = 256")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N>1: strong = the workload's scene itself, sharded; weak = one scene of N x the workload's tracks")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "collective"],
+                    help="N>1: peer = hand-written peer-memory kernels (graph-captured step); collective = NCCL all_gather arm (eager)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
-                    help="default cfg2 = the configuration the headline metric is quoted on")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N>1: weak = one scene of N x the workload's tracks; strong = the workload's scene itself")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-cfg2", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time the device-resident step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
-
-    from gasfm_b200 import _lib
-    _lib.load()   # fail loudly if the CUDA library is missing
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        from gasfm_b200 import dist as gdist
-        return gdist.bench_main(args, WORKLOADS[args.workload], workload_config, ClockSampler, measured_peaks, timed,
-                                surrogate_loss)
-    dev = torch.device("cuda", local_rank)
-    cfg = dict(WORKLOADS[args.workload])
-    peaks, peak_kind = measured_peaks()
-
-    conf, model, scene_host = build_workload(cfg)
-    model = model.to(dev)
-    scene_host.pin_memory()
-    E = scene_host.x.indices.shape[1]
-    n_gat = 2 * (cfg["num_layers"] + 1)
-
-    # ---- device-resident throughput ------------------------------------------------------------
-    scene_dev = scene_host.to(dev)
-    step_device(model, scene_dev)           # builds and caches the CSR/CSC index
-    torch.cuda.synchronize()
-    launches0 = _lib.launch_count
-    eager_ms = timed(lambda: step_device(model, scene_dev), max(2, args.steps // 2), args.warmup)
-    launches = (_lib.launch_count - launches0) // (max(2, args.steps // 2) + args.warmup)
-    # the device-resident step is replayed as ONE CUDA graph (same kernels, no per-launch host overhead)
-    step_fn, graphed = (lambda: step_device(model, scene_dev)), False
-    if not args.no_graph:
-        try:
-            from gasfm_b200.graphs import GraphedStep
-            gstep = GraphedStep(model, scene_dev, surrogate_loss)
-            step_fn, graphed = gstep, True
-        except Exception as exc:  # capture is an optimisation; report and fall back to eager timing
-            print(f"[bench] CUDA graph capture failed, timing eagerly: {exc}", file=sys.stderr)
-            torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ms = timed(step_fn, args.steps, args.warmup)
-    clocks = sampler.stop()
-    value = E * n_gat / (ms / 1e3)
-
-    # ---- forward only (ms per scene) -----------------------------------------------------------
-    def fwd_only():
-        with torch.no_grad():
-            model(scene_dev)
-    fwd_ms = timed(fwd_only, max(3, args.steps), 2)
-
-    # ---- end to end: host scene -> device -> fwd+bwd -> predictions back on the host -----------
-    h2d = (scene_host.x.values.numel() * 4 + scene_host.x.indices.numel() * 8 +
-           scene_host.x.cam_per_pts.numel() * 8 + scene_host.x.pts_per_cam.numel() * 8 +
-           sum(w.valid_indices.numel() * 8 for k, w in scene_host.graph_wrappers.items() if k.endswith("2global")))
-    d2h_holder = {}
-
-    def step_e2e():
-        s = scene_host.to(dev, non_blocking=True)
-        model.zero_grad(set_to_none=True)
-        out = model(s)
-        loss = surrogate_loss(out)
-        loss.backward()
-        d2h_holder["Ps"] = out["Ps_norm"].detach().cpu()
-        d2h_holder["pts"] = out["pts3D"].detach().cpu()
-        d2h_holder["loss"] = float(loss)
-    e2e_ms = timed(step_e2e, args.steps, args.warmup)
-    d2h = d2h_holder["Ps"].numel() * 4 + d2h_holder["pts"].numel() * 4 + 4
-    e2e_value = E * n_gat / (e2e_ms / 1e3)
-
-    roofline = None if args.no_roofline else kernel_roofline(cfg, peaks, peak_kind)
-    line = {"metric": "gat_layer_edges_per_sec_fwd_bwd", "value": value, "unit": "edges/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(cfg, E, 1), "forward_ms_per_scene": fwd_ms,
-            "cuda_graph": graphed, "eager_ms_per_step": eager_ms,
-            "e2e": {"value": e2e_value, "unit": "edges/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
-            "clocks": clocks, "roofline": roofline}
-    if not args.no_cpu_baseline and rank == 0:
-        del scene_dev
-        torch.cuda.empty_cache()
-        line["cpu_baseline"], _ = cpu_baseline(cfg, layers=1, repeats=1)
-    print(json.dumps(line))
+    args.warmup = max(args.warmup, 3)
+    return run_ours(args)
 
 
 if __name__ == "__main__":

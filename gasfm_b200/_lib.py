@@ -62,6 +62,20 @@ SIGNATURES = {
     "gasfm_esfm_loss_ws_bytes": (_SZ, [_L]),
     "gasfm_esfm_loss_fwd": (_I, [_P, _P, _L, _P, _P, _P, _L, _F, _I, _F, _P, _P, _P]),
     "gasfm_esfm_loss_bwd": (_I, [_P, _P, _L, _P, _P, _P, _L, _F, _I, _F, _P, _P, _I, _P, _P]),
+    "gasfm_peer_alloc": (_I, [_SZ, _c.POINTER(_P)]),
+    "gasfm_peer_free": (_I, [_P]),
+    "gasfm_peer_export": (_I, [_P, _P]),
+    "gasfm_peer_import": (_I, [_P, _c.POINTER(_P)]),
+    "gasfm_peer_close": (_I, [_P]),
+    "gasfm_peer_buffer_bytes": (_SZ, [_I, _L]),
+    "gasfm_peer_flags_bytes": (_SZ, [_I]),
+    "gasfm_peer_comm_create": (_I, [_I, _I, _P, _P, _L, _c.c_double, _c.POINTER(_P)]),
+    "gasfm_peer_comm_destroy": (_I, [_P]),
+    "gasfm_peer_comm_error": (_I, [_P, _c.POINTER(_I)]),
+    "gasfm_peer_allreduce_sum": (_I, [_P, _P, _P, _L, _F, _P]),
+    "gasfm_peer_lse_merge": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "gasfm_lse_merge_gathered": (_I, [_P, _I, _L, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "gasfm_sum_gathered": (_I, [_P, _I, _L, _L, _F, _P, _P]),
     "gasfm_csr_build_host": (_I, [_P, _L, _I, _I, _P, _P, _P]),
     "gasfm_gat_edge_fwd_host": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _I, _F, _P]),
 }
@@ -106,6 +120,13 @@ def call(name, *args):
 
             raise torch.cuda.OutOfMemoryError(f"{name}: {msg}")
         raise RuntimeError(f"{name} failed (code {rc}): {msg}")
+
+
+def call_setup(name, *args):
+    """Like ``call`` for entry points that launch no kernel (allocation, IPC set-up, status reads)."""
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed (code {rc}): {last_error()}")
 
 
 def size_query(name, *args):

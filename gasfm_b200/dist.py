@@ -1,4 +1,4 @@
-"""Track-sharded multi-GPU execution of the GASFM attention path (one process per GPU, NCCL).
+"""Track-sharded multi-GPU execution of the GASFM attention path (one process per GPU).
 
 The reference has no distributed code at all (single ``cuda:0``, ``code/main.py:78``); this is the
 B200 design of SURVEY.md section 8(e).
@@ -6,33 +6,40 @@ B200 design of SURVEY.md section 8(e).
 Partition.  Tracks (columns of the observation matrix) are split into ``world`` contiguous blocks of
 equal *edge* load, so every observation of a point lives on exactly one GPU: the column direction
 (proj2scenepoint, the per-observation update, all point-level layers) needs no communication.  View
-features ``[m, .]``, the global feature and all parameters are replicated.
+features ``[m, .]``, the global feature and all parameters are replicated, and every replicated
+quantity is computed bit-identically on every rank.
 
-Exchange.  A view's softmax runs over observations held by all ranks.  Each rank computes, with the
-same fused kernel, the un-normalised partial ``(max_g, sum_g, acc_g)`` over its local edges; the
-partials are merged like flash-attention blocks:
-    M = max_g max_g          (all-reduce MAX,  m*H floats)
-    [L, A] = sum_g e^{max_g-M} [sum_g, acc_g]   (all-reduce SUM, m*H*(C+1) floats)
-    out = A / L + bias
-The same merge (with one target) serves scenepoint2global.  Everything downstream of a merge is
-replicated compute.
+Forward exchange.  A view's softmax runs over observations held by all ranks.  Each rank computes, with
+the ordinary fused kernel, the un-normalised partial ``(max_g, sum_g, acc_g)`` over its local edges; ONE
+kernel per aggregation (``gasfm_peer_lse_merge``) pushes the partial into every peer's exchange buffer
+over NVLink, waits for the peers' flags and merges like flash-attention blocks, in rank order:
+    M = max_g max_g;   [L, A] = sum_g e^{max_g-M} [sum_g, acc_g];   out = A / L + bias
+The same merge (with one target) serves scenepoint2global.
 
-Backward.  The job's loss is the SUM over ranks of rank-local losses (replicated terms divided by
-``world``, see ``shard_loss``).  Then every gradient in the system is a *partial* whose sum over ranks
-is the true gradient: backward is linear, so replicated layers propagate partials unchanged, and the
-only communication is at the merges, where a rank's local edges need the FULL output gradient --
-one all-reduce SUM of ``dOut [m, H*C]`` per merge, mirroring the forward one.  A single flat
-all-reduce of all parameter gradients (``allreduce_gradients``) finishes the step; that is also the
-gradient exchange for scene-per-GPU data parallelism (SUM, like ``batch_loss += loss`` in
-``code/train.py:88``).
+Backward.  Replicated tensors carry FULL gradients, identical on every rank: the loss terms computed from
+replicated predictions (``Ps_norm``) are evaluated on every rank, the terms of local predictions
+(``pts3D`` of the rank's tracks) locally.  Gradients are summed exactly where a replicated tensor feeds
+local work -- the per-view query ``XR`` of the sharded aggregation, the per-view / global terms of the
+observation update (``V[row]``, ``g``; ``code/models/layers.py:941-945``) -- by one
+``gasfm_peer_allreduce_sum`` each (``[m, d]`` floats).  The output gradient of a merge is already full, so
+the backward of a merge needs no exchange at all.  Parameters applied to replicated tensors (the 145 M
+view-/global-level weights) therefore hold complete gradients without communication; only the
+observation-/point-level parameters (``is_local_parameter``; ~1 % of the model) hold partial sums, and
+one exchange over a persistent flat bucket (``LocalGradBucket``) completes them.
+
+No NCCL call is on the step's path (torch.distributed only carries the IPC handles at set-up), so a
+whole sharded step -- forward, loss, backward, exchanges -- is captured in one CUDA graph
+(``gasfm_b200.graphs.GraphedStep``).  ``CollectiveExchange`` is the library arm (all_gather through
+torch.distributed + the same merge kernels on the gathered buffer): the A/B baseline, and what the
+single-GPU multi-process tests use.
 """
-import json
-import os
+import ctypes
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _lib
 from .scene import Scene
 from .utils.constants import MIN_N_POINTS_PER_VIEW
 from .utils.dataset_utils import AxialAggregationGraphWrapper
@@ -71,10 +78,19 @@ def shard_observations(indices, values, m, n, rank, world, bounds=None):
     return local, np.asarray(values)[sel], lo, hi
 
 
-def shard_scene(indices, values, m, n, rank, world, group=None, bounds=None):
+class ShardInfo:
+    """Which tracks this rank holds, and the exchange that connects it to the other ranks."""
+
+    def __init__(self, rank, world, col_begin, col_end, n_global, exchange=None):
+        self.rank, self.world = rank, world
+        self.col_begin, self.col_end, self.n_global = col_begin, col_end, n_global
+        self.exchange = exchange
+
+
+def shard_scene(indices, values, m, n, rank, world, exchange=None, bounds=None):
     """Scene holding this rank's tracks.  ``view2global`` uses the GLOBAL per-view counts (views with
     >= 8 points anywhere, ``code/datasets/SceneData.py:174``); the view-aggregation and
-    scenepoint2global graphs are flagged so that the model merges their partials across ``group``."""
+    scenepoint2global graphs are flagged so that the model merges their partials through ``exchange``."""
     indices = np.asarray(indices)
     local_idx, local_vals, lo, hi = shard_observations(indices, values, m, n, rank, world, bounds)
     scene = Scene.from_observations(local_idx, local_vals, m, hi - lo)
@@ -83,39 +99,185 @@ def shard_scene(indices, values, m, n, rank, world, group=None, bounds=None):
     rows = torch.from_numpy(np.nonzero(pts_per_view >= MIN_N_POINTS_PER_VIEW)[0])
     scene.graph_wrappers["view2global"] = AxialAggregationGraphWrapper(
         m, 1, 0, valid_indices=torch.stack((rows, torch.zeros_like(rows))))
-    scene.shard = ShardInfo(rank, world, lo, hi, n, group)
+    scene.shard = ShardInfo(rank, world, lo, hi, n, exchange)
+    scene.x.shard = scene.shard
     scene.graph_wrappers["proj2view"].shard = scene.shard
     scene.graph_wrappers["scenepoint2global"].shard = scene.shard
     return scene
 
 
-class ShardInfo:
-    def __init__(self, rank, world, col_begin, col_end, n_global, group=None):
-        self.rank, self.world = rank, world
-        self.col_begin, self.col_end, self.n_global = col_begin, col_end, n_global
+# ---------------------------------------------------------------------------------------------
+# exchanges
+# ---------------------------------------------------------------------------------------------
+def _pad4(n):
+    return (int(n) + 3) // 4 * 4
+
+
+class _ExchangeBase:
+    """Shared front end: ``lse_merge`` and ``allreduce_sum`` on fp32 CUDA tensors."""
+
+    world = 1
+    region_floats = 0
+
+    def lse_merge(self, acc, seg_max, seg_sum, heads, bias=None):
+        """Merge per-rank un-normalised softmax partials.  acc [T,H*C] = sum_e e^{s-max} x_e, seg_max / seg_sum
+        [T,H] -> (normalised out [T,H*C] (+ bias), M [T,H], L [T,H]), bit-identical on every rank."""
+        acc, seg_max, seg_sum = acc.contiguous(), seg_max.contiguous(), seg_sum.contiguous()
+        T, hc = acc.shape
+        out = torch.empty_like(acc)
+        M, L = torch.empty_like(seg_max), torch.empty_like(seg_sum)
+        self._lse(acc, seg_max, seg_sum, None if bias is None else bias.contiguous(), T, heads, hc // heads, out, M, L)
+        return out, M, L
+
+    def allreduce_sum(self, t, out=None, scale=1.0):
+        """Sum of ``t`` over the ranks (same value on every rank; summed in rank order).  ``out`` may be ``t``."""
+        src = t.contiguous()
+        n = src.numel()
+        flat = src.view(-1)
+        if n % 4:                                   # the kernels move float4: pad odd sizes
+            flat = torch.cat((flat, flat.new_zeros(_pad4(n) - n)))
+        dst = flat if (out is t and flat.data_ptr() == t.data_ptr()) else torch.empty_like(flat)
+        for off in range(0, flat.numel(), self.region_floats):
+            cnt = min(self.region_floats, flat.numel() - off)
+            self._sum(flat[off:off + cnt], dst[off:off + cnt], cnt, float(scale))
+        res = dst[:n].view(t.shape)
+        if out is not None and out.data_ptr() != res.data_ptr():
+            out.copy_(res)
+            return out
+        return res
+
+    def barrier(self):
+        pass
+
+    def check(self):
+        """Raise if an exchange timed out (synchronises)."""
+
+
+class PeerExchange(_ExchangeBase):
+    """The product path: hand-written exchange kernels over NVLink peer memory (``csrc/peer_comm.cu``).
+
+    ``torch.distributed`` (any backend) is used ONCE, to pass the IPC handles of the exchange buffers around;
+    afterwards every exchange is a single kernel launch on the current stream."""
+
+    def __init__(self, device, group=None, region_floats=1 << 22, timeout_s=20.0):
+        self.device = torch.device(device)
         self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.region_floats = _pad4(region_floats)
+        lib = _lib.load()
+        with _lib.device_guard(self.device):
+            self._buf, self._flags = ctypes.c_void_p(), ctypes.c_void_p()
+            _lib.call_setup("gasfm_peer_alloc", lib.gasfm_peer_buffer_bytes(self.world, self.region_floats), ctypes.byref(self._buf))
+            _lib.call_setup("gasfm_peer_alloc", lib.gasfm_peer_flags_bytes(self.world), ctypes.byref(self._flags))
+            mine = []
+            for p in (self._buf, self._flags):
+                h = ctypes.create_string_buffer(64)
+                _lib.call_setup("gasfm_peer_export", p, h)
+                mine.append(h.raw)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine, group=group)
+            self._imported = []
+            bufs, flags = (ctypes.c_void_p * self.world)(), (ctypes.c_void_p * self.world)()
+            for r, (hb, hf) in enumerate(handles):
+                if r == self.rank:
+                    bufs[r], flags[r] = self._buf.value, self._flags.value
+                    continue
+                pb, pf = ctypes.c_void_p(), ctypes.c_void_p()
+                _lib.call_setup("gasfm_peer_import", ctypes.create_string_buffer(hb, 64), ctypes.byref(pb))
+                _lib.call_setup("gasfm_peer_import", ctypes.create_string_buffer(hf, 64), ctypes.byref(pf))
+                self._imported += [pb, pf]
+                bufs[r], flags[r] = pb.value, pf.value
+            self._comm = ctypes.c_void_p()
+            _lib.call_setup("gasfm_peer_comm_create", self.rank, self.world, bufs, flags, self.region_floats,
+                            float(timeout_s), ctypes.byref(self._comm))
+        dist.barrier(group=group)        # every rank has imported every buffer before the first push
+
+    @classmethod
+    def local_group(cls, world, device, region_floats=1 << 20, timeout_s=20.0):
+        """``world`` communicators inside ONE process (same-device buffers, no IPC): the ranks run on different
+        streams / threads of one GPU.  The kernels are the multi-GPU ones; used by the single-GPU tests."""
+        device = torch.device(device)
+        lib = _lib.load()
+        region = _pad4(region_floats)
+        ptrs = []
+        with _lib.device_guard(device):
+            for _ in range(world):
+                b, f = ctypes.c_void_p(), ctypes.c_void_p()
+                _lib.call_setup("gasfm_peer_alloc", lib.gasfm_peer_buffer_bytes(world, region), ctypes.byref(b))
+                _lib.call_setup("gasfm_peer_alloc", lib.gasfm_peer_flags_bytes(world), ctypes.byref(f))
+                ptrs.append((b, f))
+            group = []
+            for r in range(world):
+                ex = cls.__new__(cls)
+                ex.device, ex.group, ex.rank, ex.world, ex.region_floats = device, None, r, world, region
+                ex._buf, ex._flags = ptrs[r]
+                ex._imported = []
+                bufs, flags = (ctypes.c_void_p * world)(), (ctypes.c_void_p * world)()
+                for q in range(world):
+                    bufs[q], flags[q] = ptrs[q][0].value, ptrs[q][1].value
+                ex._comm = ctypes.c_void_p()
+                _lib.call_setup("gasfm_peer_comm_create", r, world, bufs, flags, region, float(timeout_s), ctypes.byref(ex._comm))
+                group.append(ex)
+        return group
+
+    def _lse(self, acc, mx, sm, bias, T, H, C, out, M, L):
+        with _lib.device_guard(acc.device):
+            _lib.call("gasfm_peer_lse_merge", self._comm, _lib.ptr(acc), _lib.ptr(mx), _lib.ptr(sm), _lib.ptr(bias),
+                      T, H, C, _lib.ptr(out), _lib.ptr(M), _lib.ptr(L), _lib.stream_ptr())
+
+    def _sum(self, src, dst, n, scale):
+        with _lib.device_guard(src.device):
+            _lib.call("gasfm_peer_allreduce_sum", self._comm, _lib.ptr(src), _lib.ptr(dst), n, scale, _lib.stream_ptr())
+
+    def barrier(self):
+        with _lib.device_guard(self.device):
+            _lib.call("gasfm_peer_allreduce_sum", self._comm, None, None, 0, 1.0, _lib.stream_ptr())
+
+    def check(self):
+        err = ctypes.c_int(0)
+        with _lib.device_guard(self.device):
+            _lib.call_setup("gasfm_peer_comm_error", self._comm, ctypes.byref(err))
+        if err.value:
+            raise RuntimeError("gasfm_b200: a peer-memory exchange timed out (a rank did not reach the matching exchange)")
+
+
+class CollectiveExchange(_ExchangeBase):
+    """Library arm: ``torch.distributed.all_gather`` (NCCL, or gloo with CUDA tensors) of every rank's partial, then
+    the same merge kernels on the gathered buffer.  Two launches + a collective per exchange; not graph-capturable."""
+
+    def __init__(self, device, group=None, region_floats=1 << 22):
+        self.device = torch.device(device)
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.region_floats = _pad4(region_floats)
+
+    def _gather(self, packed):
+        parts = [torch.empty_like(packed) for _ in range(self.world)]
+        dist.all_gather(parts, packed, group=self.group)
+        return torch.stack(parts).contiguous()
+
+    def _lse(self, acc, mx, sm, bias, T, H, C, out, M, L):
+        packed = torch.cat((acc.reshape(-1), mx.reshape(-1), sm.reshape(-1)))
+        region = _pad4(packed.numel())
+        if region != packed.numel():
+            packed = torch.cat((packed, packed.new_zeros(region - packed.numel())))
+        gathered = self._gather(packed)
+        with _lib.device_guard(acc.device):
+            _lib.call("gasfm_lse_merge_gathered", _lib.ptr(gathered), self.world, region, _lib.ptr(bias), T, H, C,
+                      _lib.ptr(out), _lib.ptr(M), _lib.ptr(L), _lib.stream_ptr())
+
+    def _sum(self, src, dst, n, scale):
+        gathered = self._gather(src.contiguous())
+        with _lib.device_guard(src.device):
+            _lib.call("gasfm_sum_gathered", _lib.ptr(gathered), self.world, n, n, scale, _lib.ptr(dst), _lib.stream_ptr())
+
+    def barrier(self):
+        dist.barrier(group=self.group)
 
 
 # ---------------------------------------------------------------------------------------------
-# collectives
+# the sharded aggregation
 # ---------------------------------------------------------------------------------------------
-def lse_merge(acc, seg_max, seg_sum, heads, group=None):
-    """Merge per-rank un-normalised softmax partials.  acc [T,H*C] = sum_e e^{s-max} x_e,
-    seg_max / seg_sum [T,H].  Returns (normalised out [T,H*C] without bias, M [T,H], L [T,H]),
-    identical on every rank.  Device-agnostic (NCCL on GPUs, gloo in the CPU tests)."""
-    T, hc = acc.shape
-    M = seg_max.clone()
-    dist.all_reduce(M, op=dist.ReduceOp.MAX, group=group)
-    M_safe = torch.where(torch.isinf(M), torch.zeros_like(M), M)
-    scale = torch.exp(seg_max - M_safe)                                   # 0 for ranks without edges
-    packed = torch.cat(((seg_sum * scale).unsqueeze(-1), acc.view(T, heads, -1) * scale.unsqueeze(-1)), dim=-1)
-    dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-    L = packed[..., 0].contiguous()
-    inv = torch.where(L > 0, 1.0 / L.clamp_min(1e-38), torch.zeros_like(L))
-    out = (packed[..., 1:] * inv.unsqueeze(-1)).reshape(T, hc)
-    return out, M, L
-
-
 class CudaEdgeBackend:
     """Local compute of the sharded GAT on the sm_100a kernels."""
 
@@ -132,37 +294,113 @@ class CudaEdgeBackend:
 
 class _ShardedGat(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, XL, XR, att, bias, plan, heads, group, backend):
+    def forward(ctx, XL, XR, att, bias, plan, heads, exchange, backend, lazy_xl):
         acc, mx, sm = backend.partial(XL, XR, att, plan, heads)
-        out_nobias, M, L = lse_merge(acc, mx, sm, heads, group)
-        ctx.save_for_backward(XL, XR, att, out_nobias, M, L)
-        ctx.plan, ctx.heads, ctx.group, ctx.backend, ctx.has_bias = plan, heads, group, backend, bias is not None
-        return out_nobias if bias is None else out_nobias + bias
+        out, M, L = exchange.lse_merge(acc, mx, sm, heads, bias)
+        if lazy_xl is None:
+            ctx.save_for_backward(XL, XR, att, bias, out, M, L)
+        else:
+            ctx.save_for_backward(XR, att, bias, out, M, L)       # XL is recomputed in backward (ops.LayerRecompute)
+        ctx.plan, ctx.heads, ctx.exchange, ctx.backend, ctx.lazy_xl = plan, heads, exchange, backend, lazy_xl
+        return out
 
     @staticmethod
     def backward(ctx, d_out):
         from . import ops
-        XL, XR, att, out_nobias, M, L = ctx.saved_tensors
-        d_bias = ops.col_sum(d_out) if ctx.has_bias else None               # partial (sums to the true grad)
-        d_full = d_out.contiguous().clone()
-        dist.all_reduce(d_full, op=dist.ReduceOp.SUM, group=ctx.group)    # local edges need the full dOut
-        dXL, dXR, datt = ctx.backend.backward(XL, XR, att, out_nobias, M, L, d_full, ctx.plan, ctx.heads)
-        return dXL, dXR, datt.view(att.shape), d_bias, None, None, None, None
+        if ctx.lazy_xl is None:
+            XL, XR, att, bias, out, M, L = ctx.saved_tensors
+        else:
+            XR, att, bias, out, M, L = ctx.saved_tensors
+            XL = ctx.lazy_xl()
+        # d_out is the FULL gradient of the replicated output, identical on every rank: no exchange is needed for it
+        d_out = d_out.contiguous()
+        d_bias = None if bias is None else ops.col_sum(d_out)
+        out_nobias = out if bias is None else out - bias
+        dXL, dXR, datt = ctx.backend.backward(XL, XR, att, out_nobias, M, L, d_out, ctx.plan, ctx.heads)
+        dXR = ctx.exchange.allreduce_sum(dXR)           # the query is replicated, its edges are spread over the ranks
+        return dXL, dXR, datt.view(att.shape), d_bias, None, None, None, None, None
 
 
-def sharded_gat(XL, XR, att, bias, plan, heads, group=None, backend=CudaEdgeBackend):
-    return _ShardedGat.apply(XL, XR, att, bias, plan, heads, group, backend)
+def sharded_gat(XL, XR, att, bias, plan, heads, exchange, backend=CudaEdgeBackend, lazy_xl=None):
+    return _ShardedGat.apply(XL, XR, att, bias, plan, heads, exchange, backend, lazy_xl)
 
 
-def shard_loss(replicated_terms, local_terms, world):
-    """Rank-local loss whose sum over ranks is the job's loss: terms computed identically on every
-    rank (from replicated predictions such as ``Ps_norm``) are divided by ``world``."""
-    return replicated_terms / world + local_terms
+class _ReplicatedToLocal(torch.autograd.Function):
+    """Identity on a replicated tensor that is about to be consumed by rank-local work; backward sums the partial
+    gradients of all ranks, so that the replicated producer sees the full gradient."""
+
+    @staticmethod
+    def forward(ctx, t, exchange):
+        ctx.exchange = exchange
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.exchange.allreduce_sum(g.contiguous()), None
+
+
+def replicated_to_local(t, shard):
+    if shard is None or shard.world == 1 or shard.exchange is None:
+        return t
+    return _ReplicatedToLocal.apply(t, shard.exchange)
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter gradients
+# ---------------------------------------------------------------------------------------------
+_LOCAL_MARKERS = (
+    "embed.", "prev_projfeat_norm_layer.", "residual_skipconn_proj_norm_layer.", "skip_projection.",
+    ".proj2scenepoint.", ".global2scenepoint.", "proj2view.graph_conv.lin_l.", "proj2view.graph_conv.att",
+    "graph_conv_scenepoint2global.lin_l.", "graph_conv_scenepoint2global.att",
+    "projection_feature_update.scenepoint_norm_layer.", "projection_feature_update.lin_scenepoint.",
+    "projection_feature_update.lin_proj.", "projection_feature_update.mlp.", "scenepoint_head.", "depth_head.",
+)
+_REPLICATED_IN_LOCAL = (".global2scenepoint.global_norm_layer.", ".global2scenepoint.lin_global.")
+
+
+def is_local_parameter(name):
+    """True for parameters applied to observation- or point-level tensors of a track-sharded scene: their gradient
+    on a rank is a partial sum over the rank's tracks.  Everything else acts on replicated tensors (views, global)
+    and already holds the complete gradient on every rank."""
+    name = "." + name
+    if any(k in name for k in _REPLICATED_IN_LOCAL):
+        return False
+    return any(k in name for k in _LOCAL_MARKERS)
+
+
+class LocalGradBucket:
+    """Persistent flat buffer behind the ``.grad`` of every local parameter: autograd accumulates into views of it,
+    and one in-place exchange per step completes the partial sums (no per-step ``torch.cat``)."""
+
+    def __init__(self, model, exchange):
+        self.exchange = exchange
+        named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]
+        self.local = [p for k, p in named if is_local_parameter(k)]
+        self.replicated = [p for k, p in named if not is_local_parameter(k)]
+        total = _pad4(sum(p.numel() for p in self.local))
+        dev = self.local[0].device if self.local else torch.device("cpu")
+        self.flat = torch.zeros(max(total, 4), dtype=torch.float32, device=dev)
+        self.views, off = [], 0
+        for p in self.local:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def prepare(self):
+        """Before forward: zero the bucket, point the local ``.grad``s at it, drop the replicated ones."""
+        self.flat.zero_()
+        for p, v in zip(self.local, self.views):
+            p.grad = v
+        for p in self.replicated:
+            p.grad = None
+
+    def allreduce(self):
+        """After backward: complete the local gradients (in place)."""
+        self.exchange.allreduce_sum(self.flat, out=self.flat)
 
 
 def allreduce_gradients(parameters, group=None):
-    """One flat all-reduce SUM over all parameter gradients (parameters that received no gradient on
-    a rank contribute zeros)."""
+    """One flat NCCL all-reduce SUM over ALL parameter gradients: the gradient exchange of scene-per-GPU data
+    parallelism (``batch_loss += loss`` over the scenes of a batch, ``code/train.py:61-88``)."""
     params = [p for p in parameters if p.requires_grad]
     grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
     flat = torch.cat([g.reshape(-1) for g in grads])
@@ -186,78 +424,3 @@ def gather_points(pts_local, shard, group=None):
     parts = [torch.empty_like(buf) for _ in range(shard.world)]
     dist.all_gather(parts, buf, group=group)
     return torch.cat([p[:, :s] for p, s in zip(parts, sizes)], dim=1)
-
-
-# ---------------------------------------------------------------------------------------------
-# bench.py --gpus N (N > 1): one scene of N x 50k tracks, track-sharded (weak scaling)
-# ---------------------------------------------------------------------------------------------
-def bench_main(args, cfg, workload_config, ClockSampler, measured_peaks, timed, surrogate_loss):
-    from . import _lib
-    from .config import gasfm_conf
-    from .models.graph_attn_sfm import GraphAttnSfMNet
-    from oracle import gasfm_cpu  # synthetic scene generator only
-
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dev = torch.device("cuda", local_rank)
-    dist.init_process_group("nccl", device_id=dev)
-    cfg = dict(cfg)
-    weak = getattr(args, "scaling", "weak") == "weak"
-    n_total, obs_total = (cfg["n"] * world, cfg["n_obs"] * world) if weak else (cfg["n"], cfg["n_obs"])
-    idx, vals = gasfm_cpu.synthetic_observations(cfg["m"], n_total, obs_total, cfg["seed"])
-    E_total = idx.shape[1]
-    scene_host = shard_scene(idx, vals, cfg["m"], n_total, rank, world).pin_memory()
-    torch.manual_seed(cfg["seed"])
-    model = GraphAttnSfMNet(gasfm_conf(n_feat_proj=cfg["n_feat_proj"], num_layers=cfg["num_layers"])).to(dev)
-    n_gat = 2 * (cfg["num_layers"] + 1)
-    scene_dev = scene_host.to(dev)
-
-    def step(scene):
-        model.zero_grad(set_to_none=True)
-        out = model(scene)
-        loss = shard_loss(out["Ps_norm"].square().mean(), out["pts3D"].square().sum() / (4 * n_total), world)
-        loss.backward()
-        allreduce_gradients(model.parameters())
-        return out, loss
-
-    step(scene_dev)
-    torch.cuda.synchronize()
-    l0 = _lib.launch_count
-    eager_ms = timed(lambda: step(scene_dev), max(2, args.steps // 2), args.warmup, sync_dist=True)
-    launches = (_lib.launch_count - l0) // (max(2, args.steps // 2) + args.warmup)
-    # NOTE: the sharded step is timed eagerly.  Capturing it as a CUDA graph (gasfm_b200.graphs) deadlocked with
-    # NCCL collectives inside the capture on this stack (torch 2.11 / NCCL 2.28, 2 ranks), so N>1 stays eager.
-    step_fn, graphed = (lambda: step(scene_dev)), False
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ms = timed(step_fn, args.steps, args.warmup, sync_dist=True)
-    clocks = sampler.stop()
-
-    holder = {}
-
-    def step_e2e():
-        out, loss = step(scene_host.to(dev, non_blocking=True))
-        holder["Ps"] = out["Ps_norm"].detach().cpu()
-        holder["pts"] = out["pts3D"].detach().cpu()
-        holder["loss"] = float(loss.detach())
-    e2e_ms = timed(step_e2e, args.steps, args.warmup, sync_dist=True)
-    h2d = torch.tensor([scene_host.x.values.numel() * 4 + scene_host.x.indices.numel() * 8], device=dev, dtype=torch.float64)
-    d2h = torch.tensor([holder["Ps"].numel() * 4 + holder["pts"].numel() * 4 + 4], device=dev, dtype=torch.float64)
-    dist.all_reduce(h2d)
-    dist.all_reduce(d2h)
-    if rank == 0:
-        wc = workload_config(cfg, E_total, world)
-        wc["workload"] = (f"{cfg['name']}{' per GPU, weak scaling' if weak else ', strong scaling'}: ONE scene of {cfg['m']} views x {n_total} points, "
-                          f"E={E_total} observations, tracks sharded over {world} GPUs (per-view softmax statistics "
-                          f"merged by NCCL all-reduce), n_feat_proj={cfg['n_feat_proj']}, 4 heads, {cfg['num_layers']} layers")
-        line = {"metric": "gat_layer_edges_per_sec_fwd_bwd", "value": E_total * n_gat / (ms / 1e3), "unit": "edges/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-                "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": wc,
-                "e2e": {"value": E_total * n_gat / (e2e_ms / 1e3), "unit": "edges/s", "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h.item())},
-                "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches), "clocks": clocks,
-                "cuda_graph": graphed, "eager_ms_per_step": eager_ms, "roofline": None, "cpu_baseline": None}
-        print(json.dumps(line))
-    dist.barrier()
-    dist.destroy_process_group()

@@ -1,4 +1,4 @@
-"""CUDA-graph capture of a whole GASFM step (forward + loss + backward [+ gradient all-reduce]).
+"""CUDA-graph capture of a whole GASFM step (forward + loss + backward [+ gradient exchange]).
 
 A step launches ~3,300 kernels (about 800 of them through the C ABI); once the per-GPU work is small
 (short scenes, or a big scene sharded over 8 GPUs) the Python / launch overhead of ~80 ms per step
@@ -8,18 +8,21 @@ plans, every workspace and every activation live at fixed addresses inside the g
     step = GraphedStep(model, scene, loss_fn)        # warm-up on a side stream, then capture
     loss = step()                                    # graph replay; gradients are in p.grad
 
-The captured scene is static: a new scene needs a new capture (``bench.py``'s end-to-end loop, which feeds
-a fresh host scene every step, therefore runs eagerly).  Single-GPU only for now: capturing the NCCL
-collectives of a track-sharded step deadlocked on this stack (torch 2.11 / NCCL 2.28), so ``gasfm_b200.dist``
-steps run eagerly.
+Track-sharded steps are captured the same way: their cross-GPU exchanges are plain kernel launches over
+peer memory (``gasfm_b200.dist.PeerExchange``), not NCCL calls, and the exchange sequence number lives in
+device memory, so every rank replays its own graph and the kernels synchronise among themselves.  Pass the
+``LocalGradBucket`` hooks as ``before_forward`` / ``after_backward``.  Every rank must run the same number
+of warm-up steps and replays.
+
+The captured scene is static: a new scene needs a new capture.
 """
 import torch
 
 
 class GraphedStep:
-    def __init__(self, model, scene, loss_fn, after_backward=None, warmup=3):
+    def __init__(self, model, scene, loss_fn, after_backward=None, warmup=3, before_forward=None):
         self.model, self.scene = model, scene
-        self._loss_fn, self._after = loss_fn, after_backward
+        self._loss_fn, self._after, self._before = loss_fn, after_backward, before_forward
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -29,12 +32,15 @@ class GraphedStep:
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        model.zero_grad(set_to_none=True)
+        if self._before is None:
+            model.zero_grad(set_to_none=True)       # gradients are (re)allocated inside the graph's pool
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.out, self.loss = self._eager_step(zero=False)
 
     def _eager_step(self, zero=True):
-        if zero:
+        if self._before is not None:
+            self._before()
+        elif zero:
             self.model.zero_grad(set_to_none=True)
         out = self.model(self.scene)
         loss = self._loss_fn(out)

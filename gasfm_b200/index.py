@@ -43,10 +43,16 @@ class SegmentPlan:
                       _lib.ptr(self.chunk_seg), self.max_chunks, _lib.stream_ptr())
 
     def workspace(self, nbytes, device):
-        """fp32 scratch of at least ``nbytes`` bytes, reused across calls on the same stream."""
+        """fp32 scratch of at least ``nbytes`` bytes, shared by every kernel that runs over this plan (attention
+        forward / backward, segment sums, the loss).  SINGLE-STREAM: callers on different streams must use different
+        plans (the track-sharded tests give every rank its own scene, hence its own plans)."""
         n = (nbytes + 3) // 4
         buf = self._ws.get("buf")
         if buf is None or buf.numel() < n or buf.device != device:
+            if buf is not None:
+                # never hand the old buffer back to the allocator: a captured CUDA graph (gasfm_b200.graphs) may have
+                # its address baked in and would otherwise write into freed / reused memory on its next replay
+                self._ws.setdefault("retired", []).append(buf)
             buf = torch.empty(max(n, 1), dtype=torch.float32, device=device)
             self._ws["buf"] = buf
         return buf

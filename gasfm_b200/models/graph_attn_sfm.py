@@ -7,6 +7,7 @@ from torch import nn
 from .baseNet import BaseNet
 from .layers import (EmbeddingLayer, GraphAttnSfMGlobalFeatureUpdate, GraphAttnSfMLayer, get_linear_layers,
                      relu_on_projection_features)
+from .. import ops
 from ..index import _INDEX_ATTR, ObservationIndex
 from ..utils.sparse_utils import SparseMat
 
@@ -18,7 +19,7 @@ class GraphAttnSfMNet(BaseNet):
         b = lambda key, **kw: conf.get_bool('model.' + key, **kw)  # noqa: E731
         num_layers = g('num_layers')
         n_heads = g('n_heads')
-        n_feat_proj = g('n_feat_proj')
+        n_feat_proj = self.n_feat_proj = g('n_feat_proj')
         n_feat_scenepoint = g('n_feat_scenepoint')
         n_feat_view = g('n_feat_view')
         n_feat_global = g('n_feat_global')
@@ -99,11 +100,26 @@ class GraphAttnSfMNet(BaseNet):
                     setattr(holder, _INDEX_ATTR, idx)
                 except AttributeError:
                     pass
+        idx.shard = getattr(data, "shard", None) or getattr(x, "shard", None)     # track-sharded scene (gasfm_b200.dist)
         return SparseMat(x.values, x.indices, x.cam_per_pts, x.pts_per_cam, tuple(x.shape), _index=idx)
+
+    def _wants_recompute(self, n_obs, device):
+        """Activation recompute policy.  A block keeps ~5 [E, n_feat_proj] fp32 tensors for backward (x_raw, relu(LN),
+        the three grouped projections); with recompute only x_raw stays.  "auto": switch it on when the kept
+        activations of all blocks would take more than half of the device memory."""
+        mode = ops.ACTIVATION_RECOMPUTE
+        if mode in ("on", "off"):
+            return mode == "on"
+        if not torch.is_grad_enabled():
+            return False
+        kept = 5.0 * n_obs * self.n_feat_proj * 4 * len(self.equivariant_blocks)
+        return kept > 0.5 * torch.cuda.get_device_properties(device).total_memory
 
     def forward(self, data):
         graph_structure = data.graph_wrappers
-        projection_features = self.embed(self._observations(data))   # [m,n,2] -> [m,n,d_emb]
+        observations = self._observations(data)
+        ops.set_activation_recompute(self._wants_recompute(observations.indices.shape[1], observations.values.device))
+        projection_features = self.embed(observations)   # [m,n,2] -> [m,n,d_emb]
         if not self.use_norm_proj_update:
             # in-place ReLU aliasing of the reference (layers.py:982-984): without a norm layer, block 0
             # rectifies the embedding tensor that later blocks concatenate as the init skip connection

@@ -267,26 +267,34 @@ class GraphAttnSfMLayer(Module):
         raw = prev_projection_features
         norm = self.prev_projfeat_norm_layer if self.use_norm_proj_update else None
         plain_residual = self.add_residual_skipconn_proj_update and self.skip_projection is None and norm is not None
-        if plain_residual:
-            # x_raw feeds LN+ReLU and the residual: one autograd node, so that the two gradients are summed
-            # inside the LN+ReLU backward kernel (ops.ln_relu_with_skip)
-            y, raw_vals = ops.ln_relu_with_skip(raw.values, norm.weight, norm.bias, norm.eps)
-            x, raw = raw.with_values(y), raw.with_values(raw_vals)
-        else:
-            x = relu_on_projection_features(None, _fused_norm=(raw, norm))
-        if norm is None:
-            # The reference's ReLU is in-place (layers.py:982-984): without a norm layer in front it
-            # also rectifies the values the residual branch reads.
-            raw = x
-
-        # lin_l of both attention graphs and lin_proj all read x: one autograd node, so that the three input
-        # gradients are summed inside the GEMM epilogues (ops.linear_multi)
         gfu, pfu = self.global_feature_update, self.projection_feature_update
-        d_main = x.shape[2]
+        d_main = raw.shape[2]
         conv_sp, conv_v = gfu.proj2scenepoint.graph_conv, gfu.proj2view.graph_conv
-        xl_sp, xl_v, proj = ops.linear_multi(x.values, [
-            (conv_sp.lin_l.weight, conv_sp.lin_l.bias), (conv_v.lin_l.weight, conv_v.lin_l.bias),
-            (0.25 * pfu.lin_proj.weight[:, :d_main], 0.25 * pfu.lin_proj.bias)])
+        # lin_l of both attention graphs and lin_proj all read x = relu(LN(x_raw))
+        projections = [(conv_sp.lin_l.weight, conv_sp.lin_l.bias), (conv_v.lin_l.weight, conv_v.lin_l.bias),
+                       (0.25 * pfu.lin_proj.weight[:, :d_main], 0.25 * pfu.lin_proj.bias)]
+        if plain_residual and ops.edge_block_supported(raw.values, norm.weight, projections):
+            # the whole observation-level front end of the block as ONE autograd node: LN+ReLU, the grouped projection
+            # GEMM, and in backward the concatenated input gradient + the LN backward with the residual gradient;
+            # under activation recompute it keeps only x_raw and the LayerNorm statistics (ops.EdgeBlockContext)
+            rc = ops.EdgeBlockContext(ops.activation_recompute_enabled())
+            xl_sp, xl_v, proj, raw_vals = ops.edge_block_project(raw.values, norm.weight, norm.bias, norm.eps, rc, projections)
+            x, raw = raw.with_values(None, n_feat=d_main), raw.with_values(raw_vals)
+            xl_sp, xl_v = (xl_sp, rc.xl_getter(0)), (xl_v, rc.xl_getter(1))
+        else:
+            if plain_residual:
+                # x_raw feeds LN+ReLU and the residual: one autograd node, so that the two gradients are summed
+                # inside the LN+ReLU backward kernel (ops.ln_relu_with_skip)
+                y, raw_vals = ops.ln_relu_with_skip(raw.values, norm.weight, norm.bias, norm.eps)
+                x, raw = raw.with_values(y), raw.with_values(raw_vals)
+            else:
+                x = relu_on_projection_features(None, _fused_norm=(raw, norm))
+            if norm is None:
+                # The reference's ReLU is in-place (layers.py:982-984): without a norm layer in front it
+                # also rectifies the values the residual branch reads.
+                raw = x
+            # one autograd node, so that the three input gradients are summed inside the GEMM epilogues (ops.linear_multi)
+            xl_sp, xl_v, proj = ops.linear_multi(x.values, projections)
         scenepoint_features, view_features, global_features = gfu(
             x, graph_structure,
             prev_scenepoint_features = prev_scenepoint_features,

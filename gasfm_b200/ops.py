@@ -37,7 +37,7 @@ def _rows(t):
 # ---------------------------------------------------------------------------------------------
 class _GatEdge(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, XL, XR, att, bias, plan, heads):
+    def forward(ctx, XL, XR, att, bias, plan, heads, lazy_xl=None):
         _require_cuda(XL, XR, att, bias)
         XL, ldxl = _rows(XL)
         hc = XL.shape[1]
@@ -58,13 +58,16 @@ class _GatEdge(torch.autograd.Function):
             _lib.call("gasfm_gat_edge_fwd", _lib.ptr(XL), ldxl, _lib.ptr(XR), ldxr, _lib.ptr(att_flat), _lib.ptr(bias),
                       *plan.abi_args(), heads, head_dim, LEAKY_SLOPE, 1,
                       _lib.ptr(out), _lib.ptr(seg_max), _lib.ptr(seg_sum), _lib.ptr(ws), _lib.stream_ptr())
-        ctx.save_for_backward(XL, XR, att_flat, bias, out, seg_max, seg_sum)
-        ctx.plan, ctx.heads, ctx.bcast, ctx.att_shape = plan, heads, bcast, att.shape
+        # lazy_xl: the projected sources are not kept for backward but rebuilt by the layer's EdgeBlockContext
+        ctx.save_for_backward(XL if lazy_xl is None else None, XR, att_flat, bias, out, seg_max, seg_sum)
+        ctx.plan, ctx.heads, ctx.bcast, ctx.att_shape, ctx.lazy_xl = plan, heads, bcast, att.shape, lazy_xl
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         XL, XR, att_flat, bias, out, seg_max, seg_sum = ctx.saved_tensors
+        if XL is None:
+            XL, _ = _rows(ctx.lazy_xl())
         plan, heads = ctx.plan, ctx.heads
         hc = XL.shape[1]
         head_dim = hc // heads
@@ -85,15 +88,15 @@ class _GatEdge(torch.autograd.Function):
         if ctx.bcast:
             dXR = dXR.sum(dim=0, keepdim=True)
         d_bias = None if bias is None else col_sum(d_out)
-        return dXL, dXR, datt.view(ctx.att_shape), d_bias, None, None
+        return dXL, dXR, datt.view(ctx.att_shape), d_bias, None, None, None
 
 
-def gat_edge_attention(XL, XR, att, bias, plan: SegmentPlan, heads: int):
+def gat_edge_attention(XL, XR, att, bias, plan: SegmentPlan, heads: int, lazy_xl=None):
     """out[T,HC] = GATv2 softmax-aggregate of XL rows over ``plan``'s segments (+ bias).
 
     XL [E,HC] projected sources (rows may be a strided slice), XR [T,HC] projected targets, or
     [1,HC] to broadcast one query row to every target (stateless first block)."""
-    return _GatEdge.apply(XL, XR, att, bias, plan, heads)
+    return _GatEdge.apply(XL, XR, att, bias, plan, heads, lazy_xl)
 
 
 def gat_edge_partial(XL, XR, att, plan: SegmentPlan, heads: int):
@@ -328,6 +331,10 @@ class _EdgeUpdate(torch.autograd.Function):
         dV = None
         if (has_V and ctx.needs_input_grad[4]) or (has_g and ctx.needs_input_grad[5]):
             dV = seg_sum_raw(d_out, index.by_view, scale)
+            shard = getattr(index, "shard", None)
+            if shard is not None and shard.world > 1:
+                # track-sharded scene: V and g are replicated, this rank saw only its own observations of every view
+                dV = shard.exchange.allreduce_sum(dV)
         dg = col_sum(dV, keepdim=True) if (has_g and ctx.needs_input_grad[5]) else None
         dx0 = dW0 = None
         if x0 is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
@@ -588,6 +595,118 @@ class _LinearMulti(torch.autograd.Function):
                 dx = g
             grads += [dw, db]
         return (dx, *grads)
+
+
+# ---------------------------------------------------------------------------------------------
+# one GASFM block's observation-level front end: relu(LN(x_raw)) -> lin_l (x2) + lin_proj, as ONE autograd node
+# ---------------------------------------------------------------------------------------------
+ACTIVATION_RECOMPUTE = os.environ.get("GASFM_RECOMPUTE", "auto")   # "on" | "off" | "auto" (decided per scene by the model)
+_recompute_now = False
+
+
+def set_activation_recompute(flag):
+    """Forward passes issued while this is set keep only ``x_raw`` + LayerNorm statistics per block and rebuild
+    relu(LN(x_raw)) and the projected attention sources in backward (activation memory)."""
+    global _recompute_now
+    _recompute_now = bool(flag)
+
+
+def activation_recompute_enabled():
+    return _recompute_now
+
+
+class EdgeBlockContext:
+    """What one block needs to rebuild its [E, d] activations in backward: shared by the block's projection node and
+    its two attention nodes (which fetch their ``XL`` through ``xl_getter``)."""
+
+    def __init__(self, recompute):
+        self.recompute = bool(recompute)
+        self.y = self.xl = None
+        self.args = None
+
+    def bind(self, x_raw, mean, rstd, gamma, beta, eps, weights, biases, y, xl):
+        self.args = (x_raw, mean, rstd, gamma, beta, eps, weights, biases)
+        self.n_out = weights[0].shape[0]
+        if not self.recompute:
+            self.y, self.xl = y, xl
+
+    def get_y(self):
+        if self.y is None:
+            x_raw, mean, rstd, gamma, beta, eps = self.args[:6]
+            with torch.no_grad():
+                self.y = _ln_relu_forward(x_raw, gamma, beta, eps)[1]
+        return self.y
+
+    def get_xl(self, g):
+        if self.xl is None:
+            weights, biases = self.args[6], self.args[7]
+            with torch.no_grad():
+                self.xl = gemm_f16x2_groups(self.get_y(), [w.detach() for w in weights[:2]], [b.detach() for b in biases[:2]])
+        return self.xl[:, g * self.n_out:(g + 1) * self.n_out]
+
+    def xl_getter(self, g):
+        return (lambda: self.get_xl(g)) if self.recompute else None
+
+    def release(self):
+        self.y = self.xl = None
+
+
+def edge_block_supported(x_raw, gamma, weights_and_biases):
+    """The fused front end needs the grouped fp16 GEMM (three projections of equal width, 64 <= d <= 256) and biases."""
+    if GEMM_KIND != "f16x2" or WGRAD_KIND != "f16x2" or gamma is None or len(weights_and_biases) != 3:
+        return False
+    M, K = x_raw.shape
+    N = weights_and_biases[0][0].shape[0]
+    return (x_raw.is_cuda and M >= TENSOR_CORE_MIN_ROWS and all(w.shape == (N, K) and b is not None for w, b in weights_and_biases)
+            and gemm_f16x2_supported(M, N, K, K, 3 * N) and gemm_tf32x3_supported(M, K, 3 * N, N, K)
+            and wgrad_f16x2_supported(M, N, K, N, K))
+
+
+class _EdgeBlockProject(torch.autograd.Function):
+    """(x_raw, LayerNorm, W_sp, W_v, W_proj) -> (lin_l_sp(y), lin_l_v(y), lin_proj(y), x_raw) with y = relu(LN(x_raw)).
+
+    Backward is one concatenated input-gradient GEMM, three fp16 weight gradients and the LayerNorm+ReLU backward with
+    the residual gradient added in the same pass.  With ``rc.recompute`` nothing of size [E, d] except ``x_raw`` is kept:
+    y and the two attention sources are rebuilt when the first backward node of the block asks for them."""
+
+    @staticmethod
+    def forward(ctx, x_raw, gamma, beta, eps, rc, *wb):
+        weights, biases = wb[0::2], wb[1::2]
+        x_raw, y, mean, rstd, gamma, beta = _ln_relu_forward(x_raw, gamma, beta, eps)
+        out, x_amax = gemm_f16x2_groups(y, weights, biases, want_amax=True)
+        N = weights[0].shape[0]
+        rc.bind(x_raw, mean, rstd, gamma, beta, eps, weights, biases, y, out)
+        ctx.save_for_backward(x_raw, mean, rstd, gamma, beta, x_amax, *weights)
+        ctx.rc = rc
+        ctx.set_materialize_grads(False)
+        return (*(out[:, g * N:(g + 1) * N] for g in range(3)), x_raw.view_as(x_raw))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x_raw, mean, rstd, gamma, beta, x_amax, *weights = ctx.saved_tensors
+        *dys, dskip = grads
+        rc = ctx.rc
+        N = weights[0].shape[0]
+        if all(dy is None for dy in dys):
+            zeros = torch.zeros_like(gamma)
+            return (dskip, zeros, zeros, None, None, *([None] * 6))
+        y = rc.get_y()
+        dys = [torch.zeros((x_raw.shape[0], N), dtype=torch.float32, device=x_raw.device) if dy is None else dy.contiguous()
+               for dy in dys]
+        dy_x, dy_amax = gemm_tf32x3_cat(dys, torch.cat([w.t() for w in weights], dim=1), want_amax=True)
+        wgrads = []
+        for i, dy in enumerate(dys):
+            dw, db = wgrad_f16x2(dy, y, dy_amax[i:i + 1], x_amax, with_bias=True)
+            wgrads += [dw, db]
+        del y
+        rc.release()
+        dx, dgamma, dbeta = _ln_relu_backward(x_raw, mean, rstd, gamma, beta, dy_x, add=dskip)
+        return (dx, dgamma, dbeta, None, None, *wgrads)
+
+
+def edge_block_project(x_raw, gamma, beta, eps, rc, weights_and_biases):
+    flat = [t for wb in weights_and_biases for t in wb]
+    return _EdgeBlockProject.apply(x_raw, gamma, beta, eps, rc, *flat)
 
 
 def _x0_backward(d_out, x0, W0, scale):

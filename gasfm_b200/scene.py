@@ -43,6 +43,19 @@ class Scene:
         ret.device = device
         return ret
 
+    def prepare(self):
+        """Build everything the model derives from the scene on first use -- the CSR/CSC observation index, the
+        chunk tables and the two single-target global plans -- now, so that the first forward issues no host
+        synchronisation (needed before CUDA-graph capture and by ranks that share one GPU)."""
+        from .index import index_for
+        from .models.layers import plan_for
+
+        idx = index_for(self.x)
+        idx.shard = getattr(self, "shard", None)
+        for key in ("view2global", "scenepoint2global"):
+            plan_for(self.graph_wrappers[key])
+        return self
+
     def pin_memory(self):
         """Page-lock the host tensors so that ``.to(device, non_blocking=True)`` is a true async copy."""
         self.x.values = self.x.values.pin_memory()

@@ -22,7 +22,7 @@ class SparseMat:
         self.shape = shape
         self.cam_per_pts = cam_per_pts
         self.pts_per_cam = pts_per_cam
-        self.device = self.values.device
+        self.device = self.values.device if self.values is not None else self.indices.device
         if _index is not None:
             setattr(self, _INDEX_ATTR, _index)
 
@@ -36,7 +36,8 @@ class SparseMat:
         return index_for(self)
 
     def with_values(self, values, n_feat=None):
-        """Same sparsity pattern (and cached index), new feature values."""
+        """Same sparsity pattern (and cached index), new feature values (``None`` + ``n_feat``: a placeholder
+        whose values are never materialised, e.g. relu(LN(x)) of a block that fuses it into its projections)."""
         n_feat = values.shape[1] if n_feat is None else n_feat
         return SparseMat(values, self.indices, self.cam_per_pts, self.pts_per_cam,
                          (self.shape[0], self.shape[1], n_feat), _index=getattr(self, _INDEX_ATTR, None))

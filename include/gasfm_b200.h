@@ -267,6 +267,55 @@ GASFM_API int gasfm_esfm_loss_bwd(const float* Ps, const float* pts3D, int64_t n
                                   int grad_mode, float* G, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Track-sharded multi-GPU exchange over NVLink peer memory (the reference is single-GPU,
+ * main.py:78, so there is no reference interface to cite -- these serve GATv2Conv's per-view softmax,
+ * models/layers.py:329-335, when the observations of a view are spread over several GPUs).
+ *
+ * Setup, once per process: every rank allocates an exchange buffer (gasfm_peer_buffer_bytes) and a flag array
+ * (gasfm_peer_flags_bytes) with gasfm_peer_alloc, exports both as 64-byte IPC handles, exchanges the handles through
+ * any host channel (torch.distributed here), imports its peers' handles and hands the world pointers (its own ones at
+ * index ``rank``) to gasfm_peer_comm_create.  A communicator may also be built from buffers of ONE process (several
+ * "ranks" on streams of one device): the kernels only see pointers.
+ *
+ * Every rank must issue the same sequence of exchanges with the same sizes.  An exchange is ONE kernel: push the local
+ * partial into every peer's buffer, release a flag per CTA, wait for the peers' matching CTAs, combine in rank order
+ * (bit-identical results on every rank).  No host synchronisation, no NCCL: the launches can be captured in a CUDA graph.
+ * A peer that does not show up within ``timeout_s`` sets the communicator's error flag (gasfm_peer_comm_error) instead
+ * of hanging the GPU.
+ * ------------------------------------------------------------------------------------- */
+#define GASFM_PEER_HANDLE_BYTES 64
+GASFM_API int gasfm_peer_alloc(size_t bytes, void** ptr);                 /* cudaMalloc + zero fill */
+GASFM_API int gasfm_peer_free(void* ptr);
+GASFM_API int gasfm_peer_export(void* ptr, void* handle64);               /* ptr from gasfm_peer_alloc */
+GASFM_API int gasfm_peer_import(const void* handle64, void** ptr);
+GASFM_API int gasfm_peer_close(void* ptr);                                /* ptr from gasfm_peer_import */
+GASFM_API size_t gasfm_peer_buffer_bytes(int world, int64_t region_floats);
+GASFM_API size_t gasfm_peer_flags_bytes(int world);
+GASFM_API int gasfm_peer_comm_create(int rank, int world, void* const* bufs, void* const* flags, int64_t region_floats,
+                                     double timeout_s, void** comm_out);
+GASFM_API int gasfm_peer_comm_destroy(void* comm);
+GASFM_API int gasfm_peer_comm_error(void* comm, int* error_out);          /* synchronising read of the error flag */
+
+/* out[n] = scale * sum over ranks of in[n] (n % 4 == 0, n <= region_floats; n == 0: a pure barrier).  Gradient
+ * exchanges of the sharded backward: dXR of the per-view queries, the per-view term of the observation update
+ * (models/layers.py:941-945), and the flat bucket of the observation-/point-level parameter gradients. */
+GASFM_API int gasfm_peer_allreduce_sum(void* comm, const float* in, float* out, int64_t n, float scale, void* stream);
+
+/* Log-sum-exp merge of the per-rank un-normalised softmax partials that gasfm_gat_edge_fwd(normalize = 0) produces:
+ *   M = max_r max_r;  L = sum_r e^(max_r - M) sum_r;  out = sum_r e^(max_r - M) acc_r / L (+ bias);  L == 0 -> out = bias.
+ * acc[T,H*C], seg_max / seg_sum[T,H] are this rank's partial; out[T,H*C], M[T,H], L[T,H] are identical on all ranks. */
+GASFM_API int gasfm_peer_lse_merge(void* comm, const float* acc, const float* seg_max, const float* seg_sum,
+                                   const float* bias, int n_seg, int heads, int head_dim,
+                                   float* out, float* M, float* L, void* stream);
+
+/* The same two combines on a buffer that already holds every rank's contribution (gathered[world][region_floats],
+ * region = acc | max | sum resp. the n summands), e.g. after an NCCL / gloo all_gather: the library-collective arm. */
+GASFM_API int gasfm_lse_merge_gathered(const float* gathered, int world, int64_t region_floats, const float* bias,
+                                       int n_seg, int heads, int head_dim, float* out, float* M, float* L, void* stream);
+GASFM_API int gasfm_sum_gathered(const float* gathered, int world, int64_t region_floats, int64_t n, float scale,
+                                 float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Host-buffer convenience entry points (inputs and outputs in HOST memory; allocation and the
  * host<->device copies happen inside the call).  These are what a non-torch host binds.
  * ------------------------------------------------------------------------------------- */

@@ -1,6 +1,6 @@
 """The N>1 path on CPU: world_size-2 gloo processes exercise the track partition, the log-sum-exp
-merge of per-rank softmax partials and the "every gradient is a partial" backward rule of
-gasfm_b200.dist, with the oracle standing in for the CUDA kernels (injected backend)."""
+merge of per-rank softmax partials and the "replicated tensors carry full gradients" backward rule of
+gasfm_b200.dist, with the oracle standing in for the CUDA kernels (injected backend + exchange)."""
 import os
 import tempfile
 
@@ -14,6 +14,37 @@ from oracle import gasfm_cpu
 from oracle.gatv2conv import gatv2_edge_softmax_aggregate
 
 H, C, M_VIEWS, N_TRACKS = 4, 4, 10, 120
+
+
+class TorchExchange:
+    """CPU stand-in for gasfm_b200.dist.PeerExchange (same contract: rank-ordered, identical on every rank)."""
+
+    def __init__(self, group=None):
+        self.group, self.world, self.rank = group, dist.get_world_size(group), dist.get_rank(group)
+
+    def _gather(self, t):
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(parts, t.contiguous(), group=self.group)
+        return parts
+
+    def lse_merge(self, acc, seg_max, seg_sum, heads, bias=None):
+        T, hc = acc.shape
+        accs, mxs, sms = self._gather(acc), self._gather(seg_max), self._gather(seg_sum)
+        M = torch.stack(mxs).max(dim=0).values
+        L, A = torch.zeros_like(M), torch.zeros_like(acc).view(T, heads, -1)
+        for a, mx, sm in zip(accs, mxs, sms):
+            w = torch.where(torch.isinf(mx), torch.zeros_like(mx), torch.exp(mx - torch.where(torch.isinf(M), torch.zeros_like(M), M)))
+            L = L + w * sm
+            A = A + w.unsqueeze(-1) * a.view(T, heads, -1)
+        out = torch.where(L.unsqueeze(-1) > 0, A / L.clamp_min(1e-300).unsqueeze(-1), torch.zeros_like(A)).reshape(T, hc)
+        return (out if bias is None else out + bias), M, L
+
+    def allreduce_sum(self, t, out=None, scale=1.0):
+        res = sum(self._gather(t)) * scale
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
 
 
 class OracleEdgeBackend:
@@ -79,21 +110,26 @@ def _worker(rank, world, init_file, result_file):
     dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
     try:
         idx, XL, XR, att, bias, W = _problem()
+        ex = TorchExchange()
         bounds = gdist.partition_tracks(np.bincount(idx[1], minlength=N_TRACKS), world)
         lo, hi = bounds[rank], bounds[rank + 1]
         sel = torch.from_numpy((idx[1] >= lo) & (idx[1] < hi))
         xl = XL[sel].clone().requires_grad_(True)
         xr, a, b = XR.clone().requires_grad_(True), att.clone().requires_grad_(True), bias.clone().requires_grad_(True)
         plan = {"rows": torch.from_numpy(idx[0])[sel], "T": M_VIEWS}
-        out = gdist.sharded_gat(xl, xr, a, b, plan, H, None, OracleEdgeBackend)
-        loss = gdist.shard_loss((out * W).sum(), (xl ** 2).sum() * 0.1, world)
+        out = gdist.sharded_gat(xl, xr, a, b, plan, H, ex, OracleEdgeBackend)
+        # replicated term (evaluated identically on every rank) + rank-local term
+        loss = (out * W).sum() + (xl ** 2).sum() * 0.1
         loss.backward()
-        flat = gdist.allreduce_gradients([xr, a, b])
-        assert flat.numel() == xr.numel() + a.numel() + b.numel()
+        datt_partial = a.grad.clone()
+        datt = ex.allreduce_sum(a.grad)                      # att acts on local edges: partial -> summed
+        # a replicated tensor consumed by local work: backward sums the ranks' partial gradients
+        v = torch.arange(6, dtype=torch.float64).requires_grad_(True)
+        (gdist.replicated_to_local(v, gdist.ShardInfo(rank, world, 0, 0, 0, ex)) * (rank + 1)).sum().backward()
         pts = torch.arange(4 * int(hi - lo), dtype=torch.float64).reshape(4, -1) + 1000 * rank
         gathered = gdist.gather_points(pts, gdist.ShardInfo(rank, world, int(lo), int(hi), N_TRACKS))
-        torch.save(dict(out=out.detach(), sel=sel, dxl=xl.grad, dxr=xr.grad, datt=a.grad, dbias=b.grad,
-                        gathered=gathered), f"{result_file}.{rank}")
+        torch.save(dict(out=out.detach(), sel=sel, dxl=xl.grad, dxr=xr.grad, datt=datt, datt_partial=datt_partial,
+                        dbias=b.grad, gathered=gathered, vgrad=v.grad), f"{result_file}.{rank}")
     finally:
         dist.destroy_process_group()
 
@@ -109,9 +145,12 @@ def test_sharded_gat_equals_unsharded_world2():
     for r in res:
         assert torch.allclose(r["out"], out, rtol=1e-12, atol=1e-12)               # merged output replicated on every rank
         assert torch.allclose(r["dxl"], dxl[r["sel"]], rtol=1e-10, atol=1e-12)    # local edges got their exact gradient
-        assert torch.allclose(r["dxr"], dxr, rtol=1e-10, atol=1e-12)              # partials summed to the true gradients
-        assert torch.allclose(r["datt"], datt, rtol=1e-10, atol=1e-12)
-        assert torch.allclose(r["dbias"], dbias, rtol=1e-10, atol=1e-12)
+        assert torch.allclose(r["dxr"], dxr, rtol=1e-10, atol=1e-12)              # replicated query: FULL gradient, no extra reduce
+        assert torch.allclose(r["dbias"], dbias, rtol=1e-10, atol=1e-12)          # replicated parameter: full gradient
+        assert torch.allclose(r["datt"], datt, rtol=1e-10, atol=1e-12)            # local parameter: partials summed
+        assert torch.equal(r["vgrad"], torch.full((6,), 3.0, dtype=torch.float64))
+    assert torch.equal(res[0]["out"], res[1]["out"]) and torch.equal(res[0]["dxr"], res[1]["dxr"])   # bit-identical replicas
+    assert not torch.allclose(res[0]["datt_partial"], datt)
     assert torch.equal(res[0]["gathered"], res[1]["gathered"])
     assert res[0]["gathered"].shape == (4, N_TRACKS)
 
@@ -152,8 +191,66 @@ def test_lse_merge_single_rank_identity():
             acc = torch.tensor([[2.0, 4.0], [0.0, 0.0]])
             mx = torch.tensor([[0.5], [float("-inf")]])
             sm = torch.tensor([[2.0], [0.0]])
-            out, Mx, L = gdist.lse_merge(acc, mx, sm, heads=1)
+            out, Mx, L = TorchExchange().lse_merge(acc, mx, sm, heads=1)
             assert torch.equal(out, torch.tensor([[1.0, 2.0], [0.0, 0.0]]))     # empty segment stays 0 (bias added later)
             assert torch.equal(L, sm) and torch.equal(Mx, mx)
         finally:
             dist.destroy_process_group()
+
+
+def test_parameter_classification_covers_the_shipped_model():
+    """Every parameter of the shipped configuration is either local (applied to observation / point tensors: partial
+    gradient per rank) or replicated; the local ones are the small minority that needs the gradient exchange."""
+    from gasfm_b200.config import gasfm_conf
+    from gasfm_b200.models.graph_attn_sfm import GraphAttnSfMNet
+
+    with torch.device("meta"):
+        model = GraphAttnSfMNet(gasfm_conf(n_feat_proj=256, num_layers=3))
+    names = [k for k, _ in model.named_parameters()]
+    local = [k for k in names if gdist.is_local_parameter(k)]
+    sizes = dict((k, p.numel()) for k, p in model.named_parameters())
+    assert sum(sizes[k] for k in local) < 0.1 * sum(sizes.values())
+    must_be_local = ["embed.post_embed_lin.weight", "equivariant_blocks.1.prev_projfeat_norm_layer.weight",
+                     "equivariant_blocks.1.global_feature_update.proj2view.graph_conv.lin_l.weight",
+                     "equivariant_blocks.1.global_feature_update.proj2view.graph_conv.att",
+                     "equivariant_blocks.1.global_feature_update.proj2scenepoint.graph_conv.lin_r.weight",
+                     "equivariant_blocks.1.global_feature_update.proj2scenepoint.mlp.0.weight",
+                     "equivariant_blocks.1.global_feature_update.view_and_scenepoint2global.graph_conv_scenepoint2global.lin_l.weight",
+                     "equivariant_blocks.1.projection_feature_update.lin_proj.weight",
+                     "equivariant_blocks.1.projection_feature_update.lin_scenepoint.weight",
+                     "equivariant_blocks.0.skip_projection.lin_proj.weight",
+                     "final_global_update.proj2scenepoint.graph_conv.att", "scenepoint_head.4.weight"]
+    must_be_replicated = ["equivariant_blocks.1.global_feature_update.proj2view.graph_conv.lin_r.weight",
+                          "equivariant_blocks.1.global_feature_update.proj2view.graph_conv.bias",
+                          "equivariant_blocks.1.global_feature_update.proj2view.norm_and_proj_view2proj.2.weight",
+                          "equivariant_blocks.1.global_feature_update.proj2view.mlp.0.weight",
+                          "equivariant_blocks.1.global_feature_update.view_and_scenepoint2global.graph_conv_scenepoint2global.lin_r.weight",
+                          "equivariant_blocks.1.global_feature_update.view_and_scenepoint2global.graph_conv_scenepoint2global.bias",
+                          "equivariant_blocks.1.global_feature_update.view_and_scenepoint2global.graph_conv_view2global.lin_l.weight",
+                          "equivariant_blocks.1.projection_feature_update.lin_view.weight",
+                          "equivariant_blocks.1.projection_feature_update.lin_global.weight",
+                          "equivariant_blocks.1.projection_feature_update.view_norm_layer.weight", "view_head.0.weight"]
+    for k in must_be_local:
+        assert k in names and gdist.is_local_parameter(k), k
+    for k in must_be_replicated:
+        assert k in names and not gdist.is_local_parameter(k), k
+
+
+def test_local_grad_bucket_points_gradients_at_one_flat_buffer():
+    class _Ex:
+        region_floats = 1 << 20
+
+        def allreduce_sum(self, t, out=None, scale=1.0):
+            out.copy_(2 * t)
+            return out
+
+    model = torch.nn.ModuleDict({"scenepoint_head": torch.nn.Linear(3, 2), "view_head": torch.nn.Linear(3, 2)})
+    bucket = gdist.LocalGradBucket(model, _Ex())
+    assert len(bucket.local) == 2 and len(bucket.replicated) == 2 and bucket.flat.numel() == 8
+    bucket.prepare()
+    x = torch.ones(4, 3)
+    (model["scenepoint_head"](x).sum() + model["view_head"](x).sum()).backward()
+    assert model["scenepoint_head"].weight.grad.data_ptr() == bucket.flat.data_ptr()      # accumulated in place
+    bucket.allreduce()
+    assert torch.equal(model["scenepoint_head"].weight.grad, torch.full((2, 3), 8.0))
+    assert torch.equal(model["view_head"].weight.grad, torch.full((2, 3), 4.0))

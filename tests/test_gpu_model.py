@@ -150,14 +150,58 @@ def test_full_size_properties_cfg2():
         assert torch.allclose(seg_sum_raw(XL, plan).double().sum(0), tot, rtol=1e-4, atol=1e-2)
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_track_sharded_model_matches_single_gpu():
-    """N=2 over NCCL: sharded forward/backward == single-GPU forward/backward (tools/check_sharded_model.py)."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29631",
-                        os.path.join(root, "tools", "check_sharded_model.py")], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+def test_cfg2_scale_model_matches_fp32_oracle():
+    """BASELINE.json configs[1] at FULL scene size (300 views x 50k points, ~500k observations, d=256, 4 heads) against
+    the CPU oracle in fp32 -- outputs and every gradient; depth reduced to 2 blocks + the final update (6 edge-level GATs, 4 at
+    full width), which is what the reference's materialise-everything style fits in host memory (~10 GB per wide block)."""
+    conf = gasfm_conf(n_feat_proj=256, num_layers=2)
+    m, n = 300, 50000
+    torch.manual_seed(0)
+    model = GraphAttnSfMNet(conf)
+    idx, vals = gasfm_cpu.synthetic_observations(m, n, 500000, seed=0)
+    assert idx.shape[1] > 490000
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    ref = gasfm_cpu.gasfm_forward(params, gasfm_cpu.scene_from_sparse(torch.from_numpy(idx), torch.from_numpy(vals), m, n))
+    (ref["Ps_norm"].square().mean() + ref["pts3D"].square().mean()).backward()
+    model = model.to(DEV)
+    out = model(Scene.from_observations(idx, vals, m, n).to(DEV))
+    (out["Ps_norm"].square().mean() + out["pts3D"].square().mean()).backward()
+    for key in ("Ps_norm", "pts3D"):
+        want = ref[key].detach().numpy()
+        err = np.abs(out[key].detach().cpu().numpy() - want).max() / max(1.0, np.abs(want).max())
+        assert err < OUT_TOL, (key, err)
+    want = {k: v.grad.numpy() for k, v in params.items() if v.grad is not None}
+    got = {k: p.grad.detach().cpu().numpy() for k, p in model.named_parameters()}
+    worst, key = grad_errors(got, want)
+    assert worst < GRAD_TOL, (key, worst)
+
+
+def test_activation_recompute_gives_identical_results():
+    """GASFM_RECOMPUTE: keeping only x_raw + LayerNorm statistics per block and rebuilding relu(LN(x)) and the projected
+    attention sources in backward must not change a single bit of the outputs or gradients."""
+    from gasfm_b200 import ops
+    conf = gasfm_conf(n_feat_proj=128, n_feat_view=128, n_feat_global=256, num_layers=3)
+    torch.manual_seed(3)
+    model = GraphAttnSfMNet(conf).to(DEV)
+    idx, vals = gasfm_cpu.synthetic_observations(40, 4000, 30000, seed=3)
+    scene = Scene.from_observations(idx, vals, 40, 4000).to(DEV)
+    res = {}
+    old = ops.ACTIVATION_RECOMPUTE
+    try:
+        for mode in ("off", "on"):
+            ops.ACTIVATION_RECOMPUTE = mode
+            model.zero_grad(set_to_none=True)
+            torch.cuda.reset_peak_memory_stats()
+            out = model(scene)
+            assert ops.activation_recompute_enabled() == (mode == "on")
+            kept = torch.cuda.memory_allocated()
+            _loss(out).backward()
+            res[mode] = (out["Ps_norm"].detach().clone(), out["pts3D"].detach().clone(),
+                         {k: p.grad.detach().clone() for k, p in model.named_parameters()}, kept)
+            del out
+    finally:
+        ops.ACTIVATION_RECOMPUTE = old
+    assert torch.equal(res["off"][0], res["on"][0]) and torch.equal(res["off"][1], res["on"][1])
+    for k, g in res["off"][2].items():
+        assert torch.equal(g, res["on"][2][k]), k
+    assert res["on"][3] < 0.7 * res["off"][3]          # activations held between forward and backward
