@@ -111,6 +111,23 @@ def make_model(cfg, layers=None):
     return GraphAttnSfMNet(gasfm_conf(n_feat_proj=cfg["n_feat_proj"], num_layers=layers or cfg["num_layers"]))
 
 
+def build_workload(cfg):
+    """(conf, model, host scene) of a single-GPU workload (also used by tools/profile_step.py, tools/one_step.py)."""
+    from gasfm_b200.scene import Scene
+
+    idx, vals = observations(cfg["m"], cfg["n"], cfg["n_obs"], cfg["seed"])
+    model = make_model(cfg)
+    return None, model, Scene.from_observations(idx, vals, cfg["m"], cfg["n"])
+
+
+def step_device(model, scene):
+    model.zero_grad(set_to_none=True)
+    out = model(scene)
+    loss = out["Ps_norm"].square().mean() + out["pts3D"].square().mean()
+    loss.backward()
+    return loss
+
+
 def timed(fn, steps, warmup, sync_dist=False):
     for _ in range(warmup):
         fn()

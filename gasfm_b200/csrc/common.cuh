@@ -58,6 +58,15 @@ __device__ __forceinline__ unsigned group_mask(int lane) {
   }
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: launchers remember the size they opted into
+// per (kernel slot, current device), so that a process driving several GPUs opts in on each of them.
+static inline size_t& smem_opt_in_slot(int kernel_slot) {
+  static size_t allowed[4][32] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return allowed[kernel_slot & 3][dev & 31];
+}
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace gasfm

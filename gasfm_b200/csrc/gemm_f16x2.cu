@@ -380,14 +380,11 @@ extern "C" int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi,
   GemmF16Args args{A, lda, b_descale, bias, C, ldc, M, N, K, groups, tmem_cols, accumulate, debug, a_amax, g_trace};
 #define LAUNCH_F16(KB)                                                                                                     \
   do {                                                                                                                     \
-    static size_t allowed = 0; /* static smem (barriers, scales) also counts against the 227 KB per-CTA limit */          \
-    if (smem > allowed) {                                                                                                  \
-      cudaError_t e = cudaFuncSetAttribute(gemm_f16x2_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      if (e != cudaSuccess) {                                                                                              \
-        set_error("linear_f16x2: cannot reserve %zu bytes of shared memory (%s)", smem, cudaGetErrorString(e));            \
-        return (int)e;                                                                                                     \
-      }                                                                                                                    \
-      allowed = smem;                                                                                                      \
+    /* per-device attribute: set on every call (static smem -- barriers, scales -- also counts against the 227 KB limit) */ \
+    cudaError_t e = cudaFuncSetAttribute(gemm_f16x2_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e != cudaSuccess) {                                                                                                \
+      set_error("linear_f16x2: cannot reserve %zu bytes of shared memory (%s)", smem, cudaGetErrorString(e));              \
+      return (int)e;                                                                                                       \
     }                                                                                                                      \
     gemm_f16x2_kernel<KB><<<grid, kFThreads, smem, (cudaStream_t)stream>>>(mh, ml, args);                             \
   } while (0)

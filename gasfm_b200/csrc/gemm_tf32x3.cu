@@ -528,7 +528,7 @@ static int launch_linear_tf32x3(const float* const* A, const int64_t* lda, int n
   int tmem_cols = 32;
   while (tmem_cols < 2 * N) tmem_cols <<= 1;
   const size_t smem = (size_t)kStages * (2 * kATileBytes + 2 * (size_t)N * kBlockK * 4) + 4 * 4096 + 1024;
-  static size_t smem_allowed = 0;   // static smem (barriers, bias) also counts against the 227 KB per-CTA limit
+  size_t& smem_allowed = smem_opt_in_slot(0);   // per device; static smem (barriers, bias) also counts against the 227 KB per-CTA limit
   if (smem > smem_allowed) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -597,7 +597,7 @@ extern "C" int gasfm_wgrad_tf32x3(const float* dY, int64_t lddy, const float* X,
   int tmem_cols = 32;
   while (tmem_cols < m_tiles * Kout) tmem_cols <<= 1;
   const size_t smem = (size_t)kWgStages * 2 * (a_boxes + b_boxes) * kWgBoxBytes + 1024;
-  static size_t smem_allowed = 0;
+  size_t& smem_allowed = smem_opt_in_slot(1);
   if (smem > smem_allowed) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_tf32x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("wgrad_tf32x3: cannot reserve %zu bytes of shared memory (%s)", smem, cudaGetErrorString(e)); return (int)e; }

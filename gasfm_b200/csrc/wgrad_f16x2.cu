@@ -290,7 +290,7 @@ extern "C" int gasfm_wgrad_f16x2(const float* dY, int64_t lddy, const float* X, 
   int tmem_cols = 32;
   while (tmem_cols < m_tiles * Kout) tmem_cols <<= 1;
   const size_t smem = (size_t)kHStages * 2 * ((size_t)(Nout / 64) + (Kout / 64)) * kHLbo + 1024;
-  static size_t smem_allowed = 0;
+  size_t& smem_allowed = smem_opt_in_slot(2);
   if (smem > smem_allowed) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_f16x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {

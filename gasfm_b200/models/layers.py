@@ -40,8 +40,8 @@ class LayerNorm(nn.LayerNorm):
     """``nn.LayerNorm`` (same parameters); ``relu_(ln(x))`` patterns call ``ln_relu`` to get one fused kernel."""
 
     def ln_relu(self, x):
-        if (x.dim() == 2 and x.is_cuda and x.dtype == torch.float32 and x.shape[0] >= 256 and x.shape[1] <= 1024
-                and self.elementwise_affine and self.bias is not None):
+        if (x.dim() == 2 and x.is_cuda and x.dtype == torch.float32 and x.shape[0] >= 256
+                and ops.ln_relu_width_supported(x.shape[1]) and self.elementwise_affine and self.bias is not None):
             return ops.ln_relu(x, self.weight, self.bias, self.eps)
         return F.relu(F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps))
 
@@ -282,7 +282,7 @@ class GraphAttnSfMLayer(Module):
             x, raw = raw.with_values(None, n_feat=d_main), raw.with_values(raw_vals)
             xl_sp, xl_v = (xl_sp, rc.xl_getter(0)), (xl_v, rc.xl_getter(1))
         else:
-            if plain_residual:
+            if plain_residual and ops.ln_relu_width_supported(d_main):
                 # x_raw feeds LN+ReLU and the residual: one autograd node, so that the two gradients are summed
                 # inside the LN+ReLU backward kernel (ops.ln_relu_with_skip)
                 y, raw_vals = ops.ln_relu_with_skip(raw.values, norm.weight, norm.bias, norm.eps)
@@ -706,12 +706,16 @@ def normalize_projection_features(x, norm_layer=None):
 def relu_on_projection_features(x, _fused_norm=None):
     """ReLU on the observation features (layers.py:982-984).  ``_fused_norm=(x, LayerNorm)`` runs the
     preceding LayerNorm in the same kernel (normalize_projection_features + relu, layers.py:232-234)."""
+    norm = None
     if _fused_norm is not None:
         x, norm = _fused_norm
-        if norm is None:
-            return x.with_values(ops.ln_relu(x.values))
-        return x.with_values(ops.ln_relu(x.values, norm.weight, norm.bias, norm.eps))
-    return x.with_values(ops.ln_relu(x.values))
+    if not ops.ln_relu_width_supported(x.values.shape[1]):
+        # widths the fused kernel does not take (> 256 and not a multiple of 4): plain torch
+        v = x.values if norm is None else F.layer_norm(x.values, norm.normalized_shape, norm.weight, norm.bias, norm.eps)
+        return x.with_values(F.relu(v))
+    if norm is None:
+        return x.with_values(ops.ln_relu(x.values))
+    return x.with_values(ops.ln_relu(x.values, norm.weight, norm.bias, norm.eps))
 
 
 class IdentityLayer(Module):

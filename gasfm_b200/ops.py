@@ -168,6 +168,12 @@ def col_sum(x, keepdim=False):
     return out.unsqueeze(0) if keepdim else out
 
 
+def ln_relu_width_supported(width):
+    """Mirror of the kernel's own predicate (gasfm_ln_relu_fwd / _bwd, csrc/edge_ops.cu): rows up to 1024 wide as
+    float4, or up to 256 wide scalar."""
+    return 0 < width <= 1024 and (width % 4 == 0 or width <= 256)
+
+
 def _ln_relu_forward(x, gamma, beta, eps):
     _require_cuda(x, gamma, beta)
     x = x.contiguous()

@@ -4,7 +4,7 @@ The reference instantiates its model through
 ``general_utils.get_class("models." + conf.get_string("model.type"))(conf)``
 (``code/main.py:134-136``, ``code/utils/general_utils.py:84-90``) with
 ``model.type = "graph_attn_sfm.GraphAttnSfMNet"``.  After ``install()``, ``import models.graph_attn_sfm``
-(and ``models.layers``, ``models.baseNet``, ``utils.sparse_utils``) resolve to this package, so the
+(and ``models.layers``, ``models.baseNet``, ``models.SetOfSet``) resolve to this package, so the
 reference's drivers pick up the B200 implementation without source changes.  See INTEGRATION.md."""
 import importlib
 import sys
@@ -18,13 +18,11 @@ _MAP = {
 }
 
 
-def install(override_utils=False):
-    """Make ``models.*`` resolve to gasfm_b200.  With ``override_utils`` the sparse containers
-    (``utils.sparse_utils.SparseMat``, ``utils.dataset_utils.M2sparse`` / graph wrapper) are swapped
-    too; otherwise the reference's own containers are used and duck-typed by the model."""
+def install():
+    """Make ``models.*`` resolve to gasfm_b200.  The reference's own data containers (``utils.sparse_utils.SparseMat``,
+    ``utils.dataset_utils`` graph wrappers, ``datasets.SceneData``) stay in place: the models duck-type them
+    (``tests/test_gpu_model.py::test_accepts_duck_typed_reference_containers``) and build their CSR/CSC index on first use."""
     mapping = dict(_MAP)
-    if override_utils:
-        mapping["utils.sparse_utils"] = "gasfm_b200.utils.sparse_utils"
     pkg = sys.modules.get("models")
     if pkg is None:
         pkg = types.ModuleType("models")

@@ -59,6 +59,14 @@ def test_tensor_core_kernel_shape_predicates():
     assert lib.gasfm_col_sum_ws_bytes(100, 256) == 0 and lib.gasfm_col_sum_ws_bytes(50000, 256) == 195 * 256 * 4
 
 
+def test_ln_relu_width_predicate_mirrors_the_kernel():
+    """Widths the fused LayerNorm+ReLU kernel rejects (> 256 and not a multiple of 4; csrc/edge_ops.cu) must take the
+    torch fallback in the layers instead of raising."""
+    from gasfm_b200 import ops
+    assert all(ops.ln_relu_width_supported(w) for w in (1, 2, 3, 32, 64, 255, 256, 260, 512, 1024))
+    assert not any(ops.ln_relu_width_supported(w) for w in (0, 257, 258, 514, 1023, 1028, 2048))
+
+
 def test_header_cites_the_reference_for_each_entry_point():
     text = open(os.path.join(ROOT, "include", "gasfm_b200.h")).read()
     for cite in ("utils/dataset_utils.py:86-113", "utils/sparse_utils.py:436-449", "models/layers.py:329-335",

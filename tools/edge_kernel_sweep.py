@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from gasfm_b200 import ops  # noqa: E402
 from gasfm_b200.index import ObservationIndex  # noqa: E402
-from oracle import gasfm_cpu  # noqa: E402
+from gasfm_b200 import synthetic as gasfm_cpu  # noqa: E402  (synthetic scene generator)
 
 peaks, kind = bench.measured_peaks()
 peak = float(peaks["hbm_gbs"])

@@ -16,7 +16,7 @@ from gasfm_b200.config import ConfigTree, gasfm_conf  # noqa: E402
 from gasfm_b200.loss_functions import ESFMLoss  # noqa: E402
 from gasfm_b200.models.graph_attn_sfm import GraphAttnSfMNet  # noqa: E402
 from gasfm_b200.scene import Scene  # noqa: E402
-from oracle import gasfm_cpu  # noqa: E402  (synthetic scene generator)
+from gasfm_b200 import synthetic as gasfm_cpu  # noqa: E402  (synthetic scene generator)
 
 
 def main():
