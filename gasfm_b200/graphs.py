@@ -20,7 +20,9 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, model, scene, loss_fn, after_backward=None, warmup=3, before_forward=None):
+    def __init__(self, model, scene, loss_fn, after_backward=None, warmup=3, before_forward=None, capture_lock=None):
+        """``capture_lock``: a ``threading.Lock`` shared by ranks that live in ONE process (the single-GPU tests): their
+        warm-up steps run concurrently (the exchanges need every rank), the captures one after the other."""
         self.model, self.scene = model, scene
         self._loss_fn, self._after, self._before = loss_fn, after_backward, before_forward
         cur = torch.cuda.current_stream()
@@ -30,12 +32,19 @@ class GraphedStep:
             for _ in range(warmup):
                 self._eager_step()
         cur.wait_stream(side)
-        torch.cuda.synchronize()
+        side.synchronize()
+        cur.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         if self._before is None:
             model.zero_grad(set_to_none=True)       # gradients are (re)allocated inside the graph's pool
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-            self.out, self.loss = self._eager_step(zero=False)
+        if capture_lock is not None:
+            capture_lock.acquire()
+        try:
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.out, self.loss = self._eager_step(zero=False)
+        finally:
+            if capture_lock is not None:
+                capture_lock.release()
 
     def _eager_step(self, zero=True):
         if self._before is not None:

@@ -188,6 +188,7 @@ def test_track_sharded_step_replays_as_cuda_graph():
     group = gdist.PeerExchange.local_group(world, DEV, region_floats=1 << 20, timeout_s=30.0)
     models = [copy.deepcopy(model).to(DEV) for _ in range(world)]
     graphed = [None] * world
+    lock = threading.Lock()
 
     def work(r):
         def fn():
@@ -197,10 +198,11 @@ def test_track_sharded_step_replays_as_cuda_graph():
             wp, wx = wP.to(DEV), wX[:, lo:hi].to(DEV)
             torch.cuda.current_stream().synchronize()
             graphed[r] = GraphedStep(models[r], scene, lambda o: (o["Ps_norm"] * wp).sum() + (o["pts3D"] * wx).sum(),
-                                     warmup=2, before_forward=bucket.prepare, after_backward=bucket.allreduce)
+                                     warmup=2, before_forward=bucket.prepare, after_backward=bucket.allreduce,
+                                     capture_lock=lock)
         return fn
 
-    # capture is serialised per process by torch, so the two ranks capture one after the other: warm-ups in lockstep first
+    # warm-ups run in lockstep (the exchanges need both ranks); the captures are serialised by ``lock``
     _on_streams([work(r) for r in range(world)])
     for _ in range(2):
         _on_streams([graphed[r] for r in range(world)])

@@ -204,4 +204,5 @@ def test_activation_recompute_gives_identical_results():
     assert torch.equal(res["off"][0], res["on"][0]) and torch.equal(res["off"][1], res["on"][1])
     for k, g in res["off"][2].items():
         assert torch.equal(g, res["on"][2][k]), k
-    assert res["on"][3] < 0.7 * res["off"][3]          # activations held between forward and backward
+    # activations held between forward and backward: each of the two fused blocks drops relu(LN(x)) and its three projections
+    assert res["off"][3] - res["on"][3] > 2 * 3.5 * idx.shape[1] * 128 * 4
