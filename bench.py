@@ -501,6 +501,7 @@ def parity_sharded_vs_single(dev, rank, world, exchange):
         model.zero_grad(set_to_none=True)
         o1 = model(Scene.from_observations(idx, vals, cfg["m"], cfg["n"]).to(dev))
         ((o1["Ps_norm"] * wP).sum() + (o1["pts3D"] * wX).sum()).backward()
+        o1 = {k: v.detach() for k, v in o1.items()}
         want = {k: p.grad.detach() for k, p in model.named_parameters() if p.grad is not None}
         worst, key = _grad_error(got, want)
         e_ps = float((got_out["Ps_norm"] - o1["Ps_norm"]).abs().max() / max(1.0, float(o1["Ps_norm"].abs().max())))
