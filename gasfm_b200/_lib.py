@@ -62,6 +62,7 @@ SIGNATURES = {
     "gasfm_esfm_loss_ws_bytes": (_SZ, [_L]),
     "gasfm_esfm_loss_fwd": (_I, [_P, _P, _L, _P, _P, _P, _L, _F, _I, _F, _P, _P, _P]),
     "gasfm_esfm_loss_bwd": (_I, [_P, _P, _L, _P, _P, _P, _L, _F, _I, _F, _P, _P, _I, _P, _P]),
+    "gasfm_reproj_error": (_I, [_P, _P, _L, _P, _P, _P, _L, _P, _P, _P]),
     "gasfm_peer_alloc": (_I, [_SZ, _c.POINTER(_P)]),
     "gasfm_peer_free": (_I, [_P]),
     "gasfm_peer_export": (_I, [_P, _P]),

@@ -102,6 +102,42 @@ __global__ void __launch_bounds__(256) esfm_bwd_kernel(EsfmArgs a, const float* 
                        P[2] * g[0] + P[6] * g[1] + P[10] * g[2], P[3] * g[0] + P[7] * g[1] + P[11] * g[2]);
 }
 
+// Mean reprojection error over the observed pairs (evaluation.compute_core_errors -> 'our_repro', evaluation.py:27-32;
+// geo_utils.reprojection_error_with_points, geo_utils.py:371-391): err_e = || u_e - (P_i X_j)_xy / (P_i X_j)_z ||,
+// nan-mean (a 0/0 projection is skipped, an infinite one is not -- as numpy's nanmean does).
+__global__ void __launch_bounds__(256) reproj_err_kernel(EsfmArgs a, float* __restrict__ partial) {
+  __shared__ float sm[8][2];
+  float sum = 0.f, cnt = 0.f;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.E; e += (int64_t)gridDim.x * blockDim.x) {
+    float P[12], X[4], p[3];
+    project(a, e, P, X, p);
+    const float rx = __ldg(a.obs + 2 * e) - p[0] / p[2], ry = __ldg(a.obs + 2 * e + 1) - p[1] / p[2];
+    const float err = sqrtf(rx * rx + ry * ry);
+    if (err == err) { sum += err; cnt += 1.f; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+  }
+  if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5][0] = sum; sm[threadIdx.x >> 5][1] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f, c = 0.f;
+    for (int w = 0; w < 8; ++w) { s += sm[w][0]; c += sm[w][1]; }
+    partial[2 * blockIdx.x] = s;
+    partial[2 * blockIdx.x + 1] = c;
+  }
+}
+
+// out[0] = sum / count (nan if nothing was counted, like nanmean of an all-nan array), out[1] = count
+__global__ void reproj_finish_kernel(const float* __restrict__ partial, int blocks, float* __restrict__ out) {
+  double s = 0.0, c = 0.0;
+  for (int b = 0; b < blocks; ++b) { s += partial[2 * b]; c += partial[2 * b + 1]; }
+  out[0] = (float)(s / c);
+  out[1] = (float)c;
+}
+
 static int esfm_blocks(int64_t E) {
   int64_t need = (E + 255) / 256;
   int64_t cap = (int64_t)kNumSMs * 8;
@@ -134,4 +170,15 @@ extern "C" int gasfm_esfm_loss_bwd(const float* Ps, const float* pts3D, int64_t 
   EsfmArgs a{Ps, pts3D, n, obs, row_idx, col_idx, E, margin, hinge, hinge ? hinge_weight : 0.f};
   esfm_bwd_kernel<<<ceil_div(E, 256), 256, 0, (cudaStream_t)stream>>>(a, upstream, stats, grad_mode, G);
   return check_launch("esfm_loss_bwd");
+}
+
+extern "C" int gasfm_reproj_error(const float* Ps, const float* pts3D, int64_t n, const float* obs, const int32_t* row_idx,
+                                  const int32_t* col_idx, int64_t E, float* out, void* ws, void* stream) {
+  GASFM_REQUIRE(E > 0 && n > 0 && ws != nullptr && out != nullptr, "reproj_error: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  EsfmArgs a{Ps, pts3D, n, obs, row_idx, col_idx, E, 0.f, 0, 0.f};
+  const int blocks = esfm_blocks(E);
+  reproj_err_kernel<<<blocks, 256, 0, st>>>(a, (float*)ws);
+  reproj_finish_kernel<<<1, 1, 0, st>>>((const float*)ws, blocks, out);
+  return check_launch("reproj_error");
 }

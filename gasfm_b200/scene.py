@@ -1,45 +1,64 @@
-"""Scene container holding what the model reads from the reference's ``SceneData``
-(``code/datasets/SceneData.py``): ``x`` (SparseMat of normalised observations) and
-``graph_wrappers`` (the four aggregation graphs).  Sparse-first: a scene can be built straight
-from an observation list without ever forming the dense ``M[2m,n]``."""
+"""Scene container holding what the model, the loss and the per-step metric read from the reference's ``SceneData``
+(``code/datasets/SceneData.py``): ``x`` (SparseMat of normalised observations), ``graph_wrappers`` (the four
+aggregation graphs), and optionally the raw image points of the same observations, ``Ns`` and ``y``.  Sparse-first: a
+scene can be built straight from an observation list without ever forming the dense ``M[2m,n]``, and view sub-sampling
+(``sample_data``, SceneData.py:306-355) works on the observation list."""
 import copy
 
+import numpy as np
 import torch
 
 from .utils import dataset_utils
+from .utils.constants import MIN_N_VIEWS_PER_POINT
 from .utils.sparse_utils import SparseMat
 
 
 class Scene:
-    def __init__(self, x, scene_name="scene", y=None):
+    def __init__(self, x, scene_name="scene", y=None, Ns=None, obs=None, calibrated=True):
         self.x = x
         self.scene_name = scene_name
-        self.y = y
+        self.y = y                      # [m,3,4] ground-truth cameras (SceneData.y) or None
+        self.Ns = Ns                    # [m,3,3] normalisation matrices (SceneData.Ns) or None
+        self.obs = obs                  # [E,2] raw image points of the observations, in x's order, or None
+        self.calibrated = calibrated
         self.device = x.values.device
         self.graph_wrappers = dataset_utils.create_axial_aggregation_graphs(x)
 
-    @classmethod
-    def from_measurements(cls, M, Ns, scene_name="scene", y=None):
-        """Dense path, as ``SceneData.__init__`` does it: ``x = M2sparse(M, normalize=True, Ns)``
-        (SceneData.py:43)."""
-        return cls(dataset_utils.M2sparse(M, normalize=True, Ns=Ns), scene_name, y)
+    @property
+    def Ns_invT(self):
+        """transpose(inverse(Ns)) as SceneData stores it (SceneData.py:49)."""
+        return torch.transpose(torch.inverse(self.Ns), 1, 2)
 
     @classmethod
-    def from_observations(cls, indices, values, m, n, scene_name="scene"):
-        """Sparse path: ``indices [2,E]`` int64 row-major sorted, ``values [E,2]`` fp32."""
+    def from_measurements(cls, M, Ns, scene_name="scene", y=None, calibrated=True):
+        """Dense path, as ``SceneData.__init__`` does it: ``x = M2sparse(M, normalize=True, Ns)`` (SceneData.py:43);
+        the raw image points are kept sparsely (same observations, same order) instead of the dense ``M``."""
+        x = dataset_utils.M2sparse(M, normalize=True, Ns=Ns)
+        raw = dataset_utils.M2sparse(M, normalize=False)
+        return cls(x, scene_name, y, Ns, raw.values, calibrated)
+
+    @classmethod
+    def from_observations(cls, indices, values, m, n, scene_name="scene", Ns=None, obs=None, y=None, calibrated=True):
+        """Sparse path: ``indices [2,E]`` int64 row-major sorted, ``values [E,2]`` fp32 normalised image points
+        (``obs``: the raw ones, needed by the reprojection metric and by re-normalising view subsets)."""
         indices = torch.as_tensor(indices, dtype=torch.int64)
         values = torch.as_tensor(values, dtype=torch.float32)
         cam_per_pts = torch.bincount(indices[1], minlength=n).unsqueeze(1)
         pts_per_cam = torch.bincount(indices[0], minlength=m).unsqueeze(1)
-        return cls(SparseMat(values, indices, cam_per_pts, pts_per_cam, (m, n, 2)), scene_name)
+        obs = None if obs is None else torch.as_tensor(obs, dtype=torch.float32)
+        return cls(SparseMat(values, indices, cam_per_pts, pts_per_cam, (m, n, 2)), scene_name, y, Ns, obs, calibrated)
 
     def to(self, device, *args, **kwargs):
+        """``SceneData.to`` (SceneData.py:241-264).  ``dense_on_demand`` is accepted and meaningless: there are no
+        dense members to leave behind."""
         kwargs.pop("dense_on_demand", None)
         ret = copy.copy(self)
         ret.x = self.x.to(device, **kwargs)
         ret.graph_wrappers = {k: w.to(device, **kwargs) for k, w in self.graph_wrappers.items()}
-        if torch.is_tensor(self.y):
-            ret.y = self.y.to(device, **kwargs)
+        for key in ("y", "Ns", "obs"):
+            v = getattr(self, key)
+            if torch.is_tensor(v):
+                setattr(ret, key, v.to(device, **kwargs))
         ret.device = device
         return ret
 
@@ -70,3 +89,50 @@ class Scene:
         for k in ("proj2view", "proj2scenepoint"):
             self.graph_wrappers[k].valid_indices = self.x.indices
         return self
+
+    # -- view sub-sampling ----------------------------------------------------------------------
+    def subset_views(self, view_ids):
+        """The scene restricted to ``view_ids``, as ``SceneData.sample_data`` builds it (SceneData.py:306-355) but on
+        the observation list: the selected rows of ``M`` in ascending view order, tracks seen by fewer than
+        ``MIN_N_VIEWS_PER_POINT`` of the selected views dropped and the rest renumbered, observations re-normalised.
+        Like the reference, ``Ns`` / ``y`` are taken in the order of ``view_ids`` as given (``data.Ns[indices]``) while
+        the measurement rows are sorted (``M_indices = np.sort(...)``) -- identical for consecutive views, the shipped case."""
+        view_ids = np.asarray(view_ids, dtype=np.int64).reshape(-1)
+        m, n = self.x.shape[0], self.x.shape[1]
+        dev = self.x.indices.device
+        order = torch.as_tensor(np.sort(view_ids), device=dev)
+        if order.numel() > 1 and bool((order[1:] == order[:-1]).any()):
+            raise ValueError("view_ids must be distinct")
+        new_row_of = torch.full((m,), -1, dtype=torch.int64, device=dev)
+        new_row_of[order] = torch.arange(order.numel(), device=dev)
+        rows, cols = self.x.indices[0], self.x.indices[1]
+        keep = new_row_of[rows] >= 0
+        views_per_track = torch.bincount(cols[keep], minlength=n)
+        track_ok = views_per_track >= MIN_N_VIEWS_PER_POINT
+        keep &= track_ok[cols]
+        new_col_of = torch.cumsum(track_ok.to(torch.int64), 0) - 1
+        sel = torch.nonzero(keep)[:, 0]
+        new_idx = torch.stack((new_row_of[rows[sel]], new_col_of[cols[sel]]))          # row-major order is preserved
+        n_new = int(track_ok.sum().item())
+        taken = torch.as_tensor(view_ids, device=dev)
+        Ns = None if self.Ns is None else self.Ns[taken]
+        y = None if self.y is None else self.y[taken.to(self.y.device)]
+        obs = None if self.obs is None else self.obs[sel]
+        if obs is not None and Ns is not None:
+            hom = torch.cat((obs, torch.ones_like(obs[:, :1])), dim=1)                 # (Ns @ [x; y; 1])[:2], geo_utils.py:689-703
+            values = torch.einsum("eij,ej->ei", Ns[new_idx[0]][:, :2, :], hom)
+        else:
+            if not np.array_equal(view_ids, np.sort(view_ids)):
+                raise ValueError("re-ordering views needs the raw image points and Ns (Scene.obs / Scene.Ns)")
+            values = self.x.values[sel]
+        cam_per_pts = torch.bincount(new_idx[1], minlength=n_new).unsqueeze(1)
+        pts_per_cam = torch.bincount(new_idx[0], minlength=order.numel()).unsqueeze(1)
+        x = SparseMat(values, new_idx, cam_per_pts, pts_per_cam, (int(order.numel()), n_new, 2))
+        return Scene(x, self.scene_name, y, Ns, obs, self.calibrated)
+
+
+def sample_data(data, num_views, consecutive_views=True):
+    """``SceneData.sample_data`` (SceneData.py:306-355): a random subset of the views (numpy RNG, like the reference's
+    ``dataset_utils.sample_indices``), built sparsely on the scene's own device."""
+    indices = dataset_utils.sample_indices(data.x.shape[0], num_views, adjacent=consecutive_views)
+    return data.subset_views(indices)

@@ -11,6 +11,30 @@ from .constants import MIN_N_VIEWS_PER_POINT, MIN_N_POINTS_PER_VIEW  # noqa: F40
 from .sparse_utils import SparseMat
 
 
+def sample_indices(N, num_samples, adjacent):
+    """View ids of a training sample (dataset_utils.py:25-40): all views, a fraction / number of consecutive views, or
+    a random subset -- same numpy RNG calls as the reference, so equal seeds give equal samples."""
+    import numpy as np
+
+    if num_samples == 1:
+        return np.arange(N)
+    if num_samples < 1:
+        num_samples = int(np.ceil(num_samples * N))
+    num_samples = max(2, num_samples)
+    if num_samples >= N:
+        return np.arange(N)
+    if adjacent:
+        start = np.random.randint(0, N - num_samples + 1)
+        return np.arange(start, start + num_samples)
+    return np.random.choice(N, num_samples, replace=False)
+
+
+def is_valid_sample(data):
+    """dataset_utils.py:12-13."""
+    return (data.x.pts_per_cam.min().item() >= MIN_N_POINTS_PER_VIEW and
+            data.x.cam_per_pts.min().item() >= MIN_N_VIEWS_PER_POINT)
+
+
 def _cuda_device():
     if not torch.cuda.is_available():
         raise RuntimeError("gasfm_b200: building the observation index needs a CUDA device (no CPU fallback)")

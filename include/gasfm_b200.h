@@ -266,6 +266,15 @@ GASFM_API int gasfm_esfm_loss_bwd(const float* Ps, const float* pts3D, int64_t n
                                   int hinge, float hinge_weight, const float* upstream, const float* stats,
                                   int grad_mode, float* G, void* stream);
 
+/* Per-step reprojection metric on the device (evaluation.compute_core_errors -> core_errors['our_repro'],
+ * evaluation.py:8-32; geo_utils.reprojection_error_with_points, utils/geo_utils.py:371-391): the nan-mean over the E
+ * observed pairs of || u_e - pflat(P_i X_j)_xy ||.  Ps[m,3,4] are the UNNORMALISED cameras (Ns^-1 Ps_norm), pts3D[4,n],
+ * obs[E,2] the raw image points.  out[0] = mean error, out[1] = number of pairs counted; ws as for the loss.  Nothing
+ * leaves the device (the reference moves predictions to numpy and builds dense [m,n] arrays every training step). */
+GASFM_API int gasfm_reproj_error(const float* Ps, const float* pts3D, int64_t n, const float* obs,
+                                 const int32_t* row_idx, const int32_t* col_idx, int64_t E, float* out, void* ws,
+                                 void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Track-sharded multi-GPU exchange over NVLink peer memory (the reference is single-GPU,
  * main.py:78, so there is no reference interface to cite -- these serve GATv2Conv's per-view softmax,

@@ -188,9 +188,51 @@ def main():
         fix["conf_json"] = np.array(__import__("json").dumps(conf_d))
         np.savez_compressed(os.path.join(HERE, f"model_{name}.npz"), **to_np(fix))
     make_loss_and_dpesfm(ref)
+    make_metric_and_sampling(ref)
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+def make_metric_and_sampling(ref):
+    """SURVEY 8(f2, f3): the reference's own per-step metric (evaluation.compute_core_errors) and view sub-sampling
+    (SceneData.sample_data) on seeded inputs."""
+    import importlib
+    import types
+    sys.modules.setdefault("PyCeres", types.ModuleType("PyCeres"))      # import-time only (utils/ba_functions.py)
+    ev = importlib.import_module("evaluation")
+    m, n = 9, 70
+    M, Ns = random_dense_scene(m, n, 0.45, 31)
+    y = torch.zeros(m, 3, 4)
+    y[:, 0, 0] = torch.arange(m)                                        # lets the fixture record WHICH views were drawn
+    data = ref.SceneData.SceneData(M, Ns, y, "metric", calibrated=True)
+    g = torch.Generator().manual_seed(6)
+    Ps = torch.randn(m, 3, 4, generator=g)
+    Ps[:, 2, 3] += 3.0
+    X = torch.cat((torch.randn(3, n, generator=g), 0.5 + torch.rand(1, n, generator=g)))     # not yet pflat'ed
+    conf = ref.ConfigTree.from_dict({"dataset": {"calibrated": True}, "eval": {"calc_reprojerr_with_gtposes_for_depth_pred": False},
+                                     "model": {"view_head": {"enabled": True}, "scenepoint_head": {"enabled": True}}})
+    fix = dict(M=M, Ns=Ns, Ps_norm=Ps, pts3D=X)
+    fix["our_repro.f32"] = np.float64(ev.compute_core_errors(data, {"Ps_norm": Ps, "pts3D": X}, conf)["our_repro"])
+    data64 = ref.SceneData.SceneData(M.double(), Ns.double(), y.double(), "metric", calibrated=True)
+    fix["our_repro.f64"] = np.float64(ev.compute_core_errors(data64, {"Ps_norm": Ps.double(), "pts3D": X.double()}, conf)["our_repro"])
+    np.savez_compressed(os.path.join(HERE, "core_errors.npz"), **to_np(fix))
+    print("core_errors ok:", float(fix["our_repro.f32"]), float(fix["our_repro.f64"]))
+
+    fix = dict(M=M, Ns=Ns, y=y)
+    for name, num_views, consecutive, seed in (("consecutive4", 4, True, 1), ("fraction", 0.6, True, 2), ("random5", 5, False, 3)):
+        np.random.seed(seed)
+        sub = ref.SceneData.sample_data(data, num_views, consecutive_views=consecutive)
+        fix[f"{name}.args"] = np.array([num_views, float(consecutive), seed], dtype=np.float64)
+        fix[f"{name}.view_ids"] = sub.y[:, 0, 0].to(torch.int64)
+        fix[f"{name}.indices"], fix[f"{name}.values"] = sub.x.indices, sub.x.values
+        fix[f"{name}.cam_per_pts"], fix[f"{name}.pts_per_cam"] = sub.x.cam_per_pts, sub.x.pts_per_cam
+        fix[f"{name}.shape"] = np.array(sub.x.shape)
+        fix[f"{name}.Ns"] = sub.Ns
+        for key, w in sub.graph_wrappers.items():
+            fix[f"{name}.graph.{key}"] = w.edge_index
+    np.savez_compressed(os.path.join(HERE, "sample_data.npz"), **to_np(fix))
+    print("sample_data ok:", {k: fix[k].tolist() for k in fix if k.endswith("view_ids")})
 
 
 LOSS_VARIANTS = {
