@@ -31,6 +31,10 @@ SIGNATURES = {
     "gasfm_gat_bwd_ws_bytes": (_SZ, [_L, _I, _I, _I, _I]),
     "gasfm_gat_edge_bwd": (_I, [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _F,
                                 _P, _L, _P, _P, _P, _P]),
+    "gasfm_gat_edge_fwd_bf16": (_I, [_P, _L, _P, _L, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _F, _I,
+                                     _P, _P, _P, _P, _P]),
+    "gasfm_gat_edge_bwd_bf16": (_I, [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _F,
+                                     _P, _L, _P, _P, _P, _P]),
     "gasfm_seg_sum": (_I, [_P, _L, _I, _P, _P, _I, _I, _P, _P, _I, _F, _I, _P, _P, _P]),
     "gasfm_seg_sum_ws_bytes": (_SZ, [_I, _I]),
     "gasfm_seg_bcast": (_I, [_P, _I, _P, _P, _L, _F, _I, _P, _P]),

@@ -151,6 +151,35 @@ struct Acc {
   }
 };
 
+// Storage type of the projected sources: fp32, or bf16 (BASELINE.json configs[4] "fp32 vs bf16": half the bytes per
+// edge; arithmetic stays fp32).  BF is a template parameter, so the fp32 kernels compile exactly as before.
+template <bool BF>
+__device__ __forceinline__ float4 load_xl4(const float* base, int64_t row, int64_t ld, int col) {
+  if constexpr (BF) {
+    const uint16_t* q = reinterpret_cast<const uint16_t*>(base) + row * ld + col;
+    uint32_t a, b;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "l"(q));
+    return make_float4(__uint_as_float(a << 16), __uint_as_float(a & 0xffff0000u), __uint_as_float(b << 16),
+                       __uint_as_float(b & 0xffff0000u));
+  } else {
+    return ld_stream4(base + row * ld + col);
+  }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <bool BF>
+__device__ __forceinline__ void store_dxl4(float* base, int64_t row, int64_t ld, int col, const float4& g) {
+  if constexpr (BF) {
+    uint16_t* q = reinterpret_cast<uint16_t*>(base) + row * ld + col;
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(q), "r"(pack_bf16x2(g.x, g.y)), "r"(pack_bf16x2(g.z, g.w)) : "memory");
+  } else {
+    st_stream4(base + row * ld + col, g);
+  }
+}
+
 struct GatFwdArgs {
   const float* XL; int64_t ldxl;
   const float* XR; int64_t ldxr;
@@ -163,7 +192,7 @@ struct GatFwdArgs {
 };
 
 // consume rows [begin, end) with stride `step` into acc
-template <class L>
+template <class L, bool BF = false>
 __device__ __forceinline__ void consume_rows(const GatFwdArgs& p, int begin, int end, int step,
                                              int lir, unsigned mask, const float4 (&xr)[L::NV],
                                              const float4 (&att)[L::NV], Acc<L>& acc) {
@@ -175,9 +204,8 @@ __device__ __forceinline__ void consume_rows(const GatFwdArgs& p, int begin, int
       int pos = i + u * step;
       int posc = pos < end ? pos : begin;  // clamp: loads stay in range, score masked below
       int e = p.perm ? __ldg(p.perm + posc) : posc;
-      const float* row = p.XL + (int64_t)e * p.ldxl + 4 * lir;
 #pragma unroll
-      for (int v = 0; v < L::NV; ++v) x[u][v] = ld_stream4(row + 4 * L::LPR * v);
+      for (int v = 0; v < L::NV; ++v) x[u][v] = load_xl4<BF>(p.XL, e, p.ldxl, 4 * lir + 4 * L::LPR * v);
     }
 #pragma unroll
     for (int u = 0; u < L::U; ++u) {
@@ -249,7 +277,7 @@ __device__ __forceinline__ void finalize_segment(const GatFwdArgs& p, int t, int
 // Resident CTAs per SM (register cap), measured on B200 at H*C = 256 (profiles/r01_edge_kernel_occupancy_ab.md):
 // the gathered short-segment schedule wants more warps in flight (3 CTAs, <= 80 regs, a few spills),
 // the contiguous chunked schedule is faster with 2 CTAs and no spills.
-template <int H, int C, bool CHUNKED>
+template <int H, int C, bool CHUNKED, bool BF = false>
 __global__ void __launch_bounds__(256, (H * C <= 256) ? (CHUNKED ? 2 : 3) : 1) gat_fwd_kernel(GatFwdArgs p) {
   using L = Lay<H, C>;
   const int lane = threadIdx.x & 31;
@@ -272,7 +300,7 @@ __global__ void __launch_bounds__(256, (H * C <= 256) ? (CHUNKED ? 2 : 3) : 1) g
 #pragma unroll
     for (int v = 0; v < L::NV; ++v) xr[v] = ld4(xrrow + 4 * L::LPR * v);
     const int b = __ldg(p.seg_ptr + t), e = __ldg(p.seg_ptr + t + 1);
-    consume_rows<L>(p, b, e, 1, lir, gmask, xr, att, acc);
+    consume_rows<L, BF>(p, b, e, 1, lir, gmask, xr, att, acc);
     finalize_segment<L>(p, t, lir, H, acc);
   } else {
     const int total = __ldg(p.chunk_ptr + p.n_seg);
@@ -286,7 +314,7 @@ __global__ void __launch_bounds__(256, (H * C <= 256) ? (CHUNKED ? 2 : 3) : 1) g
     const int sb = __ldg(p.seg_ptr + t), se = __ldg(p.seg_ptr + t + 1);
     const int b = sb + (k - c0) * p.chunk;
     const int e = min(b + p.chunk, se);
-    consume_rows<L>(p, b + grp, e, L::RPW, lir, gmask, xr, att, acc);
+    consume_rows<L, BF>(p, b + grp, e, L::RPW, lir, gmask, xr, att, acc);
     __syncwarp();
     acc.merge_across_groups();
     if (grp == 0) {
@@ -417,7 +445,7 @@ struct BwdSeg {
   }
 };
 
-template <class L>
+template <class L, bool BF = false>
 __device__ __forceinline__ void bwd_rows(const GatBwdArgs& p, int begin, int end, int step, int lir,
                                          unsigned mask, const BwdSeg<L>& sg, const float4 (&att)[L::NV],
                                          float4 (&dxr)[L::NV], float4 (&datt)[L::NV]) {
@@ -430,9 +458,8 @@ __device__ __forceinline__ void bwd_rows(const GatBwdArgs& p, int begin, int end
       int pos = i + u * step;
       int posc = pos < end ? pos : begin;
       eid[u] = p.perm ? __ldg(p.perm + posc) : posc;
-      const float* row = p.XL + (int64_t)eid[u] * p.ldxl + 4 * lir;
 #pragma unroll
-      for (int v = 0; v < L::NV; ++v) x[u][v] = ld_stream4(row + 4 * L::LPR * v);
+      for (int v = 0; v < L::NV; ++v) x[u][v] = load_xl4<BF>(p.XL, eid[u], p.ldxl, 4 * lir + 4 * L::LPR * v);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -457,7 +484,6 @@ __device__ __forceinline__ void bwd_rows(const GatBwdArgs& p, int begin, int end
         alpha[s] = valid ? __expf(sc[s] - sg.M[s]) * sg.invL[s] : 0.f;
         ds[s] = alpha[s] * (da[s] - sg.D[s]);
       }
-      float* drow = p.dXL + (int64_t)eid[u] * p.lddxl + 4 * lir;
 #pragma unroll
       for (int v = 0; v < L::NV; ++v) {
         float4 g;
@@ -470,7 +496,7 @@ __device__ __forceinline__ void bwd_rows(const GatBwdArgs& p, int begin, int end
           comp(dxr[v], k) += dz;
           comp(datt[v], k) = fmaf(ds[s], leaky(z, p.slope), comp(datt[v], k));
         }
-        if (valid) st_stream4(drow + 4 * L::LPR * v, g);
+        if (valid) store_dxl4<BF>(p.dXL, eid[u], p.lddxl, 4 * lir + 4 * L::LPR * v, g);
       }
     }
   }
@@ -492,7 +518,7 @@ __device__ __forceinline__ void sum_across_groups(float4 (&a)[L::NV]) {
   }
 }
 
-template <int H, int C, bool CHUNKED>
+template <int H, int C, bool CHUNKED, bool BF = false>
 __global__ void __launch_bounds__(kBwdThreads, (H * C <= 256) ? (CHUNKED ? 2 : 3) : 1) gat_bwd_kernel(GatBwdArgs p) {
   using L = Lay<H, C>;
   constexpr int NW = kBwdThreads / 32;
@@ -517,7 +543,7 @@ __global__ void __launch_bounds__(kBwdThreads, (H * C <= 256) ? (CHUNKED ? 2 : 3
       float4 dxr[L::NV];
 #pragma unroll
       for (int v = 0; v < L::NV; ++v) dxr[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      bwd_rows<L>(p, __ldg(p.seg_ptr + t), __ldg(p.seg_ptr + t + 1), 1, lir, gmask, sg, att, dxr, datt);
+      bwd_rows<L, BF>(p, __ldg(p.seg_ptr + t), __ldg(p.seg_ptr + t + 1), 1, lir, gmask, sg, att, dxr, datt);
       float* xrow = p.dXR + (int64_t)t * L::HC + 4 * lir;
 #pragma unroll
       for (int v = 0; v < L::NV; ++v) st4(xrow + 4 * L::LPR * v, dxr[v]);
@@ -535,7 +561,7 @@ __global__ void __launch_bounds__(kBwdThreads, (H * C <= 256) ? (CHUNKED ? 2 : 3
       float4 dxr[L::NV];
 #pragma unroll
       for (int v = 0; v < L::NV; ++v) dxr[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      bwd_rows<L>(p, b + grp, e, L::RPW, lir, gmask, sg, att, dxr, datt);
+      bwd_rows<L, BF>(p, b + grp, e, L::RPW, lir, gmask, sg, att, dxr, datt);
       __syncwarp();
       sum_across_groups<L>(dxr);
       if (grp == 0) {
@@ -793,31 +819,31 @@ static int bwd_grid_blocks(int64_t work_warps, int warps_per_block) {
   return (int)(need < 1 ? 1 : (need < cap ? need : cap));
 }
 
-template <int H, int C>
+template <int H, int C, bool BF = false>
 static int launch_fwd(const GatFwdArgs& a, cudaStream_t st) {
   using L = Lay<H, C>;
   if (a.chunk == 0) {
     int64_t warps = ((int64_t)a.n_seg + L::RPW - 1) / L::RPW;
     int blocks = ceil_div(warps, 8);
-    if (blocks > 0) gat_fwd_kernel<H, C, false><<<blocks, 256, 0, st>>>(a);
+    if (blocks > 0) gat_fwd_kernel<H, C, false, BF><<<blocks, 256, 0, st>>>(a);
   } else {
     int blocks = ceil_div(a.max_chunks, 8);
-    if (blocks > 0) gat_fwd_kernel<H, C, true><<<blocks, 256, 0, st>>>(a);
+    if (blocks > 0) gat_fwd_kernel<H, C, true, BF><<<blocks, 256, 0, st>>>(a);
     if (a.n_seg > 0) gat_merge_kernel<H, C><<<a.n_seg, kMergeThreads, 0, st>>>(a);
   }
   return check_launch("gat_edge_fwd");
 }
 
-template <int H, int C>
+template <int H, int C, bool BF = false>
 static int launch_bwd(const GatBwdArgs& a, int* n_blocks_out, cudaStream_t st) {
   using L = Lay<H, C>;
   int blocks;
   if (a.chunk == 0) {
     blocks = bwd_grid_blocks(((int64_t)a.n_seg + L::RPW - 1) / L::RPW, kBwdThreads / 32);
-    gat_bwd_kernel<H, C, false><<<blocks, kBwdThreads, 0, st>>>(a);
+    gat_bwd_kernel<H, C, false, BF><<<blocks, kBwdThreads, 0, st>>>(a);
   } else {
     blocks = bwd_grid_blocks(a.max_chunks, kBwdThreads / 32);
-    gat_bwd_kernel<H, C, true><<<blocks, kBwdThreads, 0, st>>>(a);
+    gat_bwd_kernel<H, C, true, BF><<<blocks, kBwdThreads, 0, st>>>(a);
     if (a.n_seg > 0) gat_bwd_merge_kernel<<<dim3(a.n_seg, (H * C + 31) / 32), 256, 0, st>>>(a, H * C);
   }
   *n_blocks_out = blocks;
@@ -852,7 +878,7 @@ extern "C" size_t gasfm_gat_ws_bytes(int max_chunks, int heads, int head_dim) {
   return (size_t)max_chunks * (size_t)(heads * head_dim + 2 * heads) * sizeof(float);
 }
 
-extern "C" int gasfm_gat_edge_fwd(const float* XL, int64_t ldxl, const float* XR, int64_t ldxr,
+static int gat_edge_fwd_impl(bool bf16, const float* XL, int64_t ldxl, const float* XR, int64_t ldxr,
                                   const float* att, const float* bias, const int32_t* seg_ptr,
                                   const int32_t* perm, int n_seg, int chunk, const int32_t* chunk_ptr,
                                   const int32_t* chunk_seg, int max_chunks, int heads, int head_dim,
@@ -876,9 +902,15 @@ extern "C" int gasfm_gat_edge_fwd(const float* XL, int64_t ldxl, const float* XR
       a.ws_l = a.ws_m + (size_t)max_chunks * heads;
     }
     int rc;
+    if (bf16) {
+      GASFM_REQUIRE(heads == 4 && (head_dim == 32 || head_dim == 64), "gat_edge_fwd_bf16: head shapes 4 x 32 and 4 x 64 only");
+      rc = head_dim == 32 ? launch_fwd<4, 32, true>(a, st) : launch_fwd<4, 64, true>(a, st);
+      return rc;
+    }
     GASFM_DISPATCH_C(launch_fwd, a, st);
     return rc;
   }
+  GASFM_REQUIRE(!bf16, "gat_edge_fwd_bf16: head shapes 4 x 32 and 4 x 64 only");
   GASFM_REQUIRE(heads <= kGenMaxH && HC <= 1024, "gat_edge_fwd: unsupported head shape %d x %d", heads, head_dim);
   int blocks = ceil_div(n_seg, 4);
   switch (generic_ni(HC)) {
@@ -892,6 +924,27 @@ extern "C" int gasfm_gat_edge_fwd(const float* XL, int64_t ldxl, const float* XR
   return check_launch("gat_edge_fwd(generic)");
 }
 
+extern "C" int gasfm_gat_edge_fwd(const float* XL, int64_t ldxl, const float* XR, int64_t ldxr,
+                                  const float* att, const float* bias, const int32_t* seg_ptr,
+                                  const int32_t* perm, int n_seg, int chunk, const int32_t* chunk_ptr,
+                                  const int32_t* chunk_seg, int max_chunks, int heads, int head_dim,
+                                  float slope, int normalize, float* out, float* seg_max,
+                                  float* seg_sum, void* ws, void* stream) {
+  return gat_edge_fwd_impl(false, XL, ldxl, XR, ldxr, att, bias, seg_ptr, perm, n_seg, chunk, chunk_ptr, chunk_seg, max_chunks,
+                           heads, head_dim, slope, normalize, out, seg_max, seg_sum, ws, stream);
+}
+
+extern "C" int gasfm_gat_edge_fwd_bf16(const void* XL_bf16, int64_t ldxl, const float* XR, int64_t ldxr,
+                                       const float* att, const float* bias, const int32_t* seg_ptr,
+                                       const int32_t* perm, int n_seg, int chunk, const int32_t* chunk_ptr,
+                                       const int32_t* chunk_seg, int max_chunks, int heads, int head_dim,
+                                       float slope, int normalize, float* out, float* seg_max,
+                                       float* seg_sum, void* ws, void* stream) {
+  GASFM_REQUIRE((uintptr_t)XL_bf16 % 8 == 0, "gat_edge_fwd_bf16: XL must be 8-byte aligned");
+  return gat_edge_fwd_impl(true, (const float*)XL_bf16, ldxl, XR, ldxr, att, bias, seg_ptr, perm, n_seg, chunk, chunk_ptr, chunk_seg,
+                           max_chunks, heads, head_dim, slope, normalize, out, seg_max, seg_sum, ws, stream);
+}
+
 extern "C" size_t gasfm_gat_bwd_ws_bytes(int64_t n_obs, int n_seg, int max_chunks, int heads, int head_dim) {
   (void)n_obs;
   const size_t HC = (size_t)heads * head_dim;
@@ -901,7 +954,7 @@ extern "C" size_t gasfm_gat_bwd_ws_bytes(int64_t n_obs, int n_seg, int max_chunk
   return (blocks * HC + (size_t)max_chunks * HC) * sizeof(float);
 }
 
-extern "C" int gasfm_gat_edge_bwd(const float* XL, int64_t ldxl, const float* XR, int64_t ldxr,
+static int gat_edge_bwd_impl(bool bf16, const float* XL, int64_t ldxl, const float* XR, int64_t ldxr,
                                   const float* att, const float* out_nobias, const float* seg_max,
                                   const float* seg_sum, const float* dOut, const int32_t* seg_ptr,
                                   const int32_t* perm, int n_seg, int chunk, const int32_t* chunk_ptr,
@@ -921,12 +974,18 @@ extern "C" int gasfm_gat_edge_bwd(const float* XL, int64_t ldxl, const float* XR
   int blocks = 0, rc;
   if (has_fast_path(heads, head_dim)) {
     GASFM_REQUIRE(ldxl % 4 == 0 && ldxr % 4 == 0 && lddxl % 4 == 0, "gat_edge_bwd: row strides must be multiples of 4 floats");
-    GASFM_REQUIRE(((uintptr_t)XL | (uintptr_t)XR | (uintptr_t)att | (uintptr_t)out_nobias | (uintptr_t)dOut |
-                   (uintptr_t)dXL | (uintptr_t)dXR) % 16 == 0, "gat_edge_bwd: pointers must be 16-byte aligned");
+    GASFM_REQUIRE(((uintptr_t)XR | (uintptr_t)att | (uintptr_t)out_nobias | (uintptr_t)dOut | (uintptr_t)dXR) % 16 == 0 &&
+                  ((uintptr_t)XL | (uintptr_t)dXL) % (bf16 ? 8 : 16) == 0, "gat_edge_bwd: pointers must be 16-byte aligned");
     a.ws_dxr = (float*)ws + (size_t)kNumSMs * 8 * HC;
-    GASFM_DISPATCH_C(launch_bwd, a, &blocks, st);
+    if (bf16) {
+      GASFM_REQUIRE(heads == 4 && (head_dim == 32 || head_dim == 64), "gat_edge_bwd_bf16: head shapes 4 x 32 and 4 x 64 only");
+      rc = head_dim == 32 ? launch_bwd<4, 32, true>(a, &blocks, st) : launch_bwd<4, 64, true>(a, &blocks, st);
+    } else {
+      GASFM_DISPATCH_C(launch_bwd, a, &blocks, st);
+    }
     if (rc) return rc;
   } else {
+    GASFM_REQUIRE(!bf16, "gat_edge_bwd_bf16: head shapes 4 x 32 and 4 x 64 only");
     GASFM_REQUIRE(heads <= kGenMaxH && HC <= 1024, "gat_edge_bwd: unsupported head shape %d x %d", heads, head_dim);
     int64_t need = ((int64_t)n_seg + 3) / 4;
     blocks = (int)(need < (int64_t)kNumSMs * 16 ? need : (int64_t)kNumSMs * 16);
@@ -943,4 +1002,27 @@ extern "C" int gasfm_gat_edge_bwd(const float* XL, int64_t ldxl, const float* XR
   }
   col_sum_kernel<<<ceil_div(HC, 32), dim3(32, 8), 0, st>>>((const float*)ws, blocks, HC, datt);
   return check_launch("gat_edge_bwd(datt)");
+}
+
+extern "C" int gasfm_gat_edge_bwd(const float* XL, int64_t ldxl, const float* XR, int64_t ldxr,
+                                  const float* att, const float* out_nobias, const float* seg_max,
+                                  const float* seg_sum, const float* dOut, const int32_t* seg_ptr,
+                                  const int32_t* perm, int n_seg, int chunk, const int32_t* chunk_ptr,
+                                  const int32_t* chunk_seg, int max_chunks, int heads, int head_dim,
+                                  float slope, float* dXL, int64_t lddxl, float* dXR, float* datt,
+                                  void* ws, void* stream) {
+  return gat_edge_bwd_impl(false, XL, ldxl, XR, ldxr, att, out_nobias, seg_max, seg_sum, dOut, seg_ptr, perm, n_seg, chunk,
+                           chunk_ptr, chunk_seg, max_chunks, heads, head_dim, slope, dXL, lddxl, dXR, datt, ws, stream);
+}
+
+extern "C" int gasfm_gat_edge_bwd_bf16(const void* XL_bf16, int64_t ldxl, const float* XR, int64_t ldxr,
+                                       const float* att, const float* out_nobias, const float* seg_max,
+                                       const float* seg_sum, const float* dOut, const int32_t* seg_ptr,
+                                       const int32_t* perm, int n_seg, int chunk, const int32_t* chunk_ptr,
+                                       const int32_t* chunk_seg, int max_chunks, int heads, int head_dim,
+                                       float slope, void* dXL_bf16, int64_t lddxl, float* dXR, float* datt,
+                                       void* ws, void* stream) {
+  return gat_edge_bwd_impl(true, (const float*)XL_bf16, ldxl, XR, ldxr, att, out_nobias, seg_max, seg_sum, dOut, seg_ptr, perm,
+                           n_seg, chunk, chunk_ptr, chunk_seg, max_chunks, heads, head_dim, slope, (float*)dXL_bf16, lddxl, dXR,
+                           datt, ws, stream);
 }

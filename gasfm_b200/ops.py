@@ -102,7 +102,8 @@ def gat_edge_attention(XL, XR, att, bias, plan: SegmentPlan, heads: int, lazy_xl
 def gat_edge_partial(XL, XR, att, plan: SegmentPlan, heads: int):
     """Un-normalised per-shard result (no autograd): (sum_e exp(s-max)*XL[e], max, sum).
     Used by the track-sharded multi-GPU path, which merges these across ranks."""
-    _require_cuda(XL, XR, att)
+    bf16 = XL.dtype == torch.bfloat16          # bf16-STORED sources (kernel sweep, BASELINE.json configs[4]); arithmetic stays fp32
+    _require_cuda(None if bf16 else XL, XR, att)
     XL, ldxl = _rows(XL)
     hc = XL.shape[1]
     head_dim = hc // heads
@@ -118,7 +119,7 @@ def gat_edge_partial(XL, XR, att, plan: SegmentPlan, heads: int):
     if plan.chunk > 0:
         ws = plan.workspace(_lib.size_query("gasfm_gat_ws_bytes", plan.max_chunks, heads, head_dim), dev)
     with _lib.device_guard(dev):
-        _lib.call("gasfm_gat_edge_fwd", _lib.ptr(XL), ldxl, _lib.ptr(XR), 0 if bcast else hc, _lib.ptr(att_flat), None,
+        _lib.call("gasfm_gat_edge_fwd_bf16" if bf16 else "gasfm_gat_edge_fwd", _lib.ptr(XL), ldxl, _lib.ptr(XR), 0 if bcast else hc, _lib.ptr(att_flat), None,
                   *plan.abi_args(), heads, head_dim, LEAKY_SLOPE, 0,
                   _lib.ptr(out), _lib.ptr(seg_max), _lib.ptr(seg_sum), _lib.ptr(ws), _lib.stream_ptr())
     return out, seg_max, seg_sum
@@ -126,20 +127,21 @@ def gat_edge_partial(XL, XR, att, plan: SegmentPlan, heads: int):
 
 def gat_edge_backward_raw(XL, XR, att, out_nobias, seg_max, seg_sum, d_out, plan, heads):
     """Backward kernel with explicitly supplied (global) softmax statistics; returns
-    (dXL, dXR, datt).  The multi-GPU path calls this with the merged statistics."""
+    (dXL, dXR, datt).  The multi-GPU path calls this with the merged statistics.  bf16 ``XL`` -> bf16 ``dXL``."""
     XL, ldxl = _rows(XL)
     hc = XL.shape[1]
     head_dim = hc // heads
     dev = XL.device
+    bf16 = XL.dtype == torch.bfloat16
     bcast = XR.shape[0] == 1 and plan.n_seg != 1
     covers_all = plan.perm is None or plan.n_edges == XL.shape[0]
-    dXL = (torch.empty if covers_all else torch.zeros)((XL.shape[0], hc), dtype=torch.float32, device=dev)
+    dXL = (torch.empty if covers_all else torch.zeros)((XL.shape[0], hc), dtype=XL.dtype, device=dev)
     dXR = torch.empty((plan.n_seg, hc), dtype=torch.float32, device=dev)
     datt = torch.empty(hc, dtype=torch.float32, device=dev)
     ws = plan.workspace(_lib.size_query("gasfm_gat_bwd_ws_bytes", XL.shape[0], plan.n_seg, plan.max_chunks,
                                         heads, head_dim), dev)
     with _lib.device_guard(dev):
-        _lib.call("gasfm_gat_edge_bwd", _lib.ptr(XL), ldxl, _lib.ptr(XR.contiguous()), 0 if bcast else hc,
+        _lib.call("gasfm_gat_edge_bwd_bf16" if bf16 else "gasfm_gat_edge_bwd", _lib.ptr(XL), ldxl, _lib.ptr(XR.contiguous()), 0 if bcast else hc,
                   _lib.ptr(att.reshape(-1).contiguous()), _lib.ptr(out_nobias.contiguous()),
                   _lib.ptr(seg_max.contiguous()), _lib.ptr(seg_sum.contiguous()), _lib.ptr(d_out.contiguous()),
                   *plan.abi_args(), heads, head_dim, LEAKY_SLOPE,

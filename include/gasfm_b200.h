@@ -125,6 +125,24 @@ GASFM_API int gasfm_gat_edge_bwd(const float* XL, int64_t ldxl, const float* XR,
                        int heads, int head_dim, float slope,
                        float* dXL, int64_t lddxl, float* dXR, float* datt, void* ws, void* stream);
 
+/* The same two kernels with the projected sources STORED as bf16 (XL / dXL: 2-byte elements, row strides in elements,
+ * 8-byte aligned; everything else fp32, arithmetic fp32): half the bytes per edge of the bandwidth-bound pass
+ * (BASELINE.json configs[4], "fp32 vs bf16").  Head shapes 4 x 32 and 4 x 64.  The result is exact for the bf16-rounded
+ * inputs; against fp32 inputs the storage rounding (2^-9 relative per element) is the error. */
+GASFM_API int gasfm_gat_edge_fwd_bf16(const void* XL_bf16, int64_t ldxl, const float* XR, int64_t ldxr,
+                       const float* att, const float* bias,
+                       const int32_t* seg_ptr, const int32_t* perm, int n_seg,
+                       int chunk, const int32_t* chunk_ptr, const int32_t* chunk_seg, int max_chunks,
+                       int heads, int head_dim, float slope, int normalize,
+                       float* out, float* seg_max, float* seg_sum, void* ws, void* stream);
+GASFM_API int gasfm_gat_edge_bwd_bf16(const void* XL_bf16, int64_t ldxl, const float* XR, int64_t ldxr,
+                       const float* att, const float* out_nobias, const float* seg_max,
+                       const float* seg_sum, const float* dOut,
+                       const int32_t* seg_ptr, const int32_t* perm, int n_seg,
+                       int chunk, const int32_t* chunk_ptr, const int32_t* chunk_seg, int max_chunks,
+                       int heads, int head_dim, float slope,
+                       void* dXL_bf16, int64_t lddxl, float* dXR, float* datt, void* ws, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Row / column pooling  (SparseMat.sum / .mean, utils/sparse_utils.py:406-419; sparse_mean,
  * utils/sparse_utils.py:91-131; and the segment sums of the backward passes)

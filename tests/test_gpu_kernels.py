@@ -162,6 +162,37 @@ def test_gat_long_segments_chunked(H, C):
     _check_gat(idx_np[0], XL, XR, att, bias, dOut, m + 2, H, C, oi.by_view)
 
 
+@pytest.mark.parametrize("C", [32, 64])
+@pytest.mark.parametrize("direction", ["tracks", "views"])
+def test_gat_bf16_stored_sources(C, direction):
+    """BASELINE.json configs[4], "fp32 vs bf16": XL stored as bf16 (half the bytes per edge), arithmetic in fp32.  The kernel
+    must be exact for the bf16-ROUNDED inputs (fp32 tolerances against the fp64 oracle fed with the rounded values); dXL comes
+    back in bf16, i.e. within its storage rounding (2^-9 relative per element).  Both schedules, empty segments included."""
+    H, m, n = 4, 12, 300
+    idx_np, _ = gasfm_cpu.synthetic_observations(m, n, 2400, seed=C)
+    E = idx_np.shape[1]
+    oi = ObservationIndex(torch.from_numpy(idx_np).to(DEV), m + 1, n + 3)
+    plan, T, target = (oi.by_track, n + 3, idx_np[1]) if direction == "tracks" else (oi.by_view, m + 1, idx_np[0])
+    _, XL, XR, att, bias, dOut = _gat_case(E, T, H, C, seed=C + 5)
+    xl16 = torch.from_numpy(XL).to(DEV).to(torch.bfloat16)
+    XLr = xl16.float().cpu().numpy()                              # what the kernel actually reads
+    t = lambda a: torch.from_numpy(a).to(DEV)  # noqa: E731
+    acc, mx, sm = ops.gat_edge_partial(xl16, t(XR), t(att.reshape(1, H, C)), plan, H)
+    L = sm.repeat_interleave(C, dim=1)
+    out = torch.where(L > 0, acc / L.clamp_min(1e-30), torch.zeros_like(acc))
+    ref_out, ref_max, ref_sum = gat_edge_c.gat_edge_fwd(XLr, XR, att, None, target, T, H, C)
+    assert rel_err(out, ref_out) < FP32_TOL
+    dXL, dXR, datt, _ = gat_edge_c.gat_edge_bwd(XLr, XR, att, target, dOut, T, H, C)
+    gxl, gxr, gatt = ops.gat_edge_backward_raw(xl16, t(XR), t(att.reshape(1, H, C)), out, mx, sm, t(dOut), plan, H)
+    assert gxl.dtype == torch.bfloat16
+    assert np.abs(gxl.float().cpu().numpy() - dXL).max() < 2.0 ** -8 * max(1.0, np.abs(dXL).max())
+    assert rel_err(gxr, dXR) < GRAD_TOL
+    assert rel_err(gatt, datt) < GRAD_TOL * 5
+    # against the UNROUNDED fp32 inputs the storage rounding is what is left: stated, looser tolerance
+    full_out, _, _ = gat_edge_c.gat_edge_fwd(XL, XR, att, None, target, T, H, C)
+    assert rel_err(out, full_out) < 2e-2
+
+
 @pytest.mark.parametrize("H,C,E,chunk", [(4, 16, 5000, None), (4, 256, 300, None), (4, 8, 70, 8), (4, 64, 1, 8), (2, 6, 100, 8)])
 def test_gat_single_target_global_graph(H, C, E, chunk):
     """view2global / scenepoint2global: ONE segment holding every edge; with a subset permutation"""
