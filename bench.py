@@ -580,13 +580,135 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------
+# cfg4: multi-scene training step, scenes sharded over the GPUs (BASELINE.json configs[3])
+# ---------------------------------------------------------------------------------------------
+CFG4_SCENES = 8
+
+
+def cfg4_scene_shapes():
+    """8 synthetic scenes, 100 ... 500 views, 60 tracks per view, 3 % density."""
+    shapes = []
+    for k in range(CFG4_SCENES):
+        m = 100 + (400 * k) // (CFG4_SCENES - 1)
+        shapes.append((m, 60 * m, int(0.03 * m * 60 * m), 100 + k))
+    return shapes
+
+
+def run_cfg4(args):
+    """One optimisation step of the reference's multi-scene learning (code/train.py:61-137): forward + ESFM loss + backward
+    over every scene of the batch, gradients SUMMED over the scenes, Adam step.  Scenes are dealt to the ranks in snake
+    order (largest with smallest); the 580 MB gradient all-reduce is bucketed and overlapped with backward."""
+    from gasfm_b200 import _lib
+    from gasfm_b200 import dist as gdist
+    from gasfm_b200.config import ConfigTree, gasfm_conf
+    from gasfm_b200.loss_functions import ESFMLoss
+    from gasfm_b200.models.graph_attn_sfm import GraphAttnSfMNet
+    from gasfm_b200.scene import Scene
+
+    _lib.load()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    sync = world > 1
+    if sync:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    shapes = cfg4_scene_shapes()
+    order = sorted(range(CFG4_SCENES), key=lambda k: -shapes[k][2])
+    owner = {k: (i % world if (i // world) % 2 == 0 else world - 1 - i % world) for i, k in enumerate(order)}
+    mine = [k for k in range(CFG4_SCENES) if owner[k] == rank]
+    hosts, E_total = [], 0
+    for k, (m, n, n_obs, seed) in enumerate(shapes):
+        if k in mine:
+            idx, vals = observations(m, n, n_obs, seed)
+            hosts.append(Scene.from_observations(idx, vals, m, n).pin_memory())
+    E_mine = sum(h.x.indices.shape[1] for h in hosts)
+    conf = gasfm_conf()
+    conf["loss"] = ConfigTree.from_dict(dict(infinity_pts_margin=1e-4, hinge_loss=True, hinge_loss_weight=1,
+                                             pts_grad_equalization_pre_perspective_divide=True,
+                                             normalize_grad_wrt_valid_projections_only=True))
+    torch.manual_seed(0)
+    model = GraphAttnSfMNet(conf).to(dev)
+    loss_fn = ESFMLoss(conf)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    reducer = gdist.BucketedGradReducer(model) if sync else None
+    scenes_dev = [h.to(dev).prepare() for h in hosts]
+    n_params = sum(p.numel() for p in model.parameters())
+
+    def step(scenes, overlap=True):
+        if reducer is not None and overlap:
+            reducer.prepare()
+        else:
+            opt.zero_grad(set_to_none=True)
+        total = None
+        for i, sc in enumerate(scenes):
+            loss = loss_fn(model(sc), sc)
+            if reducer is not None and overlap and i < len(scenes) - 1:
+                with reducer.accumulate_only():
+                    loss.backward()
+            else:
+                loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
+        if reducer is not None and overlap:
+            reducer.finish()
+        elif sync:
+            gdist.allreduce_gradients(model.parameters())        # A/B: one flat all-reduce after backward
+        opt.step()
+        return total
+
+    l0 = _lib.launch_count
+    flat_ms = timed(lambda: step(scenes_dev, overlap=False), max(2, args.steps // 2), 2, sync_dist=sync) if sync else None
+    opt.zero_grad(set_to_none=True)
+    launches_probe = _lib.launch_count
+    step(scenes_dev)
+    launches = _lib.launch_count - launches_probe
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(lambda: step(scenes_dev), args.steps, args.warmup, sync_dist=sync)
+    clocks = sampler.stop()
+    holder = {}
+
+    def step_e2e():
+        holder["loss"] = float(step([h.to(dev, non_blocking=True) for h in hosts]))
+    e2e_ms = timed(step_e2e, max(3, args.steps // 2), 2, sync_dist=sync)
+    h2d = sum(h.x.values.numel() * 4 + h.x.indices.numel() * 8 + h.x.cam_per_pts.numel() * 8 + h.x.pts_per_cam.numel() * 8 for h in hosts)
+    t = torch.tensor([float(E_mine), float(h2d), float(launches)], device=dev, dtype=torch.float64)
+    if sync:
+        torch.distributed.all_reduce(t)
+    E_total, h2d, launches_all = int(t[0].item()), int(t[1].item()), int(t[2].item())
+    del l0
+    if rank == 0:
+        n_gat = 2 * (12 + 1)
+        line = {"metric": METRIC, "value": E_total * n_gat / (ms / 1e3), "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"cfg4: multi-scene training step over {CFG4_SCENES} synthetic scenes (100..500 views, 60 tracks per view, "
+                                       f"3% density, E={E_total} observations in total), shipped GASFM model ({n_params} parameters) replicated, "
+                                       "sparse ESFM loss, SUM gradient all-reduce (NCCL, bucketed, overlapped with backward), Adam step",
+                           "edge_level_gats_per_step": n_gat * CFG4_SCENES, "parallelism": f"{CFG4_SCENES} scenes dealt to {world} GPU(s)",
+                           "cache": "eager steps; inputs re-read every step"},
+                "scenes_per_s": CFG4_SCENES / (ms / 1e3),
+                "grad_allreduce": None if not sync else {"bytes": n_params * 4, "ms_per_step_flat_after_backward": flat_ms,
+                                                         "ms_per_step_bucketed_overlapped": ms},
+                "e2e": {"value": E_total * n_gat / (e2e_ms / 1e3), "unit": "edges/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world},
+                "gpu_launches": launches_all * args.steps, "gpu_launches_per_step": launches_all, "clocks": clocks,
+                "cuda_graph": False, "roofline": None, "cpu_baseline": None, "parity": None}
+        print(json.dumps(line))
+    if sync:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS),
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + ["cfg4"],
                     help="default cfg3_d256 = BASELINE.json's target scene (1,000 x 300k, ~5M observations) at d = 256")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="N>1: strong = the workload's scene itself, sharded; weak = one scene of N x the workload's tracks")
@@ -598,8 +720,12 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time the device-resident step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.workload == "cfg4":
+            args.workload = "cfg2"      # the CPU arm's bounded sample is scene-shaped; cfg4's scenes are cfg2-sized
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    if args.workload == "cfg4":
+        return run_cfg4(args)
     return run_ours(args)
 
 

@@ -398,6 +398,94 @@ class LocalGradBucket:
         self.exchange.allreduce_sum(self.flat, out=self.flat)
 
 
+class BucketedGradReducer:
+    """Scene-per-GPU data parallelism (BASELINE.json configs[3]): every rank trains the full model on its own scene(s);
+    the batch gradient is the SUM over scenes (``batch_loss += loss``, ``code/train.py:61-88``).  The 580 MB of
+    gradients live in a few persistent flat buckets (``.grad`` = views, filled in reverse layer order as backward
+    proceeds); each bucket's NCCL all-reduce is launched on a side stream the moment its last gradient has been
+    accumulated, so the exchange over NVLink hides behind the rest of backward.
+
+        reducer = BucketedGradReducer(model)
+        reducer.prepare(); loss.backward(); reducer.finish(); optimizer.step()
+
+    ``accumulate_only()``: a context in which backward only accumulates (more scenes than ranks: all but the last scene)."""
+
+    def __init__(self, model, group=None, bucket_bytes=64 << 20):
+        self.group = group
+        params = [p for p in model.parameters() if p.requires_grad][::-1]      # ~ the order gradients become ready
+        self.buckets, cur, cur_n = [], [], 0
+        for p in params:
+            cur.append(p)
+            cur_n += p.numel()
+            if cur_n * 4 >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, cur_n = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.flats, self.views, self.bucket_of = [], {}, {}
+        for b, plist in enumerate(self.buckets):
+            flat = torch.zeros(_pad4(sum(p.numel() for p in plist)), dtype=torch.float32, device=plist[0].device)
+            off = 0
+            for p in plist:
+                self.views[p] = flat[off:off + p.numel()].view_as(p)
+                self.bucket_of[p] = b
+                off += p.numel()
+            self.flats.append(flat)
+        self.comm_stream = torch.cuda.Stream(device=params[0].device) if params and params[0].is_cuda else None
+        self.enabled = True
+        self._pending, self._works, self._launched = [], [], []
+        for p in params:
+            p.register_post_accumulate_grad_hook(self._on_grad)
+
+    def prepare(self):
+        for flat in self.flats:
+            flat.zero_()
+        for p, v in self.views.items():
+            p.grad = v
+        self._pending = [len(b) for b in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+
+    def _launch(self, b):
+        self._launched[b] = True
+        if self.comm_stream is None:
+            self._works.append(dist.all_reduce(self.flats[b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            return
+        self.comm_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm_stream):
+            self._works.append(dist.all_reduce(self.flats[b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def _on_grad(self, p):
+        if not self.enabled or not self._pending:
+            return
+        b = self.bucket_of[p]
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and not self._launched[b]:
+            self._launch(b)
+
+    def accumulate_only(self):
+        reducer = self
+
+        class _Ctx:
+            def __enter__(self):
+                reducer.enabled = False
+
+            def __exit__(self, *exc):
+                reducer.enabled = True
+        return _Ctx()
+
+    def finish(self):
+        """Launch what is still pending (parameters that received no gradient) and make the current stream wait."""
+        for b in range(len(self.buckets)):
+            if not self._launched[b]:
+                self._launch(b)
+        for w in self._works:
+            w.wait()
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self._works = []
+
+
 def allreduce_gradients(parameters, group=None):
     """One flat NCCL all-reduce SUM over ALL parameter gradients: the gradient exchange of scene-per-GPU data
     parallelism (``batch_loss += loss`` over the scenes of a batch, ``code/train.py:61-88``)."""

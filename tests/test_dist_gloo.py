@@ -254,3 +254,40 @@ def test_local_grad_bucket_points_gradients_at_one_flat_buffer():
     bucket.allreduce()
     assert torch.equal(model["scenepoint_head"].weight.grad, torch.full((2, 3), 8.0))
     assert torch.equal(model["view_head"].weight.grad, torch.full((2, 3), 4.0))
+
+
+def _reducer_worker(rank, world, init_file, result_file):
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+        unused = torch.nn.Linear(2, 2)                       # never used in forward: its bucket is flushed by finish()
+        model.add_module("unused", unused)
+        reducer = gdist.BucketedGradReducer(model, bucket_bytes=64)     # tiny buckets: several launches per step
+        assert len(reducer.buckets) > 2
+        xs = [torch.full((4, 6), float(rank + 1)), torch.full((4, 6), float(rank + 3))]      # two scenes per rank
+        for _ in range(2):                                   # second step: buffers are re-zeroed, hooks fire again
+            reducer.prepare()
+            with reducer.accumulate_only():
+                model[:4](xs[0]).square().sum().backward()
+            model[:4](xs[1]).square().sum().backward()
+            reducer.finish()
+        torch.save({k: p.grad.clone() for k, p in model.named_parameters()}, f"{result_file}.{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_grad_reducer_sums_over_ranks_and_scenes():
+    world = 2
+    with tempfile.TemporaryDirectory() as tmp:
+        init_file, result_file = os.path.join(tmp, "init"), os.path.join(tmp, "res")
+        mp.spawn(_reducer_worker, args=(world, init_file, result_file), nprocs=world, join=True)
+        res = [torch.load(f"{result_file}.{r}") for r in range(world)]
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+    for v in (1.0, 3.0, 2.0, 4.0):                           # all four scenes of the batch, summed
+        model(torch.full((4, 6), v)).square().sum().backward()
+    for k, p in model.named_parameters():
+        for r in res:
+            assert torch.allclose(r[k], p.grad, rtol=1e-5, atol=1e-6), k
+    assert torch.equal(res[0]["unused.weight"], torch.zeros(2, 2))
