@@ -346,17 +346,21 @@ def run_reference(args):
     ms = 1e3 * float(np.mean(times))
     value = E * 2 * (s["num_layers"] + 1) / (ms / 1e3)
     base["value"] = value
-    E_full = observations(cfg["m"], cfg["n"], cfg["n_obs"], cfg["seed"])[0].shape[1] if cfg["n_obs"] <= 1_000_000 else cfg["n_obs"]
+    # the SAME config object our arm prints for this --gpus / --workload / --scaling (the CPU arm itself is one process)
+    weak = args.gpus > 1 and args.scaling == "weak"
+    n_total, obs_total = (cfg["n"] * args.gpus, cfg["n_obs"] * args.gpus) if weak else (cfg["n"], cfg["n_obs"])
+    E_full = observations(cfg["m"], n_total, obs_total, cfg["seed"])[0].shape[1]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "edges/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(cfg, E_full, 1, "strong"), "cpu_baseline": base,
+            "higher_is_better": True, "scaling": args.scaling if args.gpus > 1 else "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(dict(cfg, n=n_total), E_full, args.gpus, args.scaling if args.gpus > 1 else "strong"),
+            "cpu_baseline": base,
             "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def workload_config(cfg, E, n_gpus, scaling):
-    return {"workload": f"{cfg['name']}: GASFM fwd+bwd, {cfg['m']} views x {cfg['n']} points, E~{E} observations, "
+    return {"workload": f"{cfg['name']}: GASFM fwd+bwd, {cfg['m']} views x {cfg['n']} points, E={E} observations, "
                         f"n_feat_proj={cfg['n_feat_proj']}, 4 heads, {cfg['num_layers']} layers, shipped other widths",
             "edge_level_gats_per_step": 2 * (cfg["num_layers"] + 1),
             "cache": f"inputs larger than L2 (one [E,{cfg['n_feat_proj']}] fp32 tensor = {E * cfg['n_feat_proj'] * 4 / 1e6 / n_gpus:.0f} MB per GPU vs 126 MB L2)",
@@ -547,13 +551,11 @@ def run_ours(args):
         return
     scaling = args.scaling if world > 1 else "strong"
     wc = workload_config(dict(cfg, n=r["n_total"]), r["E"], world, scaling)
-    if exchange_kind:
-        wc["exchange"] = exchange_kind
-    wc["activation_recompute"] = r["recompute"]
     line = {"metric": METRIC, "value": r["value"], "unit": "edges/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wc,
             "forward_ms_per_scene": r["forward_ms"], "cuda_graph": r["graphed"], "eager_ms_per_step": r["eager_ms"],
+            "activation_recompute": r["recompute"], "exchange": exchange_kind,
             "e2e": {"value": r["e2e_value"], "unit": "edges/s", "ms_per_step": r["e2e_ms"],
                     "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
             "gpu_launches": r["launches"] * args.steps, "gpu_launches_per_step": r["launches"],
