@@ -53,6 +53,7 @@ SIGNATURES = {
     "gasfm_wgrad_f16x2_supported": (_I, [_L, _I, _I, _L, _L]),
     "gasfm_wgrad_f16x2_ws_bytes": (_SZ, [_I, _I]),
     "gasfm_wgrad_f16x2": (_I, [_P, _L, _P, _L, _P, _P, _L, _I, _I, _P, _P, _P, _P]),
+    "gasfm_wgrad_f16x2_multi": (_I, [_P, _P, _I, _P, _L, _P, _P, _L, _I, _I, _P, _P, _P, _P]),
     "gasfm_linear_tf32x3_supported": (_I, [_L, _I, _I, _L, _L]),
     "gasfm_linear_tf32x3": (_I, [_P, _L, _P, _P, _P, _P, _L, _L, _I, _I, _I, _P]),
     "gasfm_wgrad_tf32x3_supported": (_I, [_L, _I, _I, _L, _L]),

@@ -36,10 +36,13 @@ constexpr int kHAtomBytes = 1024;           // 8 rows x 128 B
 constexpr int kHKGroups = kHRows / 8;       // 4 atoms along E per stage
 constexpr int kHLbo = kHKGroups * kHAtomBytes;
 
+constexpr int kHMaxGroups = 3;               // weight gradients that share X, computed by one launch
 struct WgradF16Args {
-  const float* dY; int64_t lddy; const float* X; int64_t ldx; const float* amax_dy; const float* amax_x;
+  const float* dY[kHMaxGroups]; int64_t lddy[kHMaxGroups]; const float* X; int64_t ldx;
+  const float* amax_dy /* [n_groups] */; const float* amax_x;
   float* ws; float* ws_db; int64_t E; int Nout; int Kout; int m_tiles; int tmem_cols; int64_t rows_per_cta; int pass_stages;
-};
+  int n_groups;                              // CTA b works on group b % n_groups, row range b / n_groups: the CTAs that read the
+};                                           // same rows of X are launched together, so X comes from HBM once and from L2 after
 
 // MN-major SWIZZLE_128B descriptor (cute::UMMA canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units)
 __device__ __forceinline__ uint64_t make_desc_mn16(uint32_t saddr) {
@@ -62,7 +65,11 @@ __global__ void __launch_bounds__(kHThreads, 1) wgrad_f16x2_kernel(WgradF16Args 
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row_begin = (int64_t)blockIdx.x * p.rows_per_cta;
+  const int grp = (int)(blockIdx.x % p.n_groups), range = (int)(blockIdx.x / p.n_groups);
+  const float* __restrict__ dYg = p.dY[grp];
+  const int64_t lddyg = p.lddy[grp];
+  const int64_t part = (int64_t)range * p.n_groups + grp;      // this CTA's row in the partial-result workspace
+  const int64_t row_begin = (int64_t)range * p.rows_per_cta;
   const int64_t row_end = min(row_begin + p.rows_per_cta, p.E);
   const int num_stages_total = row_end > row_begin ? (int)((row_end - row_begin + kHRows - 1) / kHRows) : 0;
   const int num_passes = num_stages_total > 0 ? (num_stages_total + p.pass_stages - 1) / p.pass_stages : 1;
@@ -83,7 +90,7 @@ __global__ void __launch_bounds__(kHThreads, 1) wgrad_f16x2_kernel(WgradF16Args 
   const uint32_t tmem_base = tmem_base_slot;
 
   float s_dy, s_x, d_dy, d_x;
-  row_scale_from_amax(__ldg(p.amax_dy), s_dy, d_dy);
+  row_scale_from_amax(__ldg(p.amax_dy + grp), s_dy, d_dy);
   row_scale_from_amax(__ldg(p.amax_x), s_x, d_x);
 
   if (warp < 4) {
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(kHThreads, 1) wgrad_f16x2_kernel(WgradF16Args 
       for (int i = 0; i < RPT; ++i) {
         const int64_t e = row_begin + (int64_t)it * kHRows + r0 + 4 * i;
         const bool ok = it < num_stages_total && e < row_end;
-        a[i] = (ok && a_on) ? ld_stream4(p.dY + e * p.lddy + 4 * col4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        a[i] = (ok && a_on) ? ld_stream4(dYg + e * lddyg + 4 * col4) : make_float4(0.f, 0.f, 0.f, 0.f);
         b[i] = (ok && b_on) ? ld_stream4(p.X + e * p.ldx + 4 * col4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
@@ -202,7 +209,7 @@ __global__ void __launch_bounds__(kHThreads, 1) wgrad_f16x2_kernel(WgradF16Args 
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int n = mt * 128 + quarter * 32 + 8 * i + (lane >> 2);
-            const float* src = p.ws + ((int64_t)blockIdx.x * p.Nout + n) * p.Kout + col;
+            const float* src = p.ws + (part * p.Nout + n) * p.Kout + col;
             const bool on = pass > 0 && n < p.Nout && col < p.Kout;
             o0[i] = on ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
             o1[i] = on ? *reinterpret_cast<const float4*>(src + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -239,7 +246,7 @@ __global__ void __launch_bounds__(kHThreads, 1) wgrad_f16x2_kernel(WgradF16Args 
               float4 w = *reinterpret_cast<const float4*>(stg + rr * 128 + (((2 * pc + 1) ^ (rr & 7)) << 4));
               v.x += o0[i].x; v.y += o0[i].y; v.z += o0[i].z; v.w += o0[i].w;
               w.x += o1[i].x; w.y += o1[i].y; w.z += o1[i].z; w.w += o1[i].w;
-              float* out = p.ws + ((int64_t)blockIdx.x * p.Nout + n) * p.Kout + col;
+              float* out = p.ws + (part * p.Nout + n) * p.Kout + col;
               asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(out), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w),
                            "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w)
                            : "memory");
@@ -259,7 +266,7 @@ __global__ void __launch_bounds__(kHThreads, 1) wgrad_f16x2_kernel(WgradF16Args 
       float* S = reinterpret_cast<float*>(smem);               // [4][256]
       if (a_on) *reinterpret_cast<float4*>(S + r0 * 256 + 4 * col4) = colsum;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (t < p.Nout) p.ws_db[(int64_t)blockIdx.x * p.Nout + t] = (S[t] + S[256 + t]) + (S[512 + t] + S[768 + t]);
+      if (t < p.Nout) p.ws_db[part * p.Nout + t] = (S[t] + S[256 + t]) + (S[512 + t] + S[768 + t]);
     }
   }
   __syncthreads();
@@ -280,11 +287,16 @@ extern "C" size_t gasfm_wgrad_f16x2_ws_bytes(int Nout, int Kout) {
   return ((size_t)kNumSMs * Nout * Kout + (size_t)kNumSMs * 256) * sizeof(float);
 }
 
-extern "C" int gasfm_wgrad_f16x2(const float* dY, int64_t lddy, const float* X, int64_t ldx, const float* amax_dy, const float* amax_x,
-                                 int64_t E, int Nout, int Kout, float* dW, float* dbias, void* ws, void* stream) {
-  GASFM_REQUIRE(gasfm_wgrad_f16x2_supported(E, Nout, Kout, lddy, ldx), "wgrad_f16x2: unsupported shape E=%lld Nout=%d Kout=%d",
-                (long long)E, Nout, Kout);
-  GASFM_REQUIRE(ws != nullptr && amax_dy != nullptr && amax_x != nullptr && ((uintptr_t)dY | (uintptr_t)X | (uintptr_t)dW | (uintptr_t)ws) % 16 == 0,
+static int wgrad_f16x2_launch(const float* const* dY, const int64_t* lddy, int n_groups, const float* X, int64_t ldx,
+                              const float* amax_dy, const float* amax_x, int64_t E, int Nout, int Kout, float* dW, float* dbias,
+                              void* ws, void* stream) {
+  GASFM_REQUIRE(n_groups >= 1 && n_groups <= kHMaxGroups, "wgrad_f16x2: 1..%d groups", kHMaxGroups);
+  for (int g = 0; g < n_groups; ++g) {
+    GASFM_REQUIRE(gasfm_wgrad_f16x2_supported(E, Nout, Kout, lddy[g], ldx), "wgrad_f16x2: unsupported shape E=%lld Nout=%d Kout=%d",
+                  (long long)E, Nout, Kout);
+    GASFM_REQUIRE(dY[g] != nullptr && (uintptr_t)dY[g] % 16 == 0, "wgrad_f16x2: bad dY pointer");
+  }
+  GASFM_REQUIRE(ws != nullptr && amax_dy != nullptr && amax_x != nullptr && ((uintptr_t)X | (uintptr_t)dW | (uintptr_t)ws) % 16 == 0,
                 "wgrad_f16x2: bad pointers");
   const int m_tiles = Nout / 128;
   int tmem_cols = 32;
@@ -299,11 +311,12 @@ extern "C" int gasfm_wgrad_f16x2(const float* dY, int64_t lddy, const float* X, 
     }
     smem_allowed = smem;
   }
-  // split-K over the SMs; every CTA gets a multiple of the stage size
+  // split-K over the SMs: ``ranges`` row ranges x n_groups CTAs; every CTA gets a multiple of the stage size
   int64_t stages = (E + kHRows - 1) / kHRows;
-  int grid = (int)(stages < kNumSMs ? stages : kNumSMs);
-  const int64_t rows_per_cta = ((stages + grid - 1) / grid) * kHRows;
-  grid = (int)((E + rows_per_cta - 1) / rows_per_cta);
+  const int max_ranges = kNumSMs / n_groups;
+  int ranges = (int)(stages < max_ranges ? stages : max_ranges);
+  const int64_t rows_per_cta = ((stages + ranges - 1) / ranges) * kHRows;
+  ranges = (int)((E + rows_per_cta - 1) / rows_per_cta);
   static int pass_stages = 0;
   if (pass_stages == 0) {
     const char* env = getenv("GASFM_WGRAD_F16_PASS_STAGES");     // 32-row stages per accumulation pass (multiple of kHRegBufs)
@@ -312,13 +325,29 @@ extern "C" int gasfm_wgrad_f16x2(const float* dY, int64_t lddy, const float* X, 
     pass_stages &= ~(kHRegBufs - 1);
   }
   float* ws_db = dbias ? (float*)ws + (size_t)kNumSMs * Nout * Kout : nullptr;
-  WgradF16Args a{dY, lddy, X, ldx, amax_dy, amax_x, (float*)ws, ws_db, E, Nout, Kout, m_tiles, tmem_cols, rows_per_cta, pass_stages};
+  WgradF16Args a{};
+  for (int g = 0; g < n_groups; ++g) { a.dY[g] = dY[g]; a.lddy[g] = lddy[g]; }
+  a.X = X; a.ldx = ldx; a.amax_dy = amax_dy; a.amax_x = amax_x; a.ws = (float*)ws; a.ws_db = ws_db; a.E = E; a.Nout = Nout; a.Kout = Kout;
+  a.m_tiles = m_tiles; a.tmem_cols = tmem_cols; a.rows_per_cta = rows_per_cta; a.pass_stages = pass_stages; a.n_groups = n_groups;
   cudaStream_t st = (cudaStream_t)stream;
-  wgrad_f16x2_kernel<<<grid, kHThreads, smem, st>>>(a);
+  wgrad_f16x2_kernel<<<ranges * n_groups, kHThreads, smem, st>>>(a);
   int rc = check_launch("wgrad_f16x2");
   if (rc) return rc;
-  const int64_t width = (int64_t)Nout * Kout;
-  const ColReduceJob jw{(const float*)ws, width, width, dW, 0, 0}, jb{ws_db, Nout, Nout, dbias, 0, 0};
-  launch_col_reduce(jw, dbias ? &jb : nullptr, grid, 1.f, st);
+  // partials are [range][group][Nout x Kout]: ONE column reduction yields the stacked [n_groups x Nout, Kout] result
+  const int64_t width = (int64_t)n_groups * Nout * Kout, bwidth = (int64_t)n_groups * Nout;
+  const ColReduceJob jw{(const float*)ws, width, width, dW, 0, 0}, jb{ws_db, bwidth, bwidth, dbias, 0, 0};
+  launch_col_reduce(jw, dbias ? &jb : nullptr, ranges, 1.f, st);
   return check_launch("wgrad_f16x2(reduce)");
+}
+
+extern "C" int gasfm_wgrad_f16x2(const float* dY, int64_t lddy, const float* X, int64_t ldx, const float* amax_dy, const float* amax_x,
+                                 int64_t E, int Nout, int Kout, float* dW, float* dbias, void* ws, void* stream) {
+  return wgrad_f16x2_launch(&dY, &lddy, 1, X, ldx, amax_dy, amax_x, E, Nout, Kout, dW, dbias, ws, stream);
+}
+
+extern "C" int gasfm_wgrad_f16x2_multi(const float* const* dY, const int64_t* lddy, int n_groups, const float* X, int64_t ldx,
+                                       const float* amax_dy, const float* amax_x, int64_t E, int Nout, int Kout, float* dW,
+                                       float* dbias, void* ws, void* stream) {
+  GASFM_REQUIRE(dY != nullptr && lddy != nullptr, "wgrad_f16x2_multi: NULL argument");
+  return wgrad_f16x2_launch(dY, lddy, n_groups, X, ldx, amax_dy, amax_x, E, Nout, Kout, dW, dbias, ws, stream);
 }

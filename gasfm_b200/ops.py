@@ -520,6 +520,31 @@ def wgrad_f16x2(dy, x, amax_dy, amax_x, with_bias=False):
     return (dw, db) if with_bias else dw
 
 
+def wgrad_f16x2_multi(dys, x, amax_dys, amax_x):
+    """[dW_g, db_g] for 2..3 projections of the SAME x in one launch (x is read from HBM once, by the other groups from L2).
+    ``amax_dys``: n-element device tensor (max |dY_g|), ``amax_x``: 1-element device tensor.  -> (dW [n,Nout,Kout], db [n,Nout])."""
+    import ctypes
+
+    rows = [_rows(dy) for dy in dys]
+    x, ldx = _rows(x)
+    n = len(rows)
+    E, n_out = rows[0][0].shape
+    k_out = x.shape[1]
+    dev = x.device
+    dw = torch.empty((n, n_out, k_out), dtype=torch.float32, device=dev)
+    db = torch.empty((n, n_out), dtype=torch.float32, device=dev)
+    ws = torch.empty(_lib.size_query("gasfm_wgrad_f16x2_ws_bytes", n_out, k_out) // 4, dtype=torch.float32, device=dev)
+    ptrs = (ctypes.c_void_p * n)(*[r[0].data_ptr() for r in rows])
+    lds = (ctypes.c_int64 * n)(*[r[1] for r in rows])
+    with _lib.device_guard(dev):
+        _lib.call("gasfm_wgrad_f16x2_multi", ptrs, lds, n, _lib.ptr(x), ldx, _lib.ptr(amax_dys.contiguous()), _lib.ptr(amax_x),
+                  E, n_out, k_out, _lib.ptr(dw), _lib.ptr(db), _lib.ptr(ws), _lib.stream_ptr())
+    return dw, db
+
+
+WGRAD_MULTI = os.environ.get("GASFM_WGRAD_MULTI", "1") != "0"     # A/B switch: one launch per block instead of three
+
+
 def _linear_backward(x, weight, dy, need_x, need_w, need_b, dx_out=None, amax=None):
     """Gradients of y = x W^T + b on the tensor-core kernels; ``dx_out``: accumulate dX into this buffer."""
     dy = dy.contiguous()
@@ -594,6 +619,15 @@ class _LinearMulti(torch.autograd.Function):
             # dX = [dY_0 | dY_1 | ..] [W_0; W_1; ..]: one pass over every dY_i, one write of dX
             dys = [dy.contiguous() for dy in dys]
             dx, dy_amax = gemm_tf32x3_cat(dys, torch.cat([w.t() for w in weights], dim=1), want_amax=True)
+        ldx = x.stride(0) if x.stride(1) == 1 else K
+        if (fused_dx and ctx.x_amax is not None and WGRAD_MULTI and WGRAD_KIND == "f16x2" and len(weights) <= 3
+                and all(ctx.needs_input_grad[1 + 2 * i] for i in range(len(weights)))
+                and wgrad_f16x2_supported(M, n_out, K, n_out, ldx)):
+            # every weight gradient of the node in one launch: x is read from HBM once
+            dw_all, db_all = wgrad_f16x2_multi(dys, x, dy_amax, ctx.x_amax)
+            for i in range(len(weights)):
+                grads += [dw_all[i], db_all[i] if ctx.needs_input_grad[2 + 2 * i] else None]
+            return (dx, *grads)
         for i, (w, dy) in enumerate(zip(weights, dys)):
             # both operand maxima are known (x from the forward GEMM, dY_i from the GEMM above): fp16 weight gradient
             amax = (dy_amax[i:i + 1], ctx.x_amax) if (fused_dx and ctx.x_amax is not None) else None
@@ -703,9 +737,14 @@ class _EdgeBlockProject(torch.autograd.Function):
                for dy in dys]
         dy_x, dy_amax = gemm_tf32x3_cat(dys, torch.cat([w.t() for w in weights], dim=1), want_amax=True)
         wgrads = []
-        for i, dy in enumerate(dys):
-            dw, db = wgrad_f16x2(dy, y, dy_amax[i:i + 1], x_amax, with_bias=True)
-            wgrads += [dw, db]
+        if WGRAD_MULTI:
+            dw_all, db_all = wgrad_f16x2_multi(dys, y, dy_amax, x_amax)
+            for i in range(len(dys)):
+                wgrads += [dw_all[i], db_all[i]]
+        else:
+            for i, dy in enumerate(dys):
+                dw, db = wgrad_f16x2(dy, y, dy_amax[i:i + 1], x_amax, with_bias=True)
+                wgrads += [dw, db]
         del y
         rc.release()
         dx, dgamma, dbeta = _ln_relu_backward(x_raw, mean, rstd, gamma, beta, dy_x, add=dskip)

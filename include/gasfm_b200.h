@@ -245,6 +245,14 @@ GASFM_API int gasfm_wgrad_f16x2(const float* dY, int64_t lddy, const float* X, i
                       const float* amax_dy, const float* amax_x, int64_t E, int Nout, int Kout,
                       float* dW, float* dbias, void* ws, void* stream);
 
+/* n_groups <= 3 weight gradients that share X in ONE launch: dW[g] = dY[g]^T X, db[g] = column sums of dY[g]
+ * (lin_l x2 + lin_proj of one block all multiply the same x, models/layers.py:329,426,941).  dY / lddy: host arrays of device
+ * pointers / row strides; amax_dy[n_groups]: device array; dW: stacked [n_groups * Nout, Kout], dbias: [n_groups * Nout].
+ * The CTAs working on the same rows run side by side, so X is fetched from HBM once and from L2 by the other groups. */
+GASFM_API int gasfm_wgrad_f16x2_multi(const float* const* dY, const int64_t* lddy, int n_groups, const float* X, int64_t ldx,
+                            const float* amax_dy, const float* amax_x, int64_t E, int Nout, int Kout,
+                            float* dW, float* dbias, void* ws, void* stream);
+
 /* Weight gradient of the same projections: dW[Nout,Kout] = dY[E,Nout]^T * X[E,Kout], 3xTF32 on tcgen05,
  * deterministic split-K over the SMs.  ``ws`` needs gasfm_wgrad_tf32x3_ws_bytes(Nout,Kout) bytes. */
 GASFM_API int gasfm_wgrad_tf32x3_supported(int64_t E, int Nout, int Kout, int64_t lddy, int64_t ldx);
