@@ -46,6 +46,9 @@ struct GemmF16Args {
   int groups;                                 // B = [groups * N, K] stacked weights, C column offset g * N: one pass over A
   int tmem_cols; int accumulate; int debug;   // debug: phase-isolation bits for profiling (GASFM_GEMM_DEBUG)
   float* a_amax;                              // optional: max |A| over the whole matrix (atomicMax; zeroed by the launcher)
+  // LN variant: the operand is relu(layer_norm(A) * gamma + beta), evaluated on the register-resident tile (A = x_raw is
+  // read once, the normalised matrix never exists in memory); the row statistics are written out for backward
+  const float* ln_gamma; const float* ln_beta; float ln_eps; float* ln_mean; float* ln_rstd;
   long long* trace;                           // optional [3 roles][kTraceTiles][16] SM-clock timestamps of CTA 0 (profiling)
 };
 
@@ -55,7 +58,7 @@ constexpr int kTraceTiles = 16;
     if (p.trace && blockIdx.x == 0 && (it) < kTraceTiles) p.trace[((role) * kTraceTiles + (it)) * 16 + (slot)] = clock64(); \
   } while (0)
 
-template <int KB>   // number of 64-wide K blocks: K <= 64 * KB
+template <int KB, bool LN = false>   // KB: number of 64-wide K blocks (K <= 64 * KB); LN: LayerNorm + ReLU on the A tile
 __global__ void __cluster_dims__(kFCluster, 1, 1) __launch_bounds__(kFThreads, 1)
 gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, GemmF16Args p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -68,6 +71,7 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float bias_s[kFMaxGroups * 256], bscale_s[kFMaxGroups * 256];   // [group][256]
   __shared__ float row_descale[kFScaleSlots][kFBlockM];
+  __shared__ __align__(16) float ln_gamma_s[LN ? 256 : 4], ln_beta_s[LN ? 256 : 4];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t num_tiles = (p.M + kFBlockM - 1) / kFBlockM;
@@ -87,6 +91,12 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
     const int g = j >> 8, c = j & 255;
     bias_s[j] = (p.bias && c < p.N) ? p.bias[g * p.N + c] : 0.f;
     bscale_s[j] = c < p.N ? p.b_scale[g * p.N + c] : 1.f;
+  }
+  if constexpr (LN) {
+    for (int j = threadIdx.x; j < 256; j += kFThreads) {
+      ln_gamma_s[j] = j < p.K ? p.ln_gamma[j] : 0.f;
+      ln_beta_s[j] = j < p.K ? p.ln_beta[j] : 0.f;
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols) : "memory");
@@ -180,6 +190,46 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
     for (int kb = 0; kb < KB; ++kb) load_block(0, kb, buf[kb]);
     float seen_max = 0.f;
     for (int64_t it = 0; it < my_steps; ++it) {
+      if constexpr (LN) {
+        // LayerNorm + ReLU in place on the register tile: two-pass mean / variance over the K columns of each row
+        // (16 lanes share a row), then y = max(0, (x - mean) rstd gamma + beta) -- the arithmetic of ln_relu_fwd_kernel
+        const int64_t tile = (cluster_id + it * num_clusters) * kFCluster + cta_rank;
+        const float inv_k = 1.f / (float)p.K;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t row = tile * kFBlockM + rg + 16 * i;
+          float sum = 0.f;
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) sum += (buf[kb][i].x + buf[kb][i].y) + (buf[kb][i].z + buf[kb][i].w);
+#pragma unroll
+          for (int off = 1; off < 16; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+          const float mean = sum * inv_k;
+          float sq = 0.f;
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            if (kb * kFBlockK + q * 4 < p.K) {            // padded columns (K < 64 KB) hold zeros and do not count
+              const float dx = buf[kb][i].x - mean, dy = buf[kb][i].y - mean, dz = buf[kb][i].z - mean, dw = buf[kb][i].w - mean;
+              sq = fmaf(dx, dx, sq); sq = fmaf(dy, dy, sq); sq = fmaf(dz, dz, sq); sq = fmaf(dw, dw, sq);
+            }
+          }
+#pragma unroll
+          for (int off = 1; off < 16; off <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+          const float rstd = 1.f / sqrtf(sq * inv_k + p.ln_eps);
+          const bool live = row < p.M;                    // rows past the end stay zero (they must not enter a_amax)
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {
+            const int kcol = kb * kFBlockK + q * 4;
+            const float4 g = *reinterpret_cast<const float4*>(&ln_gamma_s[kcol & 255]);
+            const float4 b = *reinterpret_cast<const float4*>(&ln_beta_s[kcol & 255]);
+            const bool on = live && kcol < p.K;
+            buf[kb][i].x = on ? fmaxf(fmaf((buf[kb][i].x - mean) * rstd, g.x, b.x), 0.f) : 0.f;
+            buf[kb][i].y = on ? fmaxf(fmaf((buf[kb][i].y - mean) * rstd, g.y, b.y), 0.f) : 0.f;
+            buf[kb][i].z = on ? fmaxf(fmaf((buf[kb][i].z - mean) * rstd, g.z, b.z), 0.f) : 0.f;
+            buf[kb][i].w = on ? fmaxf(fmaf((buf[kb][i].w - mean) * rstd, g.w, b.w), 0.f) : 0.f;
+          }
+          if (q == 0 && live && it < my_steps) { p.ln_mean[row] = mean; p.ln_rstd[row] = rstd; }
+        }
+      }
       // row maxima -> power-of-two scales (16 lanes share a row)
       float scale[8];
       float* descale_slot = row_descale[it & (kFScaleSlots - 1)];
@@ -356,14 +406,17 @@ extern "C" int gasfm_linear_f16x2_supported(int64_t M, int N, int K, int64_t lda
   return (M > 0 && N >= 16 && N <= 256 && N % 16 == 0 && K >= 64 && K <= 256 && K % 8 == 0 && lda % 4 == 0 && ldc % 4 == 0) ? 1 : 0;
 }
 
-extern "C" int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi, const void* B_lo, const float* b_descale,
-                                  const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int groups, int accumulate,
-                                  float* a_amax, void* stream) {
+static int linear_f16x2_impl(const float* A, int64_t lda, const void* B_hi, const void* B_lo, const float* b_descale,
+                            const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int groups, int accumulate,
+                            float* a_amax, const float* ln_gamma, const float* ln_beta, float ln_eps, float* ln_mean,
+                            float* ln_rstd, void* stream) {
   GASFM_REQUIRE(gasfm_linear_f16x2_supported(M, N, K, lda, ldc), "linear_f16x2: unsupported shape M=%lld N=%d K=%d lda=%lld ldc=%lld",
                 (long long)M, N, K, (long long)lda, (long long)ldc);
   GASFM_REQUIRE(groups >= 1 && groups <= kFMaxGroups && ldc >= (int64_t)groups * N, "linear_f16x2: 1..%d groups, ldc >= groups * N", kFMaxGroups);
   GASFM_REQUIRE(b_descale != nullptr && ((uintptr_t)A | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C) % 16 == 0,
                 "linear_f16x2: pointers must be 16-byte aligned");
+  const bool ln = ln_gamma != nullptr;
+  GASFM_REQUIRE(!ln || (ln_beta && ln_mean && ln_rstd), "linear_f16x2_ln: gamma, beta, mean and rstd are all required");
   CUtensorMap mh, ml;
   if (make_map_f16(&mh, B_hi, (int64_t)groups * N, K, K, N / kFCluster, kFBlockK) ||
       make_map_f16(&ml, B_lo, (int64_t)groups * N, K, K, N / kFCluster, kFBlockK)) return 1;
@@ -377,23 +430,49 @@ extern "C" int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi,
   static int debug = -1;
   if (debug < 0) { const char* env = getenv("GASFM_GEMM_DEBUG"); debug = env ? atoi(env) : 0; }
   if (a_amax != nullptr) cudaMemsetAsync(a_amax, 0, sizeof(float), (cudaStream_t)stream);
-  GemmF16Args args{A, lda, b_descale, bias, C, ldc, M, N, K, groups, tmem_cols, accumulate, debug, a_amax, g_trace};
-#define LAUNCH_F16(KB)                                                                                                     \
+  GemmF16Args args{A, lda, b_descale, bias, C, ldc, M, N, K, groups, tmem_cols, accumulate, debug, a_amax,
+                   ln_gamma, ln_beta, ln_eps, ln_mean, ln_rstd, g_trace};
+#define LAUNCH_F16(KB, LNV)                                                                                                \
   do {                                                                                                                     \
     /* per-device attribute: set on every call (static smem -- barriers, scales -- also counts against the 227 KB limit) */ \
-    cudaError_t e = cudaFuncSetAttribute(gemm_f16x2_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    cudaError_t e = cudaFuncSetAttribute(gemm_f16x2_kernel<KB, LNV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) {                                                                                                \
       set_error("linear_f16x2: cannot reserve %zu bytes of shared memory (%s)", smem, cudaGetErrorString(e));              \
       return (int)e;                                                                                                       \
     }                                                                                                                      \
-    gemm_f16x2_kernel<KB><<<grid, kFThreads, smem, (cudaStream_t)stream>>>(mh, ml, args);                             \
+    gemm_f16x2_kernel<KB, LNV><<<grid, kFThreads, smem, (cudaStream_t)stream>>>(mh, ml, args);                        \
   } while (0)
-  switch (kb) {
-    case 1: LAUNCH_F16(1); break;
-    case 2: LAUNCH_F16(2); break;
-    case 3: LAUNCH_F16(3); break;
-    default: LAUNCH_F16(4); break;
+  if (ln) {
+    switch (kb) {
+      case 1: LAUNCH_F16(1, true); break;
+      case 2: LAUNCH_F16(2, true); break;
+      case 3: LAUNCH_F16(3, true); break;
+      default: LAUNCH_F16(4, true); break;
+    }
+  } else {
+    switch (kb) {
+      case 1: LAUNCH_F16(1, false); break;
+      case 2: LAUNCH_F16(2, false); break;
+      case 3: LAUNCH_F16(3, false); break;
+      default: LAUNCH_F16(4, false); break;
+    }
   }
 #undef LAUNCH_F16
   return check_launch("linear_f16x2");
+}
+
+extern "C" int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi, const void* B_lo, const float* b_descale,
+                                  const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int groups, int accumulate,
+                                  float* a_amax, void* stream) {
+  return linear_f16x2_impl(A, lda, B_hi, B_lo, b_descale, bias, C, ldc, M, N, K, groups, accumulate, a_amax, nullptr, nullptr, 0.f,
+                           nullptr, nullptr, stream);
+}
+
+extern "C" int gasfm_linear_f16x2_ln(const float* A, int64_t lda, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                                     float* ln_mean, float* ln_rstd, const void* B_hi, const void* B_lo, const float* b_descale,
+                                     const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int groups,
+                                     float* a_amax, void* stream) {
+  GASFM_REQUIRE(ln_gamma != nullptr, "linear_f16x2_ln: gamma is required");
+  return linear_f16x2_impl(A, lda, B_hi, B_lo, b_descale, bias, C, ldc, M, N, K, groups, 0, a_amax, ln_gamma, ln_beta, ln_eps,
+                           ln_mean, ln_rstd, stream);
 }

@@ -438,6 +438,26 @@ def gemm_f16x2_groups(a, weights, biases, want_amax=False):
     return (c, amax) if want_amax else c
 
 
+def gemm_f16x2_groups_ln(x_raw, gamma, beta, eps, weights, biases):
+    """gemm_f16x2_groups over relu(layer_norm(x_raw)) with the normalisation done inside the GEMM's operand producer:
+    x_raw is read once, the normalised matrix is never materialised.  -> (out [M, G*N], max|operand| [1], mean [M], rstd [M])."""
+    x_raw, lda = _rows(x_raw)
+    M, K = x_raw.shape
+    G, N = len(weights), weights[0].shape[0]
+    hi, lo, descale = _split_f16(torch.cat(list(weights), dim=0))
+    bias = torch.cat([b if b is not None else torch.zeros(N, dtype=torch.float32, device=x_raw.device) for b in biases])
+    dev = x_raw.device
+    c = torch.empty((M, G * N), dtype=torch.float32, device=dev)
+    amax = torch.empty(1, dtype=torch.float32, device=dev)
+    mean = torch.empty(M, dtype=torch.float32, device=dev)
+    rstd = torch.empty(M, dtype=torch.float32, device=dev)
+    with _lib.device_guard(dev):
+        _lib.call("gasfm_linear_f16x2_ln", _lib.ptr(x_raw), lda, _lib.ptr(gamma.contiguous()), _lib.ptr(beta.contiguous()), float(eps),
+                  _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(descale), _lib.ptr(bias), _lib.ptr(c), G * N,
+                  M, N, K, G, _lib.ptr(amax), _lib.stream_ptr())
+    return c, amax, mean, rstd
+
+
 def gemm_tf32x3(a, b, bias=None, out=None, accumulate=False):
     return gemm_tc(a, b, bias, out, accumulate, kind="tf32x3")
 
@@ -642,6 +662,7 @@ class _LinearMulti(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------
 # one GASFM block's observation-level front end: relu(LN(x_raw)) -> lin_l (x2) + lin_proj, as ONE autograd node
 # ---------------------------------------------------------------------------------------------
+LN_FUSED = os.environ.get("GASFM_LN_FUSED", "1") != "0"           # A/B switch: LayerNorm + ReLU inside the projection GEMM
 ACTIVATION_RECOMPUTE = os.environ.get("GASFM_RECOMPUTE", "auto")   # "on" | "off" | "auto" (decided per scene by the model)
 _recompute_now = False
 
@@ -673,6 +694,7 @@ class EdgeBlockContext:
             self.y, self.xl = y, xl
 
     def get_y(self):
+        """relu(LN(x_raw)) for the weight gradients: never kept when the forward GEMM normalises on the fly."""
         if self.y is None:
             x_raw, mean, rstd, gamma, beta, eps = self.args[:6]
             with torch.no_grad():
@@ -681,9 +703,13 @@ class EdgeBlockContext:
 
     def get_xl(self, g):
         if self.xl is None:
-            weights, biases = self.args[6], self.args[7]
+            x_raw, _, _, gamma, beta, eps, weights, biases = self.args
+            w2, b2 = [w.detach() for w in weights[:2]], [b.detach() for b in biases[:2]]
             with torch.no_grad():
-                self.xl = gemm_f16x2_groups(self.get_y(), [w.detach() for w in weights[:2]], [b.detach() for b in biases[:2]])
+                if LN_FUSED:
+                    self.xl = gemm_f16x2_groups_ln(x_raw, gamma, beta, eps, w2, b2)[0]
+                else:
+                    self.xl = gemm_f16x2_groups(self.get_y(), w2, b2)
         return self.xl[:, g * self.n_out:(g + 1) * self.n_out]
 
     def xl_getter(self, g):
@@ -714,8 +740,14 @@ class _EdgeBlockProject(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_raw, gamma, beta, eps, rc, *wb):
         weights, biases = wb[0::2], wb[1::2]
-        x_raw, y, mean, rstd, gamma, beta = _ln_relu_forward(x_raw, gamma, beta, eps)
-        out, x_amax = gemm_f16x2_groups(y, weights, biases, want_amax=True)
+        if LN_FUSED:
+            # LayerNorm + ReLU inside the GEMM's operand producer: x_raw is read once, relu(LN(x_raw)) never exists in memory
+            x_raw, y = x_raw.contiguous(), None
+            gamma, beta = gamma.contiguous(), beta.contiguous()
+            out, x_amax, mean, rstd = gemm_f16x2_groups_ln(x_raw, gamma, beta, eps, weights, biases)
+        else:
+            x_raw, y, mean, rstd, gamma, beta = _ln_relu_forward(x_raw, gamma, beta, eps)
+            out, x_amax = gemm_f16x2_groups(y, weights, biases, want_amax=True)
         N = weights[0].shape[0]
         rc.bind(x_raw, mean, rstd, gamma, beta, eps, weights, biases, y, out)
         ctx.save_for_backward(x_raw, mean, rstd, gamma, beta, x_amax, *weights)

@@ -236,6 +236,15 @@ GASFM_API int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi, 
                        int64_t M, int N, int K, int groups, int accumulate,
                        float* a_amax /* optional [1]: receives max |A| (for gasfm_wgrad_f16x2) */, void* stream);
 
+/* The same kernel with LayerNorm + ReLU applied to A on the fly: the operand is relu(layer_norm(A) * gamma + beta)
+ * (normalize_projection_features + relu_on_projection_features feeding lin_l / lin_proj, models/layers.py:232-234 ->
+ * :329,426,941), evaluated on the register-resident A tile, so the normalised features are never written to or read
+ * from memory.  ln_mean / ln_rstd [M] receive the row statistics (needed by gasfm_ln_relu_bwd); a_amax is max |operand|. */
+GASFM_API int gasfm_linear_f16x2_ln(const float* A, int64_t lda, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                          float* ln_mean, float* ln_rstd, const void* B_hi, const void* B_lo,
+                          const float* b_descale, const float* bias, float* C, int64_t ldc,
+                          int64_t M, int N, int K, int groups, float* a_amax, void* stream);
+
 /* Weight gradient on the fp16 path: dW = dY^T X (+ db), each operand scaled by ONE power of two derived from its largest
  * magnitude (amax_dy[1], amax_x[1]: DEVICE scalars, as left behind by the GEMMs above that read the same matrices).
  * Nout in {128, 256}, Kout in {64, 128, 192, 256}; ws: gasfm_wgrad_f16x2_ws_bytes.  Error ~1e-6 of max|dW|. */

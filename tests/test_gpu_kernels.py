@@ -674,3 +674,28 @@ def test_wgrad_f16x2_multi_equals_separate_launches(E, n_groups):
         assert ((db[g].double() - refb).abs().max() / refb.abs().max()).item() < 2e-6
     dw2, db2 = ops.wgrad_f16x2_multi(dys, x, amax, amax_x)
     assert torch.equal(dw, dw2) and torch.equal(db, db2)                 # deterministic
+
+
+@pytest.mark.parametrize("M,K,N,G", [(1000, 256, 256, 3), (70001, 256, 256, 2), (4097, 128, 64, 3), (300, 64, 32, 1), (129, 192, 256, 2)])
+def test_gemm_f16x2_with_fused_layernorm_relu(M, K, N, G):
+    """LayerNorm + ReLU evaluated inside the GEMM's operand producer (x_raw read once, relu(LN(x)) never in memory):
+    projections, row statistics and the operand maximum against fp64; rows with very different scales."""
+    torch.manual_seed(M + K)
+    x = torch.randn(M, K, device=DEV) * (10.0 ** torch.randint(-3, 3, (M, 1), device=DEV).float()) + 0.3
+    gamma, beta = torch.rand(K, device=DEV) + 0.5, torch.randn(K, device=DEV) * 0.3
+    ws = [torch.randn(N, K, device=DEV) / K ** 0.5 for _ in range(G)]
+    bs = [torch.randn(N, device=DEV) for _ in range(G)]
+    out, amax, mean, rstd = ops.gemm_f16x2_groups_ln(x, gamma, beta, 1e-5, ws, bs)
+    xd = x.double()
+    mu, var = xd.mean(1, keepdim=True), xd.var(1, unbiased=False, keepdim=True)
+    y = torch.relu((xd - mu) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double())
+    assert rel_err(mean, mu[:, 0].cpu().numpy()) < 1e-5 * max(1.0, float(mu.abs().max()))
+    assert float(((rstd.double() - 1 / torch.sqrt(var[:, 0] + 1e-5)).abs() * torch.sqrt(var[:, 0] + 1e-5)).max()) < 1e-5
+    assert abs(float(amax) - float(y.max())) < 1e-5 * float(y.max())
+    for g in range(G):
+        ref = y @ ws[g].double().t() + bs[g].double()
+        assert rel_err(out[:, g * N:(g + 1) * N], ref.cpu().numpy()) < FP32_TOL
+    # the unfused pair of kernels gives the same projections to fp32 accuracy
+    y32 = ops.ln_relu(x, gamma, beta, 1e-5)
+    ref32 = ops.gemm_f16x2_groups(y32, ws, bs) if G > 1 else ops.gemm_f16x2(y32, ws[0], bs[0])
+    assert rel_err(out, ref32.double().cpu().numpy()) < FP32_TOL
