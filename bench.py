@@ -36,7 +36,10 @@ CFG2 = dict(name="cfg2", m=300, n=50_000, n_obs=500_000, n_feat_proj=256, num_la
 # BASELINE.json configs[2] (1,000 views x 300k points, ~5M observations) at the shipped width and at d=256
 CFG3 = dict(name="cfg3", m=1000, n=300_000, n_obs=5_000_000, n_feat_proj=32, num_layers=12, seed=0)
 CFG3_WIDE = dict(CFG3, name="cfg3_d256", n_feat_proj=256)
-WORKLOADS = {"cfg2": CFG2, "cfg3": CFG3, "cfg3_d256": CFG3_WIDE}
+# BASELINE.json configs[0] as a TRAINING sample: the shipped model on a 20-view x 2k-point scene (~30 % density) -- the size
+# the reference's multi-scene training actually draws (code/datasets/ScenesDataSet.py:30-39); launch-bound without graph replay
+CFG1 = dict(name="cfg1", m=20, n=2000, n_obs=12_000, n_feat_proj=32, num_layers=12, seed=0)
+WORKLOADS = {"cfg1": CFG1, "cfg2": CFG2, "cfg3": CFG3, "cfg3_d256": CFG3_WIDE}
 DEFAULT_WORKLOAD = "cfg3_d256"
 FALLBACK_HBM_GBS = 6650.0     # /opt/skills/guides/B200_PROFILING.md fallback
 METRIC = "gat_layer_edges_per_sec_fwd_bwd"

@@ -662,7 +662,10 @@ class _LinearMulti(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------
 # one GASFM block's observation-level front end: relu(LN(x_raw)) -> lin_l (x2) + lin_proj, as ONE autograd node
 # ---------------------------------------------------------------------------------------------
-LN_FUSED = os.environ.get("GASFM_LN_FUSED", "1") != "0"           # A/B switch: LayerNorm + ReLU inside the projection GEMM
+# LayerNorm + ReLU inside the projection GEMM's operand producer.  Measured on cfg2 (profiles/r02_fusion_ab.md): the forward
+# gets 0.2 ms faster (the GEMM slows down by about what the separate LN kernel cost), but backward then has to rebuild
+# relu(LN(x)) for the weight gradients, +1.5 ms per step -- so it is OFF by default and meant for forward-only use.
+LN_FUSED = os.environ.get("GASFM_LN_FUSED", "0") != "0"
 ACTIVATION_RECOMPUTE = os.environ.get("GASFM_RECOMPUTE", "auto")   # "on" | "off" | "auto" (decided per scene by the model)
 _recompute_now = False
 

@@ -176,10 +176,12 @@ def test_cfg2_scale_model_matches_fp32_oracle():
     assert worst < GRAD_TOL, (key, worst)
 
 
-def test_activation_recompute_gives_identical_results():
+@pytest.mark.parametrize("ln_fused", [False, True])
+def test_activation_recompute_gives_identical_results(ln_fused, monkeypatch):
     """GASFM_RECOMPUTE: keeping only x_raw + LayerNorm statistics per block and rebuilding relu(LN(x)) and the projected
     attention sources in backward must not change a single bit of the outputs or gradients."""
     from gasfm_b200 import ops
+    monkeypatch.setattr(ops, "LN_FUSED", ln_fused)          # LayerNorm + ReLU as its own kernel / inside the projection GEMM
     conf = gasfm_conf(n_feat_proj=128, n_feat_view=128, n_feat_global=256, num_layers=3)
     torch.manual_seed(3)
     model = GraphAttnSfMNet(conf).to(DEV)
@@ -204,5 +206,5 @@ def test_activation_recompute_gives_identical_results():
     assert torch.equal(res["off"][0], res["on"][0]) and torch.equal(res["off"][1], res["on"][1])
     for k, g in res["off"][2].items():
         assert torch.equal(g, res["on"][2][k]), k
-    # activations held between forward and backward: each of the two fused blocks drops relu(LN(x)) and its three projections
-    assert res["off"][3] - res["on"][3] > 2 * 3.5 * idx.shape[1] * 128 * 4
+    # activations held between forward and backward: each of the two fused blocks drops its three projections (and relu(LN(x)))
+    assert res["off"][3] - res["on"][3] > 2 * 2.5 * idx.shape[1] * 128 * 4
