@@ -50,6 +50,8 @@ SIGNATURES = {
     "gasfm_debug_set_gemm_trace": (_I, [_P]),
     "gasfm_linear_f16x2_supported": (_I, [_L, _I, _I, _L, _L]),
     "gasfm_linear_f16x2": (_I, [_P, _L, _P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _I, _P, _P]),
+    "gasfm_linear_f16x2_cat_supported": (_I, [_L, _I, _I, _I, _L]),
+    "gasfm_linear_f16x2_cat": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _L, _L, _I, _P, _P]),
     "gasfm_linear_f16x2_ln": (_I, [_P, _L, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _P, _P]),
     "gasfm_wgrad_f16x2_supported": (_I, [_L, _I, _I, _L, _L]),
     "gasfm_wgrad_f16x2_ws_bytes": (_SZ, [_I, _I]),

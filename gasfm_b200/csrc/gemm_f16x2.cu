@@ -49,6 +49,11 @@ struct GemmF16Args {
   // LN variant: the operand is relu(layer_norm(A) * gamma + beta), evaluated on the register-resident tile (A = x_raw is
   // read once, the normalised matrix never exists in memory); the row statistics are written out for backward
   const float* ln_gamma; const float* ln_beta; float ln_eps; float* ln_mean; float* ln_rstd;
+  // CAT variant: A = [A_0 | A_1 | ..] (n_seg matrices of seg_k = 64 KB columns each, separate buffers), K = n_seg * seg_k.
+  // The tile no longer fits the registers, so the operand producer makes two passes over it: row maxima first (one scale per
+  // row across all segments), then scale + split K block by K block; the second pass and -- through an L2 prefetch issued one
+  // tile ahead -- most of the first are served by L2.  seg_amax[n_seg] receives max |A_i| (for the fp16 weight gradient).
+  const float* A_seg[4]; int64_t lda_seg[4]; int n_seg; float* seg_amax;
   long long* trace;                           // optional [3 roles][kTraceTiles][16] SM-clock timestamps of CTA 0 (profiling)
 };
 
@@ -58,7 +63,8 @@ constexpr int kTraceTiles = 16;
     if (p.trace && blockIdx.x == 0 && (it) < kTraceTiles) p.trace[((role) * kTraceTiles + (it)) * 16 + (slot)] = clock64(); \
   } while (0)
 
-template <int KB, bool LN = false>   // KB: number of 64-wide K blocks (K <= 64 * KB); LN: LayerNorm + ReLU on the A tile
+// KB: number of 64-wide K blocks (K <= 64 * KB; CAT: per segment); LN: LayerNorm + ReLU on the A tile; CAT: concatenated A
+template <int KB, bool LN = false, bool CAT = false>
 __global__ void __cluster_dims__(kFCluster, 1, 1) __launch_bounds__(kFThreads, 1)
 gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, GemmF16Args p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -108,6 +114,7 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
   const int acc_cols = p.tmem_cols / 2;     // column offset of the second accumulator
+  const int nkb = CAT ? KB * p.n_seg : KB;  // K blocks per tile
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
@@ -118,7 +125,7 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
       const int half_bytes = half_rows * kFBlockK * 2;
       for (int64_t vt = 0; vt < my_steps * p.groups; ++vt) {       // virtual tile = (M tile, group)
         const int b_row0 = (int)(vt % p.groups) * p.N + (int)cta_rank * half_rows;
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);                 // both CTAs have retired the MMAs of this stage
           uint8_t* st = smem + (size_t)stage * stage_bytes;
           if (p.debug & 4) { mbar_arrive(&full_bar[stage]); if (++stage == kFStages) { stage = 0; phase ^= 1; } continue; }
@@ -141,11 +148,11 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         GASFM_TRACE(1, it, 0);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * acc_cols);
-        for (int kb = 0; kb < KB; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[stage], phase);       // B_hi / B_lo landed (TMA)
-          GASFM_TRACE(1, it, 1 + kb);
+          if (!CAT) GASFM_TRACE(1, it, 1 + kb);
           mbar_wait(&split_bar[stage], phase);      // A_hi / A_lo written by the producer warps
-          GASFM_TRACE(1, it, 5 + kb);
+          if (!CAT) GASFM_TRACE(1, it, 5 + kb);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_hi = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t a_lo = a_hi + kFATileBytes;
@@ -161,8 +168,8 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
             umma_f16(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), idesc, 1u);
           }
           umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << kFCluster) - 1));   // frees the stage in BOTH CTAs' eyes
-          if (kb == KB - 1) umma_commit(&tmem_full_bar[acc]);
-          GASFM_TRACE(1, it, 9 + kb);
+          if (kb == nkb - 1) umma_commit(&tmem_full_bar[acc]);
+          if (!CAT) GASFM_TRACE(1, it, 9 + kb);
           if (++stage == kFStages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -176,6 +183,119 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
     const int t = threadIdx.x - 128;
     const int q = t & 15, rg = t >> 4;
     int stage = 0; uint32_t phase = 0;
+    // scale, split into fp16 hi + lo and store this thread's 8 row pieces of one 64-wide K block (128B-swizzled, K-major)
+    auto convert_block = [&](const float4 (&v)[8], const float (&scale)[8]) {
+      uint8_t* a_hi = smem + (size_t)stage * stage_bytes;
+      uint8_t* a_lo = a_hi + kFATileBytes;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = rg + 16 * i;
+        const int off = row * 128 + ((((q >> 1) ^ (row & 7))) << 4) + ((q & 1) << 3);
+        const float s = scale[i];
+        const float x0 = v[i].x * s, x1 = v[i].y * s, x2 = v[i].z * s, x3 = v[i].w * s;
+        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+        lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(a_hi + off) = hv;
+        *reinterpret_cast<uint2*>(a_lo + off) = lv;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+      mbar_arrive(&split_bar[stage]);
+      if (++stage == kFStages) { stage = 0; phase ^= 1; }
+    };
+    if constexpr (CAT) {
+      static_assert(KB % 2 == 0, "the concatenated producer alternates two register buffers per K block");
+      // global K block kbg = seg * KB + kb of tile it: this thread's float4 of rows rg + 16 i
+      auto load_kbg = [&](int64_t it, int kbg, float4 (&v)[8]) {
+        const int seg = kbg / KB, kcol = (kbg % KB) * kFBlockK + q * 4;
+        const float* base = p.A_seg[seg & 3];
+        const int64_t ld = p.lda_seg[seg & 3];
+        const int64_t tile = (cluster_id + it * num_clusters) * kFCluster + cta_rank;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t row = tile * kFBlockM + rg + 16 * i;
+          v[i] = (it < my_steps && kbg < nkb && row < p.M) ? ld_stream4(base + row * ld + kcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto absmax4 = [](const float4& a) { return fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))); };
+      float seg_seen[4] = {0.f, 0.f, 0.f, 0.f};
+      float4 v0[8], v1[8], v2[8], v3[8];
+      const int lines_per_row = KB * kFBlockK * 4 / 128;          // 128-byte lines of one segment row
+      for (int64_t it = 0; it < my_steps; ++it) {
+        // L2 prefetch of the NEXT tile (its first pass then finds the lines in L2 instead of HBM)
+        if (it + 1 < my_steps) {
+          const int64_t ntile = (cluster_id + (it + 1) * num_clusters) * kFCluster + cta_rank;
+          const int total = kFBlockM * lines_per_row;
+#pragma unroll
+          for (int seg = 0; seg < 4; ++seg) {               // constant indices: the segment table stays in the parameter bank
+            if (seg >= p.n_seg) break;
+            for (int j = t; j < total; j += 256) {
+              const int64_t row = ntile * kFBlockM + j / lines_per_row;
+              if (row < p.M) {
+                const float* a = p.A_seg[seg & 3] + row * p.lda_seg[seg & 3] + (j % lines_per_row) * 32;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+              }
+            }
+          }
+        }
+        // pass 1: row maxima over every K block of the tile, four K blocks in flight
+        float m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = 0.f;
+#pragma unroll
+        for (int seg = 0; seg < 4; ++seg) {
+          if (seg >= p.n_seg) break;
+          float sm = 0.f;
+#pragma unroll
+          for (int kb = 0; kb < KB; kb += 4) {
+            load_kbg(it, seg * KB + kb, v0);
+            load_kbg(it, seg * KB + kb + 1, v1);
+            if (kb + 2 < KB) { load_kbg(it, seg * KB + kb + 2, v2); load_kbg(it, seg * KB + kb + 3, v3); }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float r = fmaxf(absmax4(v0[i]), absmax4(v1[i]));
+              if (kb + 2 < KB) r = fmaxf(r, fmaxf(absmax4(v2[i]), absmax4(v3[i])));
+              m[i] = fmaxf(m[i], r);
+              sm = fmaxf(sm, r);
+            }
+          }
+          seg_seen[seg] = fmaxf(seg_seen[seg], sm);
+        }
+        float scale[8];
+        float* descale_slot = row_descale[it & (kFScaleSlots - 1)];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int off = 1; off < 16; off <<= 1) m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], off));
+          float descale;
+          row_scale_from_amax(m[i], scale[i], descale);
+          if (q == 0) descale_slot[rg + 16 * i] = descale;
+        }
+        // pass 2: K block by K block (from L2), the next block's loads in flight while this one is converted
+        load_kbg(it, 0, v0);
+#pragma unroll
+        for (int seg = 0; seg < 4; ++seg) {
+          if (seg >= p.n_seg) break;
+#pragma unroll
+          for (int kb = 0; kb < KB; kb += 2) {
+            load_kbg(it, seg * KB + kb + 1, v1);
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            convert_block(v0, scale);
+            load_kbg(it, seg * KB + kb + 2, v0);           // past the last block of the tile: zeros, never consumed
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            convert_block(v1, scale);
+          }
+        }
+      }
+      if (p.seg_amax != nullptr) {
+#pragma unroll
+        for (int seg = 0; seg < 4; ++seg)
+          if (seg < p.n_seg) warp_amax_to_global(seg_seen[seg], p.seg_amax + seg);
+      }
+    } else {
     float4 buf[KB][8];
     auto load_block = [&](int64_t it, int kb, float4 (&v)[8]) {
       const int64_t tile = (cluster_id + it * num_clusters) * kFCluster + cta_rank;
@@ -281,6 +401,7 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
       }
     }
     if (p.a_amax != nullptr) warp_amax_to_global(seen_max, p.a_amax);
+    }
   } else {
     // ===================== epilogue (warps 12..15 -> TMEM lane quarters 0..3) =====================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");
@@ -430,8 +551,10 @@ static int linear_f16x2_impl(const float* A, int64_t lda, const void* B_hi, cons
   static int debug = -1;
   if (debug < 0) { const char* env = getenv("GASFM_GEMM_DEBUG"); debug = env ? atoi(env) : 0; }
   if (a_amax != nullptr) cudaMemsetAsync(a_amax, 0, sizeof(float), (cudaStream_t)stream);
-  GemmF16Args args{A, lda, b_descale, bias, C, ldc, M, N, K, groups, tmem_cols, accumulate, debug, a_amax,
-                   ln_gamma, ln_beta, ln_eps, ln_mean, ln_rstd, g_trace};
+  GemmF16Args args{};
+  args.A = A; args.lda = lda; args.b_scale = b_descale; args.bias = bias; args.C = C; args.ldc = ldc; args.M = M; args.N = N; args.K = K;
+  args.groups = groups; args.tmem_cols = tmem_cols; args.accumulate = accumulate; args.debug = debug; args.a_amax = a_amax;
+  args.ln_gamma = ln_gamma; args.ln_beta = ln_beta; args.ln_eps = ln_eps; args.ln_mean = ln_mean; args.ln_rstd = ln_rstd; args.trace = g_trace;
 #define LAUNCH_F16(KB, LNV)                                                                                                \
   do {                                                                                                                     \
     /* per-device attribute: set on every call (static smem -- barriers, scales -- also counts against the 227 KB limit) */ \
@@ -459,6 +582,47 @@ static int linear_f16x2_impl(const float* A, int64_t lda, const void* B_hi, cons
   }
 #undef LAUNCH_F16
   return check_launch("linear_f16x2");
+}
+
+extern "C" int gasfm_linear_f16x2_cat_supported(int64_t M, int N, int n_seg, int seg_k, int64_t ldc) {
+  return (M > 0 && N >= 16 && N <= 256 && N % 16 == 0 && n_seg >= 1 && n_seg <= 4 && (seg_k == 128 || seg_k == 256) && ldc % 4 == 0) ? 1 : 0;
+}
+
+extern "C" int gasfm_linear_f16x2_cat(const float* const* A, const int64_t* lda, int n_seg, int seg_k, const void* B_hi,
+                                      const void* B_lo, const float* b_descale, const float* bias, float* C, int64_t ldc,
+                                      int64_t M, int N, float* a_amax, void* stream) {
+  GASFM_REQUIRE(A && lda && gasfm_linear_f16x2_cat_supported(M, N, n_seg, seg_k, ldc), "linear_f16x2_cat: unsupported shape M=%lld N=%d "
+                "n_seg=%d seg_k=%d", (long long)M, N, n_seg, seg_k);
+  GASFM_REQUIRE(b_descale != nullptr && ((uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C) % 16 == 0, "linear_f16x2_cat: pointers must be 16-byte aligned");
+  const int K = n_seg * seg_k;
+  CUtensorMap mh, ml;
+  if (make_map_f16(&mh, B_hi, N, K, K, N / kFCluster, kFBlockK) || make_map_f16(&ml, B_lo, N, K, K, N / kFCluster, kFBlockK)) return 1;
+  int tmem_cols = 32;
+  while (tmem_cols < 2 * N) tmem_cols <<= 1;
+  const size_t smem = (size_t)kFStages * (2 * kFATileBytes + 2 * (size_t)N * kFBlockK * 2) + 4 * 4096 + 1024;
+  const int64_t tiles = (M + kFBlockM - 1) / kFBlockM;
+  const int64_t pairs = (tiles + kFCluster - 1) / kFCluster;
+  const int grid = (int)(pairs < kNumSMs / kFCluster ? pairs : kNumSMs / kFCluster) * kFCluster;
+  if (a_amax != nullptr) cudaMemsetAsync(a_amax, 0, n_seg * sizeof(float), (cudaStream_t)stream);
+  GemmF16Args args{};
+  args.b_scale = b_descale; args.bias = bias; args.C = C; args.ldc = ldc; args.M = M; args.N = N; args.K = K; args.groups = 1;
+  args.tmem_cols = tmem_cols; args.n_seg = n_seg; args.seg_amax = a_amax;
+  for (int i = 0; i < n_seg; ++i) {
+    GASFM_REQUIRE(A[i] != nullptr && (uintptr_t)A[i] % 16 == 0 && lda[i] % 4 == 0, "linear_f16x2_cat: segment %d misaligned", i);
+    args.A_seg[i] = A[i]; args.lda_seg[i] = lda[i];
+  }
+#define LAUNCH_CAT(KB)                                                                                                          \
+  do {                                                                                                                          \
+    cudaError_t e = cudaFuncSetAttribute(gemm_f16x2_kernel<KB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) {                                                                                                     \
+      set_error("linear_f16x2_cat: cannot reserve %zu bytes of shared memory (%s)", smem, cudaGetErrorString(e));              \
+      return (int)e;                                                                                                            \
+    }                                                                                                                           \
+    gemm_f16x2_kernel<KB, false, true><<<grid, kFThreads, smem, (cudaStream_t)stream>>>(mh, ml, args);                     \
+  } while (0)
+  if (seg_k == 256) LAUNCH_CAT(4); else LAUNCH_CAT(2);
+#undef LAUNCH_CAT
+  return check_launch("linear_f16x2_cat");
 }
 
 extern "C" int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi, const void* B_lo, const float* b_descale,

@@ -485,6 +485,41 @@ def gemm_tf32x3_cat(a_list, b, bias=None, want_amax=False):
     return (c, amax) if want_amax else c
 
 
+DX_KIND = os.environ.get("GASFM_DX", "f16x2")      # concatenated input gradient: scaled 2 x FP16 (default) or "tf32x3"
+
+
+def gemm_f16x2_cat_supported(M, N, n_seg, seg_k):
+    return bool(_lib.load().gasfm_linear_f16x2_cat_supported(int(M), int(N), int(n_seg), int(seg_k), int(N)))
+
+
+def gemm_cat(a_list, b, bias=None, want_amax=False):
+    """[A_0 | A_1 | ..] b^T on the tensor cores: the fp16 path where the shape allows (segments 128 / 256 wide), 3xTF32 otherwise."""
+    M, seg_k = a_list[0].shape
+    if DX_KIND == "f16x2" and all(a.shape == (M, seg_k) for a in a_list) and gemm_f16x2_cat_supported(M, b.shape[0], len(a_list), seg_k):
+        return gemm_f16x2_cat(a_list, b, bias, want_amax)
+    return gemm_tf32x3_cat(a_list, b, bias, want_amax)
+
+
+def gemm_f16x2_cat(a_list, b, bias=None, want_amax=False):
+    """gemm_tf32x3_cat on the scaled 2 x FP16 path (twice the tensor rate; one row scale across the segments, found in a first
+    pass over the tile that L2 absorbs).  Same contract: returns c [M,N] (and max|A_i| per segment)."""
+    import ctypes
+
+    rows = [_rows(a) for a in a_list]
+    M, seg_k = rows[0][0].shape
+    N, n = b.shape[0], len(rows)
+    assert b.shape[1] == n * seg_k and all(r[0].shape == (M, seg_k) for r in rows)
+    hi, lo, descale = _split_f16(b)
+    c = torch.empty((M, N), dtype=torch.float32, device=b.device)
+    ptrs = (ctypes.c_void_p * n)(*[r[0].data_ptr() for r in rows])
+    lds = (ctypes.c_int64 * n)(*[r[1] for r in rows])
+    amax = torch.empty(n, dtype=torch.float32, device=b.device) if want_amax else None
+    with _lib.device_guard(b.device):
+        _lib.call("gasfm_linear_f16x2_cat", ptrs, lds, n, seg_k, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(descale),
+                  _lib.ptr(None if bias is None else bias.contiguous()), _lib.ptr(c), N, M, N, _lib.ptr(amax), _lib.stream_ptr())
+    return (c, amax) if want_amax else c
+
+
 def gemm_f16x2(a, b, bias=None, out=None, accumulate=False):
     return gemm_tc(a, b, bias, out, accumulate, kind="f16x2")
 
@@ -638,7 +673,7 @@ class _LinearMulti(torch.autograd.Function):
         if fused_dx:
             # dX = [dY_0 | dY_1 | ..] [W_0; W_1; ..]: one pass over every dY_i, one write of dX
             dys = [dy.contiguous() for dy in dys]
-            dx, dy_amax = gemm_tf32x3_cat(dys, torch.cat([w.t() for w in weights], dim=1), want_amax=True)
+            dx, dy_amax = gemm_cat(dys, torch.cat([w.t() for w in weights], dim=1), want_amax=True)
         ldx = x.stride(0) if x.stride(1) == 1 else K
         if (fused_dx and ctx.x_amax is not None and WGRAD_MULTI and WGRAD_KIND == "f16x2" and len(weights) <= 3
                 and all(ctx.needs_input_grad[1 + 2 * i] for i in range(len(weights)))
@@ -770,7 +805,7 @@ class _EdgeBlockProject(torch.autograd.Function):
         y = rc.get_y()
         dys = [torch.zeros((x_raw.shape[0], N), dtype=torch.float32, device=x_raw.device) if dy is None else dy.contiguous()
                for dy in dys]
-        dy_x, dy_amax = gemm_tf32x3_cat(dys, torch.cat([w.t() for w in weights], dim=1), want_amax=True)
+        dy_x, dy_amax = gemm_cat(dys, torch.cat([w.t() for w in weights], dim=1), want_amax=True)
         wgrads = []
         if WGRAD_MULTI:
             dw_all, db_all = wgrad_f16x2_multi(dys, y, dy_amax, x_amax)

@@ -236,6 +236,17 @@ GASFM_API int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi, 
                        int64_t M, int N, int K, int groups, int accumulate,
                        float* a_amax /* optional [1]: receives max |A| (for gasfm_wgrad_f16x2) */, void* stream);
 
+/* The fp16 path for a column-wise concatenated A = [A_0 | .. | A_{n_seg-1}] (separate buffers, seg_k in {128, 256} columns each,
+ * B = [N, n_seg * seg_k] split by gasfm_split_f16): the input gradient of a block's projections, dX = sum_i dY_i W_i
+ * (models/layers.py:329,426,941), at twice the tensor rate of gasfm_linear_tf32x3_cat.  One power-of-two scale per ROW across all
+ * segments: the operand producer passes over the tile twice (row maxima, then scale + split), the second pass and -- through an
+ * L2 prefetch issued one tile ahead -- most of the first are served by L2, so HBM still sees every A_i once.
+ * a_amax[n_seg] (optional) receives max |A_i|. */
+GASFM_API int gasfm_linear_f16x2_cat_supported(int64_t M, int N, int n_seg, int seg_k, int64_t ldc);
+GASFM_API int gasfm_linear_f16x2_cat(const float* const* A, const int64_t* lda, int n_seg, int seg_k,
+                           const void* B_hi, const void* B_lo, const float* b_descale, const float* bias,
+                           float* C, int64_t ldc, int64_t M, int N, float* a_amax, void* stream);
+
 /* The same kernel with LayerNorm + ReLU applied to A on the fly: the operand is relu(layer_norm(A) * gamma + beta)
  * (normalize_projection_features + relu_on_projection_features feeding lin_l / lin_proj, models/layers.py:232-234 ->
  * :329,426,941), evaluated on the register-resident A tile, so the normalised features are never written to or read

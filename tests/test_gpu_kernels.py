@@ -699,3 +699,23 @@ def test_gemm_f16x2_with_fused_layernorm_relu(M, K, N, G):
     y32 = ops.ln_relu(x, gamma, beta, 1e-5)
     ref32 = ops.gemm_f16x2_groups(y32, ws, bs) if G > 1 else ops.gemm_f16x2(y32, ws[0], bs[0])
     assert rel_err(out, ref32.double().cpu().numpy()) < FP32_TOL
+
+
+@pytest.mark.parametrize("M,N,n_seg,seg_k", [(70001, 256, 3, 256), (1000, 256, 2, 256), (4099, 64, 3, 128), (129, 256, 4, 256), (300, 32, 1, 128)])
+def test_gemm_f16x2_cat_has_fp32_accuracy(M, N, n_seg, seg_k):
+    """The concatenated input gradient on the fp16 path: [A_0 | A_1 | ..] W^T with ONE row scale across the segments (two-pass
+    operand producer), segments and rows of very different magnitude, against fp64; per-segment maxima exact."""
+    torch.manual_seed(M + n_seg)
+    row_scale = 10.0 ** torch.randint(-4, 4, (M, 1), device=DEV).float()
+    segs = [torch.randn(M + 2, seg_k, device=DEV)[2:] * row_scale * (10.0 ** (-2 * i)) for i in range(n_seg)]
+    w = torch.randn(N, n_seg * seg_k, device=DEV) / (n_seg * seg_k) ** 0.5
+    bias = torch.randn(N, device=DEV)
+    got, amax = ops.gemm_f16x2_cat(segs, w, bias, want_amax=True)
+    ref = torch.cat([a.double() for a in segs], dim=1) @ w.double().t() + bias.double()
+    # error relative to the size of the row's products (|a_row| |w_row|), like the forward kernel's test
+    scale = torch.cat(segs, dim=1).double().norm(dim=1, keepdim=True) * w.double().norm(dim=1).unsqueeze(0) + 1e-30
+    assert float(((got.double() - ref).abs() / scale).max()) < 2e-6
+    assert torch.equal(amax, torch.stack([a.abs().max() for a in segs]))
+    ref32 = ops.gemm_tf32x3_cat(segs, w, bias)
+    assert float(((got - ref32).double().abs() / scale).max()) < 4e-6
+    assert torch.equal(got, ops.gemm_f16x2_cat(segs, w, bias))
