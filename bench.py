@@ -218,14 +218,27 @@ def kernel_roofline(cfg, peaks, peak_kind, forward_ms=None):
                                                             pipe_util=3 * flops / gemm_ms / 1e9 / peak_tf32)
         # input gradient of a block's three projections: one 3xTF32 GEMM over [dY0 | dY1 | dY2] (K = 3 HC)
         Wcat = torch.cat([W, W, W], dim=1)
-        dx_ms = timed_batches(lambda: ops.gemm_tf32x3_cat([XL, XL, XL], Wcat))
-        res["gemm_tf32x3_cat (dX over 3 dY)"] = dict(bound="tensor", ms=dx_ms, work=3 * flops, calls=n_blocks3, hbm_bytes=4 * E * HC * 4,
-                                                     pipe_util=9 * flops / dx_ms / 1e9 / peak_tf32)
+        if ops.DX_KIND == "f16x2" and ops.gemm_f16x2_cat_supported(E, HC, 3, HC):
+            # fp16 path: half the MMA time of 3xTF32, which leaves the kernel between the two roofs; credited as HBM-bound
+            # (read the three dY once + write dX once)
+            dx_ms = timed_batches(lambda: ops.gemm_f16x2_cat([XL, XL, XL], Wcat))
+            res["gemm_f16x2_cat (dX over 3 dY)"] = dict(bound="hbm", ms=dx_ms, work=4 * E * HC * 4, calls=n_blocks3,
+                                                        pipe_util=9 * flops / dx_ms / 1e9 / (2.0 * peak_tf32))
+        else:
+            dx_ms = timed_batches(lambda: ops.gemm_tf32x3_cat([XL, XL, XL], Wcat))
+            res["gemm_tf32x3_cat (dX over 3 dY)"] = dict(bound="tensor", ms=dx_ms, work=3 * flops, calls=n_blocks3, hbm_bytes=4 * E * HC * 4,
+                                                         pipe_util=9 * flops / dx_ms / 1e9 / peak_tf32)
         if f16 and ops.WGRAD_KIND == "f16x2" and ops.wgrad_f16x2_supported(E, HC, HC, HC, HC):
             amax = XL.abs().max().reshape(1)
             wg_ms = timed_batches(lambda: ops.wgrad_f16x2(XL, XL, amax, amax))
-            res["wgrad_f16x2 (dW)"] = dict(bound="hbm", ms=wg_ms, work=io_bytes, calls=n_gemm,
-                                           pipe_util=3 * flops / wg_ms / 1e9 / (2.0 * peak_tf32))
+            res["wgrad_f16x2 (dW, single)"] = dict(bound="hbm", ms=wg_ms, work=io_bytes, calls=2,
+                                                   pipe_util=3 * flops / wg_ms / 1e9 / (2.0 * peak_tf32))
+            if ops.WGRAD_MULTI:
+                # the three weight gradients of a block in one launch: algorithmic bytes = three dY + x ONCE
+                amax3 = amax.repeat(3)
+                wg3_ms = timed_batches(lambda: ops.wgrad_f16x2_multi([XL, XL, XL], XL, amax3, amax))
+                res["wgrad_f16x2_multi (3 dW of a block)"] = dict(bound="hbm", ms=wg3_ms, work=4 * E * HC * 4, calls=n_blocks3,
+                                                                  pipe_util=9 * flops / wg3_ms / 1e9 / (2.0 * peak_tf32))
         else:
             wg_ms = timed_batches(lambda: ops.wgrad_tf32x3(XL, XL))
             res["wgrad_tf32x3 (dW)"] = dict(bound="tensor", ms=wg_ms, work=flops, calls=n_gemm, hbm_bytes=io_bytes,
