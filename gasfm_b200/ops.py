@@ -485,7 +485,9 @@ def gemm_tf32x3_cat(a_list, b, bias=None, want_amax=False):
     return (c, amax) if want_amax else c
 
 
-DX_KIND = os.environ.get("GASFM_DX", "f16x2")      # concatenated input gradient: scaled 2 x FP16 (default) or "tf32x3"
+# concatenated input gradient: "tf32x3" (default) or "f16x2" -- the fp16 variant halves the MMA time but its two-pass operand
+# producer does not keep the tensor pipe fed yet (0.89 vs 0.84 ms at cfg2, profiles/r02_fusion_ab.md)
+DX_KIND = os.environ.get("GASFM_DX", "tf32x3")
 
 
 def gemm_f16x2_cat_supported(M, N, n_seg, seg_k):
