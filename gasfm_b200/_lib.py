@@ -52,6 +52,11 @@ SIGNATURES = {
     "gasfm_linear_f16x2": (_I, [_P, _L, _P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _I, _P, _P]),
     "gasfm_linear_f16x2_cat_supported": (_I, [_L, _I, _I, _I, _L]),
     "gasfm_linear_f16x2_cat": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _L, _L, _I, _P, _P]),
+    "gasfm_linear_f16x2_cat_rowmax": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _L, _L, _I, _P, _P]),
+    "gasfm_gat_edge_bwd_rowmax_supported": (_I, [_I, _I]),
+    "gasfm_gat_edge_bwd_rowmax": (_I, [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _F,
+                                       _P, _L, _P, _P, _P, _P, _P]),
+    "gasfm_x0_bwd_rowmax": (_I, [_P, _L, _I, _P, _P, _I, _F, _P, _P, _P, _P, _P]),
     "gasfm_linear_f16x2_ln": (_I, [_P, _L, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _P, _P]),
     "gasfm_wgrad_f16x2_supported": (_I, [_L, _I, _I, _L, _L]),
     "gasfm_wgrad_f16x2_ws_bytes": (_SZ, [_I, _I]),

@@ -411,6 +411,7 @@ struct GatBwdArgs {
   int chunk; const int32_t* chunk_ptr; const int32_t* chunk_seg; int max_chunks;
   float slope;
   float* dXL; int64_t lddxl; float* dXR; float* ws_datt; float* ws_dxr;
+  float* dxl_rowmax;   // optional [E]: max |dXL[e, :]| per edge row (the row scale of the fp16 input-gradient GEMM that reads dXL next)
 };
 
 constexpr int kBwdThreads = 256;
@@ -484,6 +485,7 @@ __device__ __forceinline__ void bwd_rows(const GatBwdArgs& p, int begin, int end
         alpha[s] = valid ? __expf(sc[s] - sg.M[s]) * sg.invL[s] : 0.f;
         ds[s] = alpha[s] * (da[s] - sg.D[s]);
       }
+      float rmax = 0.f;
 #pragma unroll
       for (int v = 0; v < L::NV; ++v) {
         float4 g;
@@ -497,6 +499,12 @@ __device__ __forceinline__ void bwd_rows(const GatBwdArgs& p, int begin, int end
           comp(datt[v], k) = fmaf(ds[s], leaky(z, p.slope), comp(datt[v], k));
         }
         if (valid) store_dxl4<BF>(p.dXL, eid[u], p.lddxl, 4 * lir + 4 * L::LPR * v, g);
+        rmax = fmaxf(rmax, fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fmaxf(fabsf(g.z), fabsf(g.w))));
+      }
+      if (p.dxl_rowmax != nullptr) {
+#pragma unroll
+        for (int off = L::LPR / 2; off > 0; off >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(mask, rmax, off));
+        if (lir == 0 && valid) p.dxl_rowmax[eid[u]] = rmax;
       }
     }
   }
@@ -954,7 +962,7 @@ extern "C" size_t gasfm_gat_bwd_ws_bytes(int64_t n_obs, int n_seg, int max_chunk
   return (blocks * HC + (size_t)max_chunks * HC) * sizeof(float);
 }
 
-static int gat_edge_bwd_impl(bool bf16, const float* XL, int64_t ldxl, const float* XR, int64_t ldxr,
+static int gat_edge_bwd_impl(bool bf16, float* dxl_rowmax, const float* XL, int64_t ldxl, const float* XR, int64_t ldxr,
                                   const float* att, const float* out_nobias, const float* seg_max,
                                   const float* seg_sum, const float* dOut, const int32_t* seg_ptr,
                                   const int32_t* perm, int n_seg, int chunk, const int32_t* chunk_ptr,
@@ -970,7 +978,7 @@ static int gat_edge_bwd_impl(bool bf16, const float* XL, int64_t ldxl, const flo
     return check_launch("gat_edge_bwd(empty)");
   }
   GatBwdArgs a{XL, ldxl, XR, ldxr, att, out_nobias, seg_max, seg_sum, dOut, seg_ptr, perm, n_seg,
-               chunk, chunk_ptr, chunk_seg, max_chunks, slope, dXL, lddxl, dXR, (float*)ws, nullptr};
+               chunk, chunk_ptr, chunk_seg, max_chunks, slope, dXL, lddxl, dXR, (float*)ws, nullptr, dxl_rowmax};
   int blocks = 0, rc;
   if (has_fast_path(heads, head_dim)) {
     GASFM_REQUIRE(ldxl % 4 == 0 && ldxr % 4 == 0 && lddxl % 4 == 0, "gat_edge_bwd: row strides must be multiples of 4 floats");
@@ -1011,7 +1019,21 @@ extern "C" int gasfm_gat_edge_bwd(const float* XL, int64_t ldxl, const float* XR
                                   const int32_t* chunk_seg, int max_chunks, int heads, int head_dim,
                                   float slope, float* dXL, int64_t lddxl, float* dXR, float* datt,
                                   void* ws, void* stream) {
-  return gat_edge_bwd_impl(false, XL, ldxl, XR, ldxr, att, out_nobias, seg_max, seg_sum, dOut, seg_ptr, perm, n_seg, chunk,
+  return gat_edge_bwd_impl(false, nullptr, XL, ldxl, XR, ldxr, att, out_nobias, seg_max, seg_sum, dOut, seg_ptr, perm, n_seg, chunk,
+                           chunk_ptr, chunk_seg, max_chunks, heads, head_dim, slope, dXL, lddxl, dXR, datt, ws, stream);
+}
+
+extern "C" int gasfm_gat_edge_bwd_rowmax_supported(int heads, int head_dim) { return has_fast_path(heads, head_dim) ? 1 : 0; }
+
+extern "C" int gasfm_gat_edge_bwd_rowmax(const float* XL, int64_t ldxl, const float* XR, int64_t ldxr,
+                                         const float* att, const float* out_nobias, const float* seg_max,
+                                         const float* seg_sum, const float* dOut, const int32_t* seg_ptr,
+                                         const int32_t* perm, int n_seg, int chunk, const int32_t* chunk_ptr,
+                                         const int32_t* chunk_seg, int max_chunks, int heads, int head_dim,
+                                         float slope, float* dXL, int64_t lddxl, float* dXR, float* datt,
+                                         float* dxl_rowmax, void* ws, void* stream) {
+  GASFM_REQUIRE(dxl_rowmax != nullptr && has_fast_path(heads, head_dim), "gat_edge_bwd_rowmax: needs the vectorised head shapes (4 x 2^k)");
+  return gat_edge_bwd_impl(false, dxl_rowmax, XL, ldxl, XR, ldxr, att, out_nobias, seg_max, seg_sum, dOut, seg_ptr, perm, n_seg, chunk,
                            chunk_ptr, chunk_seg, max_chunks, heads, head_dim, slope, dXL, lddxl, dXR, datt, ws, stream);
 }
 
@@ -1022,7 +1044,7 @@ extern "C" int gasfm_gat_edge_bwd_bf16(const void* XL_bf16, int64_t ldxl, const 
                                        const int32_t* chunk_seg, int max_chunks, int heads, int head_dim,
                                        float slope, void* dXL_bf16, int64_t lddxl, float* dXR, float* datt,
                                        void* ws, void* stream) {
-  return gat_edge_bwd_impl(true, (const float*)XL_bf16, ldxl, XR, ldxr, att, out_nobias, seg_max, seg_sum, dOut, seg_ptr, perm,
+  return gat_edge_bwd_impl(true, nullptr, (const float*)XL_bf16, ldxl, XR, ldxr, att, out_nobias, seg_max, seg_sum, dOut, seg_ptr, perm,
                            n_seg, chunk, chunk_ptr, chunk_seg, max_chunks, heads, head_dim, slope, (float*)dXL_bf16, lddxl, dXR,
                            datt, ws, stream);
 }

@@ -54,6 +54,9 @@ struct GemmF16Args {
   // row across all segments), then scale + split K block by K block; the second pass and -- through an L2 prefetch issued one
   // tile ahead -- most of the first are served by L2.  seg_amax[n_seg] receives max |A_i| (for the fp16 weight gradient).
   const float* A_seg[4]; int64_t lda_seg[4]; int n_seg; float* seg_amax;
+  // ... unless the producers of the A_i left their row maxima behind (rowmax_seg[i][M], e.g. gasfm_gat_edge_bwd_rowmax,
+  // gasfm_x0_bwd_rowmax): then ONE pass suffices, with four K blocks of loads in flight ahead of the conversion
+  const float* rowmax_seg[4];
   long long* trace;                           // optional [3 roles][kTraceTiles][16] SM-clock timestamps of CTA 0 (profiling)
 };
 
@@ -184,23 +187,29 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
     const int q = t & 15, rg = t >> 4;
     int stage = 0; uint32_t phase = 0;
     // scale, split into fp16 hi + lo and store this thread's 8 row pieces of one 64-wide K block (128B-swizzled, K-major)
+    // (everything that does not change from K block to K block is computed once: shared-memory offsets of this thread's 8
+    //  row pieces, the 32-bit element offsets of its rows -- the generic loop spent 70 % of its instructions on that)
+    uint32_t soff[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = rg + 16 * i;
+      soff[i] = (uint32_t)(row * 128 + ((((q >> 1) ^ (row & 7))) << 4) + ((q & 1) << 3));
+    }
+    const uint32_t smem_base = smem_u32(smem);
     auto convert_block = [&](const float4 (&v)[8], const float (&scale)[8]) {
-      uint8_t* a_hi = smem + (size_t)stage * stage_bytes;
-      uint8_t* a_lo = a_hi + kFATileBytes;
+      const uint32_t sb = smem_base + (uint32_t)stage * (uint32_t)stage_bytes;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int row = rg + 16 * i;
-        const int off = row * 128 + ((((q >> 1) ^ (row & 7))) << 4) + ((q & 1) << 3);
         const float s = scale[i];
         const float x0 = v[i].x * s, x1 = v[i].y * s, x2 = v[i].z * s, x3 = v[i].w * s;
         const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
         const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
-        uint2 hv, lv;
-        hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-        lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-        *reinterpret_cast<uint2*>(a_hi + off) = hv;
-        *reinterpret_cast<uint2*>(a_lo + off) = lv;
+        const uint32_t addr = sb + soff[i];
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
+                     "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
+        asm volatile("st.shared.v2.b32 [%0+%3], {%1, %2};" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&l01)),
+                     "r"(*reinterpret_cast<const uint32_t*>(&l23)), "n"(kFATileBytes) : "memory");
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
       mbar_arrive(&split_bar[stage]);
@@ -211,8 +220,8 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
       // global K block kbg = seg * KB + kb of tile it: this thread's float4 of rows rg + 16 i
       auto load_kbg = [&](int64_t it, int kbg, float4 (&v)[8]) {
         const int seg = kbg / KB, kcol = (kbg % KB) * kFBlockK + q * 4;
-        const float* base = p.A_seg[seg & 3];
-        const int64_t ld = p.lda_seg[seg & 3];
+        const float* base = seg == 0 ? p.A_seg[0] : (seg == 1 ? p.A_seg[1] : (seg == 2 ? p.A_seg[2] : p.A_seg[3]));
+        const int64_t ld = seg == 0 ? p.lda_seg[0] : (seg == 1 ? p.lda_seg[1] : (seg == 2 ? p.lda_seg[2] : p.lda_seg[3]));
         const int64_t tile = (cluster_id + it * num_clusters) * kFCluster + cta_rank;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -224,6 +233,50 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
       float seg_seen[4] = {0.f, 0.f, 0.f, 0.f};
       float4 v0[8], v1[8], v2[8], v3[8];
       const int lines_per_row = KB * kFBlockK * 4 / 128;          // 128-byte lines of one segment row
+      if (p.rowmax_seg[0] != nullptr) {
+        // ---- single pass: row scales from the row maxima the upstream kernels emitted; K blocks stream through four
+        //      register buffers, three blocks of loads in flight while one is converted (the stream runs across tiles) ----
+        auto load_stream = [&](int64_t it, int kbg, float4 (&v)[8]) {         // kbg may run past the tile: next tile's blocks
+          if (kbg >= nkb) { kbg -= nkb; ++it; }
+          load_kbg(it, kbg, v);
+        };
+        load_stream(0, 0, v0); load_stream(0, 1, v1); load_stream(0, 2, v2);
+        for (int64_t it = 0; it < my_steps; ++it) {
+          const int64_t tile = (cluster_id + it * num_clusters) * kFCluster + cta_rank;
+          float scale[8];
+          float* descale_slot = row_descale[it & (kFScaleSlots - 1)];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int64_t row = tile * kFBlockM + rg + 16 * i;
+            float m = 0.f;
+#pragma unroll
+            for (int seg = 0; seg < 4; ++seg) {
+              if (seg < p.n_seg && row < p.M) {
+                const float r = __ldg(p.rowmax_seg[seg] + row);
+                m = fmaxf(m, r);
+                seg_seen[seg] = fmaxf(seg_seen[seg], r);
+              }
+            }
+            float descale;
+            row_scale_from_amax(m, scale[i], descale);
+            if (q == 0) descale_slot[rg + 16 * i] = descale;
+          }
+          for (int kbg = 0; kbg < nkb; kbg += 4) {               // nkb % 4 == 0 (launcher)
+            load_stream(it, kbg + 3, v3);
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            convert_block(v0, scale);
+            load_stream(it, kbg + 4, v0);
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            convert_block(v1, scale);
+            load_stream(it, kbg + 5, v1);
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            convert_block(v2, scale);
+            load_stream(it, kbg + 6, v2);
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            convert_block(v3, scale);
+          }
+        }
+      } else
       for (int64_t it = 0; it < my_steps; ++it) {
         // L2 prefetch of the NEXT tile (its first pass then finds the lines in L2 instead of HBM)
         // (off by default: a whole prefetched tile doubles the L2 footprint and evicts the current one before its second pass --
@@ -299,13 +352,21 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
       }
     } else {
     float4 buf[KB][8];
+    const uint32_t toff = (uint32_t)(rg * p.lda + q * 4), tstep = (uint32_t)(16 * p.lda);   // elements (lda < 2^24: launcher)
     auto load_block = [&](int64_t it, int kb, float4 (&v)[8]) {
       const int64_t tile = (cluster_id + it * num_clusters) * kFCluster + cta_rank;
       const int kcol = kb * kFBlockK + q * 4;
+      if (it < my_steps && (tile + 1) * kFBlockM <= p.M && (kb + 1) * kFBlockK <= p.K) {
+        // whole block in range (all but the last tile / a ragged K): no per-row predicates, 32-bit offsets from a uniform base
+        const float* base = p.A + tile * kFBlockM * p.lda + kb * kFBlockK;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = ld_stream4(base + (toff + (uint32_t)i * tstep));
+        return;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int64_t row = tile * kFBlockM + rg + 16 * i;
-        v[i] = (it < my_steps && row < p.M && kcol < p.K && !(p.debug & 8)) ? ld_stream4(p.A + row * p.lda + kcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = (it < my_steps && row < p.M && kcol < p.K) ? ld_stream4(p.A + row * p.lda + kcol) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
 #pragma unroll
@@ -375,29 +436,8 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (t == 0) GASFM_TRACE(0, it, 1 + kb);
-        uint8_t* a_hi = smem + (size_t)stage * stage_bytes;
-        uint8_t* a_lo = a_hi + kFATileBytes;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (p.debug & 16) break;
-          const int row = rg + 16 * i;
-          // 16-byte chunk q/2 of the row, swizzled (chunk ^= row % 8); this thread's 4 halves are its lower / upper 8 bytes
-          const int off = row * 128 + ((((q >> 1) ^ (row & 7))) << 4) + ((q & 1) << 3);
-          const float s = scale[i];
-          const float x0 = buf[kb][i].x * s, x1 = buf[kb][i].y * s, x2 = buf[kb][i].z * s, x3 = buf[kb][i].w * s;
-          const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
-          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-          const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
-          uint2 hv, lv;
-          hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-          lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-          *reinterpret_cast<uint2*>(a_hi + off) = hv;
-          *reinterpret_cast<uint2*>(a_lo + off) = lv;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
-        mbar_arrive(&split_bar[stage]);
+        convert_block(buf[kb], scale);
         if (t == 0) GASFM_TRACE(0, it, 5 + kb);
-        if (++stage == kFStages) { stage = 0; phase ^= 1; }
         if (last_group) load_block(it + 1, kb, buf[kb]);   // refill the freed registers with the next tile's K block
       }
       }
@@ -526,7 +566,7 @@ extern "C" int gasfm_split_f16(const float* w, int n_rows, int k, void* hi, void
 extern "C" int gasfm_linear_f16x2_supported(int64_t M, int N, int K, int64_t lda, int64_t ldc) {
   // K < 64 would leave half of every 64-wide K block (and of the producer lanes) empty: the 3xTF32 kernel with its
   // 32-wide blocks is the better fit there
-  return (M > 0 && N >= 16 && N <= 256 && N % 16 == 0 && K >= 64 && K <= 256 && K % 8 == 0 && lda % 4 == 0 && ldc % 4 == 0) ? 1 : 0;
+  return (M > 0 && N >= 16 && N <= 256 && N % 16 == 0 && K >= 64 && K <= 256 && K % 8 == 0 && lda % 4 == 0 && lda < (1 << 24) && ldc % 4 == 0) ? 1 : 0;
 }
 
 static int linear_f16x2_impl(const float* A, int64_t lda, const void* B_hi, const void* B_lo, const float* b_descale,
@@ -590,9 +630,27 @@ extern "C" int gasfm_linear_f16x2_cat_supported(int64_t M, int N, int n_seg, int
   return (M > 0 && N >= 16 && N <= 256 && N % 16 == 0 && n_seg >= 1 && n_seg <= 4 && (seg_k == 128 || seg_k == 256) && ldc % 4 == 0) ? 1 : 0;
 }
 
+static int linear_f16x2_cat_impl(const float* const* A, const int64_t* lda, const float* const* rowmax, int n_seg, int seg_k,
+                                const void* B_hi, const void* B_lo, const float* b_descale, const float* bias, float* C,
+                                int64_t ldc, int64_t M, int N, float* a_amax, void* stream);
+
 extern "C" int gasfm_linear_f16x2_cat(const float* const* A, const int64_t* lda, int n_seg, int seg_k, const void* B_hi,
                                       const void* B_lo, const float* b_descale, const float* bias, float* C, int64_t ldc,
                                       int64_t M, int N, float* a_amax, void* stream) {
+  return linear_f16x2_cat_impl(A, lda, nullptr, n_seg, seg_k, B_hi, B_lo, b_descale, bias, C, ldc, M, N, a_amax, stream);
+}
+
+extern "C" int gasfm_linear_f16x2_cat_rowmax(const float* const* A, const int64_t* lda, const float* const* rowmax, int n_seg,
+                                             int seg_k, const void* B_hi, const void* B_lo, const float* b_descale,
+                                             const float* bias, float* C, int64_t ldc, int64_t M, int N, float* a_amax,
+                                             void* stream) {
+  GASFM_REQUIRE(rowmax != nullptr && (n_seg * (seg_k / 64)) % 4 == 0, "linear_f16x2_cat_rowmax: needs row maxima and a multiple of 4 K blocks");
+  return linear_f16x2_cat_impl(A, lda, rowmax, n_seg, seg_k, B_hi, B_lo, b_descale, bias, C, ldc, M, N, a_amax, stream);
+}
+
+static int linear_f16x2_cat_impl(const float* const* A, const int64_t* lda, const float* const* rowmax, int n_seg, int seg_k,
+                                const void* B_hi, const void* B_lo, const float* b_descale, const float* bias, float* C,
+                                int64_t ldc, int64_t M, int N, float* a_amax, void* stream) {
   GASFM_REQUIRE(A && lda && gasfm_linear_f16x2_cat_supported(M, N, n_seg, seg_k, ldc), "linear_f16x2_cat: unsupported shape M=%lld N=%d "
                 "n_seg=%d seg_k=%d", (long long)M, N, n_seg, seg_k);
   GASFM_REQUIRE(b_descale != nullptr && ((uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)C) % 16 == 0, "linear_f16x2_cat: pointers must be 16-byte aligned");
@@ -613,6 +671,10 @@ extern "C" int gasfm_linear_f16x2_cat(const float* const* A, const int64_t* lda,
   for (int i = 0; i < n_seg; ++i) {
     GASFM_REQUIRE(A[i] != nullptr && (uintptr_t)A[i] % 16 == 0 && lda[i] % 4 == 0, "linear_f16x2_cat: segment %d misaligned", i);
     args.A_seg[i] = A[i]; args.lda_seg[i] = lda[i];
+    if (rowmax != nullptr) {
+      GASFM_REQUIRE(rowmax[i] != nullptr, "linear_f16x2_cat_rowmax: row maxima of segment %d missing", i);
+      args.rowmax_seg[i] = rowmax[i];
+    }
   }
 #define LAUNCH_CAT(KB)                                                                                                          \
   do {                                                                                                                          \

@@ -109,7 +109,8 @@ constexpr int kX0Threads = 256;
 template <int LPR, int NV, int D0>
 __global__ void __launch_bounds__(kX0Threads) x0_bwd_kernel(const float* __restrict__ dOut, int64_t E, int width,
                                                             const float* __restrict__ x0, const float* __restrict__ W0,
-                                                            float scale, float* __restrict__ dx0, float* __restrict__ ws) {
+                                                            float scale, float* __restrict__ dx0, float* __restrict__ ws,
+                                                            float* __restrict__ rowmax /* optional [E]: max |dOut[row, :]| */) {
   constexpr int RPW = 32 / LPR;
   constexpr int NW = kX0Threads / 32;
   constexpr int U = 2;                                        // rows in flight per lane group
@@ -165,6 +166,15 @@ __global__ void __launch_bounds__(kX0Threads) x0_bwd_kernel(const float* __restr
         for (int off = LPR / 2; off > 0; off >>= 1) s[q] += __shfl_xor_sync(mask, s[q], off);
       }
       const int64_t row = row0 + u * stride;
+      if (rowmax != nullptr) {                                  // row maximum of |dOut|: the fp16 input-gradient GEMM's row scale
+        float m = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+          m = fmaxf(m, fmaxf(fmaxf(fabsf(g[u][v].x), fabsf(g[u][v].y)), fmaxf(fabsf(g[u][v].z), fabsf(g[u][v].w))));
+#pragma unroll
+        for (int off = LPR / 2; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(mask, m, off));
+        if (lir == 0 && row < E) rowmax[row] = m;
+      }
       if (lir == 0 && row < E) {
 #pragma unroll
         for (int q = 0; q < D0; ++q) dx0[row * D0 + q] = scale * s[q];
@@ -246,8 +256,21 @@ extern "C" int gasfm_wgrad_small(const float* dY, int64_t lddy, const float* X, 
 
 extern "C" size_t gasfm_x0_bwd_ws_bytes(int64_t E, int width) { return (size_t)x0_blocks(E) * width * 4 * sizeof(float); }
 
+static int x0_bwd_impl(const float* dOut, int64_t E, int width, const float* x0, const float* W0, int d0, float scale,
+                       float* dx0, float* dW0, void* ws, float* rowmax, void* stream);
+
 extern "C" int gasfm_x0_bwd(const float* dOut, int64_t E, int width, const float* x0, const float* W0, int d0, float scale,
                             float* dx0, float* dW0, void* ws, void* stream) {
+  return x0_bwd_impl(dOut, E, width, x0, W0, d0, scale, dx0, dW0, ws, nullptr, stream);
+}
+
+extern "C" int gasfm_x0_bwd_rowmax(const float* dOut, int64_t E, int width, const float* x0, const float* W0, int d0, float scale,
+                                   float* dx0, float* dW0, void* ws, float* rowmax, void* stream) {
+  return x0_bwd_impl(dOut, E, width, x0, W0, d0, scale, dx0, dW0, ws, rowmax, stream);
+}
+
+static int x0_bwd_impl(const float* dOut, int64_t E, int width, const float* x0, const float* W0, int d0, float scale,
+                       float* dx0, float* dW0, void* ws, float* rowmax, void* stream) {
   GASFM_REQUIRE(width > 0 && width % 4 == 0 && width <= 1024, "x0_bwd: width %d must be a multiple of 4 and <= 1024", width);
   GASFM_REQUIRE(d0 >= 1 && d0 <= 4, "x0_bwd: d0 = %d not in 1..4", d0);
   GASFM_REQUIRE(ws && (uintptr_t)dOut % 16 == 0, "x0_bwd: bad pointers");
@@ -263,7 +286,7 @@ extern "C" int gasfm_x0_bwd(const float* dOut, int64_t E, int width, const float
   do {                                                                                                              \
     if (smem > 48 * 1024)                                                                                           \
       cudaFuncSetAttribute(x0_bwd_kernel<LPR, NV, D0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-    x0_bwd_kernel<LPR, NV, D0><<<blocks, kX0Threads, smem, st>>>(dOut, E, width, x0, W0, scale, dx0, (float*)ws);   \
+    x0_bwd_kernel<LPR, NV, D0><<<blocks, kX0Threads, smem, st>>>(dOut, E, width, x0, W0, scale, dx0, (float*)ws, rowmax);   \
   } while (0)
 #define CALL_X0(VEC, LPR, NV)                          \
   do {                                                 \

@@ -287,14 +287,14 @@ class CudaEdgeBackend:
         return ops.gat_edge_partial(XL, XR, att, plan, heads)
 
     @staticmethod
-    def backward(XL, XR, att, out_nobias, M, L, d_out, plan, heads):
+    def backward(XL, XR, att, out_nobias, M, L, d_out, plan, heads, want_rowmax=False):
         from . import ops
-        return ops.gat_edge_backward_raw(XL, XR, att, out_nobias, M, L, d_out, plan, heads)
+        return ops.gat_edge_backward_raw(XL, XR, att, out_nobias, M, L, d_out, plan, heads, want_rowmax=want_rowmax)
 
 
 class _ShardedGat(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, XL, XR, att, bias, plan, heads, exchange, backend, lazy_xl):
+    def forward(ctx, XL, XR, att, bias, plan, heads, exchange, backend, lazy_xl, rowmax_slot=None):
         acc, mx, sm = backend.partial(XL, XR, att, plan, heads)
         out, M, L = exchange.lse_merge(acc, mx, sm, heads, bias)
         if lazy_xl is None:
@@ -302,6 +302,7 @@ class _ShardedGat(torch.autograd.Function):
         else:
             ctx.save_for_backward(XR, att, bias, out, M, L)       # XL is recomputed in backward (ops.LayerRecompute)
         ctx.plan, ctx.heads, ctx.exchange, ctx.backend, ctx.lazy_xl = plan, heads, exchange, backend, lazy_xl
+        ctx.rowmax_slot = rowmax_slot
         return out
 
     @staticmethod
@@ -316,13 +317,17 @@ class _ShardedGat(torch.autograd.Function):
         d_out = d_out.contiguous()
         d_bias = None if bias is None else ops.col_sum(d_out)
         out_nobias = out if bias is None else out - bias
-        dXL, dXR, datt = ctx.backend.backward(XL, XR, att, out_nobias, M, L, d_out, ctx.plan, ctx.heads)
+        if ctx.rowmax_slot is not None:
+            dXL, dXR, datt, rowmax = ctx.backend.backward(XL, XR, att, out_nobias, M, L, d_out, ctx.plan, ctx.heads, want_rowmax=True)
+            ctx.rowmax_slot[0].note_rowmax(ctx.rowmax_slot[1], dXL, rowmax)
+        else:
+            dXL, dXR, datt = ctx.backend.backward(XL, XR, att, out_nobias, M, L, d_out, ctx.plan, ctx.heads)
         dXR = ctx.exchange.allreduce_sum(dXR)           # the query is replicated, its edges are spread over the ranks
-        return dXL, dXR, datt.view(att.shape), d_bias, None, None, None, None, None
+        return dXL, dXR, datt.view(att.shape), d_bias, None, None, None, None, None, None
 
 
-def sharded_gat(XL, XR, att, bias, plan, heads, exchange, backend=CudaEdgeBackend, lazy_xl=None):
-    return _ShardedGat.apply(XL, XR, att, bias, plan, heads, exchange, backend, lazy_xl)
+def sharded_gat(XL, XR, att, bias, plan, heads, exchange, backend=CudaEdgeBackend, lazy_xl=None, rowmax_slot=None):
+    return _ShardedGat.apply(XL, XR, att, bias, plan, heads, exchange, backend, lazy_xl, rowmax_slot)
 
 
 class _ReplicatedToLocal(torch.autograd.Function):

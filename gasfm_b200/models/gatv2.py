@@ -60,19 +60,21 @@ class GATv2Conv(nn.Module):
 
     def aggregate(self, x_elements, x_agg, plan, projected_sources=None):
         """[T, H*C] attention-aggregate of the element rows over ``plan``'s segments.  ``projected_sources``:
-        lin_l(x_elements) when the caller already computed it, optionally as ``(tensor, lazy)`` where ``lazy()``
-        rebuilds the tensor in backward instead of keeping it (activation recompute, ops.EdgeBlockContext)."""
-        lazy = None
+        lin_l(x_elements) when the caller already computed it, optionally as ``(tensor, lazy, slot)`` where ``lazy()``
+        rebuilds the tensor in backward instead of keeping it (activation recompute) and ``slot`` is where the backward
+        kernel leaves the row maxima of dXL for the block's input-gradient GEMM (ops.EdgeBlockContext)."""
+        lazy = slot = None
         if isinstance(projected_sources, tuple):
-            projected_sources, lazy = projected_sources
+            projected_sources, lazy, slot = (tuple(projected_sources) + (None, None))[:3]
         xl = self.project_sources(x_elements) if projected_sources is None else projected_sources
         shard = getattr(plan, "shard", None)
         if shard is not None and shard.world > 1:
             # track-sharded scene: this rank holds only part of every segment -> merge across ranks
             from .. import dist as gdist
             return gdist.sharded_gat(xl, self.project_targets(x_agg), self.att, self.bias, plan, self.heads,
-                                     shard.exchange, lazy_xl=lazy)
-        return ops.gat_edge_attention(xl, self.project_targets(x_agg), self.att, self.bias, plan, self.heads, lazy_xl=lazy)
+                                     shard.exchange, lazy_xl=lazy, rowmax_slot=slot)
+        return ops.gat_edge_attention(xl, self.project_targets(x_agg), self.att, self.bias, plan, self.heads, lazy_xl=lazy,
+                                      rowmax_slot=slot)
 
     def forward(self, x, edge_index):
         """PyG call convention ``conv(x[N,d], edge_index[2,E]) -> [N, H*C]`` for arbitrary graphs

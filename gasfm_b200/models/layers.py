@@ -280,8 +280,11 @@ class GraphAttnSfMLayer(Module):
             rc = ops.EdgeBlockContext(ops.activation_recompute_enabled())
             xl_sp, xl_v, proj, raw_vals = ops.edge_block_project(raw.values, norm.weight, norm.bias, norm.eps, rc, projections)
             x, raw = raw.with_values(None, n_feat=d_main), raw.with_values(raw_vals)
-            xl_sp, xl_v = (xl_sp, rc.xl_getter(0)), (xl_v, rc.xl_getter(1))
+            # (tensor, rebuild-in-backward getter, slot where the attention backward leaves the row maxima of dXL)
+            xl_sp, xl_v = (xl_sp, rc.xl_getter(0), rc.slot(0)), (xl_v, rc.xl_getter(1), rc.slot(1))
+            update_slot = rc.slot(2)
         else:
+            update_slot = None
             if plain_residual and ops.ln_relu_width_supported(d_main):
                 # x_raw feeds LN+ReLU and the residual: one autograd node, so that the two gradients are summed
                 # inside the LN+ReLU backward kernel (ops.ln_relu_with_skip)
@@ -316,7 +319,7 @@ class GraphAttnSfMLayer(Module):
                     residual = relu_on_projection_features(None, _fused_norm=(residual, self.residual_skipconn_proj_norm_layer))
                 residual = self.skip_projection(residual)
         projection_features = pfu(scenepoint_features, view_features, global_features, feats, residual = residual,
-                                  projected = proj)
+                                  projected = proj, rowmax_slot = update_slot)
         return projection_features, scenepoint_features, view_features, global_features
 
 
@@ -651,7 +654,7 @@ class GraphAttnSfMProjectionFeatureUpdate(Module):
             self.mlp = get_linear_layers(n_hidden_layers_proj_update * [n_feat_proj_out] + [n_feat_proj_out],
                                          init_activation=False, final_activation=False, norm=False)
 
-    def forward(self, scenepoint_features, view_features, global_features, x, residual=None, projected=None):
+    def forward(self, scenepoint_features, view_features, global_features, x, residual=None, projected=None, rowmax_slot=None):
         """(lin_proj(x) + lin_sp(sp)[col] + lin_view(view)[row] + lin_global(g)) / 4 [-> relu -> mlp]
         (layers.py:911-956).  Extensions: ``residual`` = SparseMat added to the result inside the same
         kernel (the skip connection of GraphAttnSfMLayer, layers.py:254-261); ``projected`` = the already
@@ -676,7 +679,8 @@ class GraphAttnSfMProjectionFeatureUpdate(Module):
             proj = projected if projected is not None else ops.linear(x.values, 0.25 * w, 0.25 * b)
         has_mlp = self.n_hidden_layers_proj_update > 0
         fused_skip = None if (residual is None or has_mlp) else residual.values
-        new = ops.edge_update(proj, x0, w0, sp, view, glob, fused_skip, index_for(x), 1.0, 0.25)
+        new = ops.edge_update(proj, x0, w0, sp, view, glob, fused_skip, index_for(x), 1.0, 0.25,
+                              rowmax_slot=rowmax_slot if projected is not None else None)
         assert new.shape == (x.indices.shape[1], self.n_feat_proj_out)
         if has_mlp:
             new = self.mlp(F.relu(new))

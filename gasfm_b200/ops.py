@@ -37,7 +37,7 @@ def _rows(t):
 # ---------------------------------------------------------------------------------------------
 class _GatEdge(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, XL, XR, att, bias, plan, heads, lazy_xl=None):
+    def forward(ctx, XL, XR, att, bias, plan, heads, lazy_xl=None, rowmax_slot=None):
         _require_cuda(XL, XR, att, bias)
         XL, ldxl = _rows(XL)
         hc = XL.shape[1]
@@ -61,6 +61,7 @@ class _GatEdge(torch.autograd.Function):
         # lazy_xl: the projected sources are not kept for backward but rebuilt by the layer's EdgeBlockContext
         ctx.save_for_backward(XL if lazy_xl is None else None, XR, att_flat, bias, out, seg_max, seg_sum)
         ctx.plan, ctx.heads, ctx.bcast, ctx.att_shape, ctx.lazy_xl = plan, heads, bcast, att.shape, lazy_xl
+        ctx.rowmax_slot = rowmax_slot
         return out
 
     @staticmethod
@@ -74,29 +75,48 @@ class _GatEdge(torch.autograd.Function):
         dev = XL.device
         d_out = d_out.contiguous()
         out_nobias = out if bias is None else out - bias
-        covers_all = plan.perm is None or plan.n_edges == XL.shape[0]
-        dXL = (torch.empty if covers_all else torch.zeros)((XL.shape[0], hc), dtype=torch.float32, device=dev)
-        dXR = torch.empty((plan.n_seg, hc), dtype=torch.float32, device=dev)
-        datt = torch.empty(hc, dtype=torch.float32, device=dev)
-        ws = plan.workspace(_lib.size_query("gasfm_gat_bwd_ws_bytes", XL.shape[0], plan.n_seg, plan.max_chunks,
-                                            heads, head_dim), dev)
-        with _lib.device_guard(dev):
-            _lib.call("gasfm_gat_edge_bwd", _lib.ptr(XL), XL.stride(0) if XL.shape[0] > 1 else hc, _lib.ptr(XR),
-                      0 if ctx.bcast else hc, _lib.ptr(att_flat), _lib.ptr(out_nobias), _lib.ptr(seg_max),
-                      _lib.ptr(seg_sum), _lib.ptr(d_out), *plan.abi_args(), heads, head_dim, LEAKY_SLOPE,
-                      _lib.ptr(dXL), hc, _lib.ptr(dXR), _lib.ptr(datt), _lib.ptr(ws), _lib.stream_ptr())
+        dXL, dXR, datt, rowmax = _gat_backward_launch(XL, XR, 0 if ctx.bcast else hc, att_flat, out_nobias, seg_max, seg_sum, d_out,
+                                                      plan, heads, want_rowmax=ctx.rowmax_slot is not None)
+        if ctx.rowmax_slot is not None:
+            ctx.rowmax_slot[0].note_rowmax(ctx.rowmax_slot[1], dXL, rowmax)
         if ctx.bcast:
             dXR = dXR.sum(dim=0, keepdim=True)
         d_bias = None if bias is None else col_sum(d_out)
-        return dXL, dXR, datt.view(ctx.att_shape), d_bias, None, None, None
+        return dXL, dXR, datt.view(ctx.att_shape), d_bias, None, None, None, None
 
 
-def gat_edge_attention(XL, XR, att, bias, plan: SegmentPlan, heads: int, lazy_xl=None):
+def _gat_backward_launch(XL, XR, ldxr, att_flat, out_nobias, seg_max, seg_sum, d_out, plan, heads, want_rowmax=False):
+    """-> (dXL, dXR, datt, rowmax | None).  ``want_rowmax``: also emit max |dXL[e, :]| per edge row (fp32, vectorised head shapes):
+    the row scale of the fp16 input-gradient GEMM that reads dXL next."""
+    hc = XL.shape[1]
+    head_dim = hc // heads
+    dev = XL.device
+    bf16 = XL.dtype == torch.bfloat16
+    covers_all = plan.perm is None or plan.n_edges == XL.shape[0]
+    dXL = (torch.empty if covers_all else torch.zeros)((XL.shape[0], hc), dtype=XL.dtype, device=dev)
+    dXR = torch.empty((plan.n_seg, hc), dtype=torch.float32, device=dev)
+    datt = torch.empty(hc, dtype=torch.float32, device=dev)
+    ws = plan.workspace(_lib.size_query("gasfm_gat_bwd_ws_bytes", XL.shape[0], plan.n_seg, plan.max_chunks, heads, head_dim), dev)
+    rowmax = None
+    if want_rowmax and not bf16 and _lib.load().gasfm_gat_edge_bwd_rowmax_supported(heads, head_dim):
+        rowmax = (torch.empty if covers_all else torch.zeros)(XL.shape[0], dtype=torch.float32, device=dev)
+    ldxl = XL.stride(0) if XL.shape[0] > 1 else hc
+    args = (_lib.ptr(XL), ldxl, _lib.ptr(XR), ldxr, _lib.ptr(att_flat), _lib.ptr(out_nobias), _lib.ptr(seg_max), _lib.ptr(seg_sum),
+            _lib.ptr(d_out), *plan.abi_args(), heads, head_dim, LEAKY_SLOPE, _lib.ptr(dXL), hc, _lib.ptr(dXR), _lib.ptr(datt))
+    with _lib.device_guard(dev):
+        if rowmax is not None:
+            _lib.call("gasfm_gat_edge_bwd_rowmax", *args, _lib.ptr(rowmax), _lib.ptr(ws), _lib.stream_ptr())
+        else:
+            _lib.call("gasfm_gat_edge_bwd_bf16" if bf16 else "gasfm_gat_edge_bwd", *args, _lib.ptr(ws), _lib.stream_ptr())
+    return dXL, dXR, datt, rowmax
+
+
+def gat_edge_attention(XL, XR, att, bias, plan: SegmentPlan, heads: int, lazy_xl=None, rowmax_slot=None):
     """out[T,HC] = GATv2 softmax-aggregate of XL rows over ``plan``'s segments (+ bias).
 
     XL [E,HC] projected sources (rows may be a strided slice), XR [T,HC] projected targets, or
     [1,HC] to broadcast one query row to every target (stateless first block)."""
-    return _GatEdge.apply(XL, XR, att, bias, plan, heads, lazy_xl)
+    return _GatEdge.apply(XL, XR, att, bias, plan, heads, lazy_xl, rowmax_slot)
 
 
 def gat_edge_partial(XL, XR, att, plan: SegmentPlan, heads: int):
@@ -125,30 +145,18 @@ def gat_edge_partial(XL, XR, att, plan: SegmentPlan, heads: int):
     return out, seg_max, seg_sum
 
 
-def gat_edge_backward_raw(XL, XR, att, out_nobias, seg_max, seg_sum, d_out, plan, heads):
-    """Backward kernel with explicitly supplied (global) softmax statistics; returns
-    (dXL, dXR, datt).  The multi-GPU path calls this with the merged statistics.  bf16 ``XL`` -> bf16 ``dXL``."""
-    XL, ldxl = _rows(XL)
+def gat_edge_backward_raw(XL, XR, att, out_nobias, seg_max, seg_sum, d_out, plan, heads, want_rowmax=False):
+    """Backward kernel with explicitly supplied (global) softmax statistics; returns (dXL, dXR, datt) -- plus the row maxima of
+    dXL with ``want_rowmax``.  The multi-GPU path calls this with the merged statistics.  bf16 ``XL`` -> bf16 ``dXL``."""
+    XL, _ = _rows(XL)
     hc = XL.shape[1]
-    head_dim = hc // heads
-    dev = XL.device
-    bf16 = XL.dtype == torch.bfloat16
     bcast = XR.shape[0] == 1 and plan.n_seg != 1
-    covers_all = plan.perm is None or plan.n_edges == XL.shape[0]
-    dXL = (torch.empty if covers_all else torch.zeros)((XL.shape[0], hc), dtype=XL.dtype, device=dev)
-    dXR = torch.empty((plan.n_seg, hc), dtype=torch.float32, device=dev)
-    datt = torch.empty(hc, dtype=torch.float32, device=dev)
-    ws = plan.workspace(_lib.size_query("gasfm_gat_bwd_ws_bytes", XL.shape[0], plan.n_seg, plan.max_chunks,
-                                        heads, head_dim), dev)
-    with _lib.device_guard(dev):
-        _lib.call("gasfm_gat_edge_bwd_bf16" if bf16 else "gasfm_gat_edge_bwd", _lib.ptr(XL), ldxl, _lib.ptr(XR.contiguous()), 0 if bcast else hc,
-                  _lib.ptr(att.reshape(-1).contiguous()), _lib.ptr(out_nobias.contiguous()),
-                  _lib.ptr(seg_max.contiguous()), _lib.ptr(seg_sum.contiguous()), _lib.ptr(d_out.contiguous()),
-                  *plan.abi_args(), heads, head_dim, LEAKY_SLOPE,
-                  _lib.ptr(dXL), hc, _lib.ptr(dXR), _lib.ptr(datt), _lib.ptr(ws), _lib.stream_ptr())
+    dXL, dXR, datt, rowmax = _gat_backward_launch(XL, XR.contiguous(), 0 if bcast else hc, att.reshape(-1).contiguous(),
+                                                  out_nobias.contiguous(), seg_max.contiguous(), seg_sum.contiguous(),
+                                                  d_out.contiguous(), plan, heads, want_rowmax)
     if bcast:
         dXR = dXR.sum(dim=0, keepdim=True)
-    return dXL, dXR, datt
+    return (dXL, dXR, datt, rowmax) if want_rowmax else (dXL, dXR, datt)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -302,7 +310,7 @@ def seg_pool(X, plan, seg_of_edge, scale=1.0, mean=False):
 # ---------------------------------------------------------------------------------------------
 class _EdgeUpdate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, P, x0, W0, S, V, g, skip, index, pscale, scale):
+    def forward(ctx, P, x0, W0, S, V, g, skip, index, pscale, scale, rowmax_slot=None):
         _require_cuda(P, x0, W0, S, V, g, skip)
         P, ldp = _rows(P)
         E, w = P.shape
@@ -325,6 +333,7 @@ class _EdgeUpdate(torch.autograd.Function):
                       float(pscale), float(scale), _lib.ptr(out), _lib.stream_ptr())
         ctx.save_for_backward(x0, W0)
         ctx.index, ctx.pscale, ctx.scale = index, pscale, scale
+        ctx.rowmax_slot = rowmax_slot
         ctx.has = (S is not None, V is not None, g is not None, skip is not None)
         return out
 
@@ -349,15 +358,18 @@ class _EdgeUpdate(torch.autograd.Function):
             E, w = d_out.shape
             d0 = x0.shape[1]
             if w % 4 == 0 and w <= 1024 and 1 <= d0 <= 4:
-                dx0, dW0 = _x0_backward(d_out, x0, W0, scale)
+                slot = ctx.rowmax_slot if ctx.pscale == 1.0 else None        # dP is d_out itself only then
+                dx0, dW0, rowmax = _x0_backward(d_out, x0, W0, scale, want_rowmax=slot is not None)
+                if slot is not None:
+                    slot[0].note_rowmax(slot[1], d_out, rowmax)
             else:
                 dx0 = torch.mm(d_out, W0).mul_(scale)
                 dW0 = torch.mm(d_out.t(), x0).mul_(scale)
-        return (dP, dx0, dW0, dS, dV if has_V else None, dg, d_out if has_skip else None, None, None, None)
+        return (dP, dx0, dW0, dS, dV if has_V else None, dg, d_out if has_skip else None, None, None, None, None)
 
 
-def edge_update(P, x0, W0, S, V, g, skip, index, pscale=1.0, scale=0.25):
-    return _EdgeUpdate.apply(P, x0, W0, S, V, g, skip, index, pscale, scale)
+def edge_update(P, x0, W0, S, V, g, skip, index, pscale=1.0, scale=0.25, rowmax_slot=None):
+    return _EdgeUpdate.apply(P, x0, W0, S, V, g, skip, index, pscale, scale, rowmax_slot)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -485,9 +497,10 @@ def gemm_tf32x3_cat(a_list, b, bias=None, want_amax=False):
     return (c, amax) if want_amax else c
 
 
-# concatenated input gradient: "tf32x3" (default) or "f16x2" -- the fp16 variant halves the MMA time but its two-pass operand
-# producer does not keep the tensor pipe fed yet (0.89 vs 0.84 ms at cfg2, profiles/r02_fusion_ab.md)
-DX_KIND = os.environ.get("GASFM_DX", "tf32x3")
+# concatenated input gradient of a block: "f16x2" (default) = the fp16 GEMM in its ONE-pass form whenever the kernels that
+# produced the three output gradients left their row maxima behind (EdgeBlockContext.note_rowmax), 3xTF32 otherwise;
+# "tf32x3" = always 3xTF32.  (The two-pass fp16 form without row maxima is slower than 3xTF32, profiles/r02_fusion_ab.md.)
+DX_KIND = os.environ.get("GASFM_DX", "f16x2")
 
 
 def gemm_f16x2_cat_supported(M, N, n_seg, seg_k):
@@ -495,14 +508,11 @@ def gemm_f16x2_cat_supported(M, N, n_seg, seg_k):
 
 
 def gemm_cat(a_list, b, bias=None, want_amax=False):
-    """[A_0 | A_1 | ..] b^T on the tensor cores: the fp16 path where the shape allows (segments 128 / 256 wide), 3xTF32 otherwise."""
-    M, seg_k = a_list[0].shape
-    if DX_KIND == "f16x2" and all(a.shape == (M, seg_k) for a in a_list) and gemm_f16x2_cat_supported(M, b.shape[0], len(a_list), seg_k):
-        return gemm_f16x2_cat(a_list, b, bias, want_amax)
+    """[A_0 | A_1 | ..] b^T on the tensor cores when no row maxima of the A_i are at hand: 3xTF32."""
     return gemm_tf32x3_cat(a_list, b, bias, want_amax)
 
 
-def gemm_f16x2_cat(a_list, b, bias=None, want_amax=False):
+def gemm_f16x2_cat(a_list, b, bias=None, want_amax=False, rowmax=None):
     """gemm_tf32x3_cat on the scaled 2 x FP16 path (twice the tensor rate; one row scale across the segments, found in a first
     pass over the tile that L2 absorbs).  Same contract: returns c [M,N] (and max|A_i| per segment)."""
     import ctypes
@@ -516,9 +526,16 @@ def gemm_f16x2_cat(a_list, b, bias=None, want_amax=False):
     ptrs = (ctypes.c_void_p * n)(*[r[0].data_ptr() for r in rows])
     lds = (ctypes.c_int64 * n)(*[r[1] for r in rows])
     amax = torch.empty(n, dtype=torch.float32, device=b.device) if want_amax else None
+    bias_ptr = _lib.ptr(None if bias is None else bias.contiguous())
     with _lib.device_guard(b.device):
-        _lib.call("gasfm_linear_f16x2_cat", ptrs, lds, n, seg_k, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(descale),
-                  _lib.ptr(None if bias is None else bias.contiguous()), _lib.ptr(c), N, M, N, _lib.ptr(amax), _lib.stream_ptr())
+        if rowmax is not None:
+            # ``rowmax``: per-segment [M] row maxima left behind by the kernels that produced the segments -> single-pass producer
+            rms = (ctypes.c_void_p * n)(*[r.data_ptr() for r in rowmax])
+            _lib.call("gasfm_linear_f16x2_cat_rowmax", ptrs, lds, rms, n, seg_k, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(descale),
+                      bias_ptr, _lib.ptr(c), N, M, N, _lib.ptr(amax), _lib.stream_ptr())
+        else:
+            _lib.call("gasfm_linear_f16x2_cat", ptrs, lds, n, seg_k, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(descale),
+                      bias_ptr, _lib.ptr(c), N, M, N, _lib.ptr(amax), _lib.stream_ptr())
     return (c, amax) if want_amax else c
 
 
@@ -726,6 +743,25 @@ class EdgeBlockContext:
         self.recompute = bool(recompute)
         self.y = self.xl = None
         self.args = None
+        self.rowmax = {}
+
+    def slot(self, i):
+        """Handle for the backward node that produces the i-th output gradient of the block's projections (0 / 1: the two
+        attention kernels' dXL, 2: the observation update's dP): it leaves the row maxima of that gradient here."""
+        return (self, i) if DX_KIND == "f16x2" else None
+
+    def note_rowmax(self, i, grad, rowmax):
+        self.rowmax[i] = None if rowmax is None else (grad.data_ptr(), tuple(grad.shape), rowmax)
+
+    def rowmaxes_for(self, dys):
+        """Row maxima of the three output gradients if every one of them was noted for exactly these tensors, else None."""
+        out = []
+        for i, dy in enumerate(dys):
+            note = self.rowmax.get(i)
+            if note is None or note[0] != dy.data_ptr() or note[1] != tuple(dy.shape):
+                return None
+            out.append(note[2])
+        return out
 
     def bind(self, x_raw, mean, rstd, gamma, beta, eps, weights, biases, y, xl):
         self.args = (x_raw, mean, rstd, gamma, beta, eps, weights, biases)
@@ -757,6 +793,7 @@ class EdgeBlockContext:
 
     def release(self):
         self.y = self.xl = None
+        self.rowmax = {}
 
 
 def edge_block_supported(x_raw, gamma, weights_and_biases):
@@ -807,7 +844,14 @@ class _EdgeBlockProject(torch.autograd.Function):
         y = rc.get_y()
         dys = [torch.zeros((x_raw.shape[0], N), dtype=torch.float32, device=x_raw.device) if dy is None else dy.contiguous()
                for dy in dys]
-        dy_x, dy_amax = gemm_cat(dys, torch.cat([w.t() for w in weights], dim=1), want_amax=True)
+        wcat = torch.cat([w.t() for w in weights], dim=1)
+        rowmaxes = rc.rowmaxes_for(dys) if DX_KIND == "f16x2" else None
+        if rowmaxes is not None and gemm_f16x2_cat_supported(x_raw.shape[0], wcat.shape[0], len(dys), N) and (len(dys) * (N // 64)) % 4 == 0:
+            # every output gradient came with its row maxima (attention backward kernels, the update's x0 kernel):
+            # one-pass fp16 input gradient at twice the 3xTF32 tensor rate
+            dy_x, dy_amax = gemm_f16x2_cat(dys, wcat, want_amax=True, rowmax=rowmaxes)
+        else:
+            dy_x, dy_amax = gemm_tf32x3_cat(dys, wcat, want_amax=True)
         wgrads = []
         if WGRAD_MULTI:
             dw_all, db_all = wgrad_f16x2_multi(dys, y, dy_amax, x_amax)
@@ -828,17 +872,23 @@ def edge_block_project(x_raw, gamma, beta, eps, rc, weights_and_biases):
     return _EdgeBlockProject.apply(x_raw, gamma, beta, eps, rc, *flat)
 
 
-def _x0_backward(d_out, x0, W0, scale):
+def _x0_backward(d_out, x0, W0, scale, want_rowmax=False):
+    """-> (dx0, dW0, rowmax | None); ``want_rowmax``: max |d_out[e, :]| per row, from the same pass over d_out."""
     E, w = d_out.shape
     d0 = x0.shape[1]
     dev = d_out.device
     dx0 = torch.empty((E, d0), dtype=torch.float32, device=dev)
     dW0 = torch.empty((w, d0), dtype=torch.float32, device=dev)
     ws = torch.empty(max(1, _lib.size_query("gasfm_x0_bwd_ws_bytes", E, w) // 4), dtype=torch.float32, device=dev)
+    rowmax = torch.empty(E, dtype=torch.float32, device=dev) if want_rowmax else None
     with _lib.device_guard(dev):
-        _lib.call("gasfm_x0_bwd", _lib.ptr(d_out), E, w, _lib.ptr(x0), _lib.ptr(W0), d0, float(scale),
-                  _lib.ptr(dx0), _lib.ptr(dW0), _lib.ptr(ws), _lib.stream_ptr())
-    return dx0, dW0
+        if want_rowmax:
+            _lib.call("gasfm_x0_bwd_rowmax", _lib.ptr(d_out), E, w, _lib.ptr(x0), _lib.ptr(W0), d0, float(scale),
+                      _lib.ptr(dx0), _lib.ptr(dW0), _lib.ptr(ws), _lib.ptr(rowmax), _lib.stream_ptr())
+        else:
+            _lib.call("gasfm_x0_bwd", _lib.ptr(d_out), E, w, _lib.ptr(x0), _lib.ptr(W0), d0, float(scale),
+                      _lib.ptr(dx0), _lib.ptr(dW0), _lib.ptr(ws), _lib.stream_ptr())
+    return dx0, dW0, rowmax
 
 
 class _LinearTinyK(torch.autograd.Function):
@@ -864,7 +914,7 @@ class _LinearTinyK(torch.autograd.Function):
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
         dy = dy.contiguous()
-        dx, dw = _x0_backward(dy, x, weight, 1.0)
+        dx, dw, _ = _x0_backward(dy, x, weight, 1.0)
         db = col_sum(dy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db
 

@@ -125,6 +125,17 @@ GASFM_API int gasfm_gat_edge_bwd(const float* XL, int64_t ldxl, const float* XR,
                        int heads, int head_dim, float slope,
                        float* dXL, int64_t lddxl, float* dXR, float* datt, void* ws, void* stream);
 
+/* gasfm_gat_edge_bwd that also writes dxl_rowmax[E] = max |dXL[e, :]| of every edge row it produces (vectorised head shapes
+ * only, gasfm_gat_edge_bwd_rowmax_supported): the row scale of the fp16 input-gradient GEMM that consumes dXL next. */
+GASFM_API int gasfm_gat_edge_bwd_rowmax_supported(int heads, int head_dim);
+GASFM_API int gasfm_gat_edge_bwd_rowmax(const float* XL, int64_t ldxl, const float* XR, int64_t ldxr,
+                       const float* att, const float* out_nobias, const float* seg_max,
+                       const float* seg_sum, const float* dOut,
+                       const int32_t* seg_ptr, const int32_t* perm, int n_seg,
+                       int chunk, const int32_t* chunk_ptr, const int32_t* chunk_seg, int max_chunks,
+                       int heads, int head_dim, float slope,
+                       float* dXL, int64_t lddxl, float* dXR, float* datt, float* dxl_rowmax, void* ws, void* stream);
+
 /* The same two kernels with the projected sources STORED as bf16 (XL / dXL: 2-byte elements, row strides in elements,
  * 8-byte aligned; everything else fp32, arithmetic fp32): half the bytes per edge of the bandwidth-bound pass
  * (BASELINE.json configs[4], "fp32 vs bf16").  Head shapes 4 x 32 and 4 x 64.  The result is exact for the bf16-rounded
@@ -247,6 +258,14 @@ GASFM_API int gasfm_linear_f16x2_cat(const float* const* A, const int64_t* lda, 
                            const void* B_hi, const void* B_lo, const float* b_descale, const float* bias,
                            float* C, int64_t ldc, int64_t M, int N, float* a_amax, void* stream);
 
+/* ... and in ONE pass when the kernels that produced the A_i left their row maxima behind (rowmax[i][M] = max |A_i[m, :]|; host
+ * array of device pointers): gasfm_gat_edge_bwd_rowmax for the two attention gradients, gasfm_x0_bwd_rowmax for the gradient that
+ * reaches lin_proj.  The operand producer then streams the K blocks with three blocks of loads in flight; n_seg * seg_k / 64 must
+ * be a multiple of 4. */
+GASFM_API int gasfm_linear_f16x2_cat_rowmax(const float* const* A, const int64_t* lda, const float* const* rowmax, int n_seg,
+                           int seg_k, const void* B_hi, const void* B_lo, const float* b_descale, const float* bias,
+                           float* C, int64_t ldc, int64_t M, int N, float* a_amax, void* stream);
+
 /* The same kernel with LayerNorm + ReLU applied to A on the fly: the operand is relu(layer_norm(A) * gamma + beta)
  * (normalize_projection_features + relu_on_projection_features feeding lin_l / lin_proj, models/layers.py:232-234 ->
  * :329,426,941), evaluated on the register-resident A tile, so the normalised features are never written to or read
@@ -294,6 +313,11 @@ GASFM_API int gasfm_wgrad_small(const float* dY, int64_t lddy, const float* X, i
 GASFM_API size_t gasfm_x0_bwd_ws_bytes(int64_t E, int width);
 GASFM_API int gasfm_x0_bwd(const float* dOut, int64_t E, int width, const float* x0, const float* W0, int d0,
                            float scale, float* dx0, float* dW0, void* ws, void* stream);
+
+/* gasfm_x0_bwd that also writes rowmax[E] = max |dOut[e, :]| (the same gradient is lin_proj's output gradient,
+ * models/layers.py:941: its row scale for the fp16 input-gradient GEMM). */
+GASFM_API int gasfm_x0_bwd_rowmax(const float* dOut, int64_t E, int width, const float* x0, const float* W0, int d0,
+                                  float scale, float* dx0, float* dW0, void* ws, float* rowmax, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Sparse ESFM reprojection loss over the E observed (view, point) pairs (ESFMLoss.forward,

@@ -722,3 +722,38 @@ def test_gemm_f16x2_cat_has_fp32_accuracy(M, N, n_seg, seg_k):
     assert torch.equal(got, ops.gemm_f16x2_cat(segs, w, None))
     with_bias = ops.gemm_f16x2_cat(segs, w, bias)
     assert float((with_bias.double() - (ref + bias.double())).abs().max() / (ref + bias.double()).abs().max()) < 1e-5
+
+
+def test_row_maxima_from_upstream_kernels_feed_the_one_pass_fp16_input_gradient():
+    """The attention backward and the update's x0 kernel emit max |row| of the gradients they produce; with those the fp16
+    concatenated GEMM runs its one-pass producer and must give bit-identical results to its two-pass form."""
+    H, C, m, n = 4, 64, 12, 700
+    idx_np, _ = gasfm_cpu.synthetic_observations(m, n, 6000, seed=9)
+    E = idx_np.shape[1]
+    oi = ObservationIndex(torch.from_numpy(idx_np).to(DEV), m, n)
+    torch.manual_seed(1)
+    XL = torch.randn(E, H * C, device=DEV)
+    att = torch.randn(1, H, C, device=DEV) * 0.3
+    grads, rowmaxes = [], []
+    for plan, T in ((oi.by_track, n), (oi.by_view, m)):
+        XR = torch.randn(T, H * C, device=DEV)
+        acc, mx, sm = ops.gat_edge_partial(XL, XR, att, plan, H)
+        out = acc / sm.repeat_interleave(C, dim=1).clamp_min(1e-30)
+        dO = torch.randn(T, H * C, device=DEV) * 10.0 ** torch.randint(-3, 3, (T, 1), device=DEV).float()
+        dXL, _, _, rm = ops.gat_edge_backward_raw(XL, XR, att, out, mx, sm, dO, plan, H, want_rowmax=True)
+        ref, _, _ = ops.gat_edge_backward_raw(XL, XR, att, out, mx, sm, dO, plan, H)
+        assert torch.equal(dXL, ref) and torch.equal(rm, dXL.abs().amax(dim=1))
+        grads.append(dXL); rowmaxes.append(rm)
+    d_out = torch.randn(E, H * C, device=DEV) * 10.0 ** torch.randint(-4, 2, (E, 1), device=DEV).float()
+    x0, W0 = torch.randn(E, 2, device=DEV), torch.randn(H * C, 2, device=DEV)
+    dx0, dW0, rm = ops._x0_backward(d_out, x0, W0, 0.25, want_rowmax=True)
+    dx0_ref, dW0_ref, _ = ops._x0_backward(d_out, x0, W0, 0.25)
+    assert torch.equal(dx0, dx0_ref) and torch.equal(dW0, dW0_ref) and torch.equal(rm, d_out.abs().amax(dim=1))
+    grads.append(d_out); rowmaxes.append(rm)
+    w = torch.randn(H * C, 3 * H * C, device=DEV) / (3 * H * C) ** 0.5
+    one_pass, amax1 = ops.gemm_f16x2_cat(grads, w, want_amax=True, rowmax=rowmaxes)
+    two_pass, amax2 = ops.gemm_f16x2_cat(grads, w, want_amax=True)
+    assert torch.equal(one_pass, two_pass) and torch.equal(amax1, amax2)
+    ref = torch.cat([g.double() for g in grads], dim=1) @ w.double().t()
+    scale = torch.cat(grads, dim=1).double().norm(dim=1, keepdim=True) * w.double().norm(dim=1).unsqueeze(0) + 1e-30
+    assert float(((one_pass.double() - ref).abs() / scale).max()) < 2e-6

@@ -14,3 +14,14 @@ dw,db=ops.wgrad_f16x2_multi(dys,x,amax3,ax)
 ref=dys[1].double().t()@x.double()
 r['err']=float((dw[1].double()-ref).abs().max()/ref.abs().max())
 print(json.dumps(r))
+w=torch.randn(256,256,device=dev)/16
+r2={}
+r2['gemm_single_ms']=bench.timed_batches(lambda: ops.gemm_f16x2(x,w))
+r2['gemm_3groups_ms']=bench.timed_batches(lambda: ops.gemm_f16x2_groups(x,[w,w,w],[None,None,None]))
+wc=torch.cat([w,w,w],1)
+r2['dx_tf32_ms']=bench.timed_batches(lambda: ops.gemm_tf32x3_cat(dys,wc))
+r2['dx_f16_ms']=bench.timed_batches(lambda: ops.gemm_f16x2_cat(dys,wc))
+print(json.dumps(r2))
+rms=[d.abs().amax(1) for d in dys]
+r3={'dx_f16_rowmax_ms': bench.timed_batches(lambda: ops.gemm_f16x2_cat(dys,wc,rowmax=rms))}
+print(json.dumps(r3))
