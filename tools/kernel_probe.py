@@ -21,6 +21,8 @@ amax_x = x.abs().max().reshape(1)
 for _ in range(3):
     if "dx_f16" in which:
         ops.gemm_f16x2_cat(dys, wcat)
+    if "dx_f16_rm" in which:
+        ops.gemm_f16x2_cat(dys, wcat, rowmax=[dy.abs().amax(1) for dy in dys])
     if "dx_tf32" in which:
         ops.gemm_tf32x3_cat(dys, wcat)
     if "wgrad_multi" in which:
