@@ -221,9 +221,11 @@ def kernel_roofline(cfg, peaks, peak_kind, forward_ms=None):
         if ops.DX_KIND == "f16x2" and ops.gemm_f16x2_cat_supported(E, HC, 3, HC):
             # fp16 path: half the MMA time of 3xTF32, which leaves the kernel between the two roofs; credited as HBM-bound
             # (read the three dY once + write dX once)
-            dx_ms = timed_batches(lambda: ops.gemm_f16x2_cat([XL, XL, XL], Wcat))
-            res["gemm_f16x2_cat (dX over 3 dY)"] = dict(bound="hbm", ms=dx_ms, work=4 * E * HC * 4, calls=n_blocks3,
-                                                        pipe_util=9 * flops / dx_ms / 1e9 / (2.0 * peak_tf32))
+            # (one-pass form: the row maxima come from the kernels that produced the dY_i, as in the model's backward)
+            rowmax = XL.abs().amax(dim=1)
+            dx_ms = timed_batches(lambda: ops.gemm_f16x2_cat([XL, XL, XL], Wcat, rowmax=[rowmax, rowmax, rowmax]))
+            res["gemm_f16x2_cat (dX over 3 dY, row maxima from upstream)"] = dict(
+                bound="hbm", ms=dx_ms, work=4 * E * HC * 4, calls=n_blocks3, pipe_util=9 * flops / dx_ms / 1e9 / (2.0 * peak_tf32))
         else:
             dx_ms = timed_batches(lambda: ops.gemm_tf32x3_cat([XL, XL, XL], Wcat))
             res["gemm_tf32x3_cat (dX over 3 dY)"] = dict(bound="tensor", ms=dx_ms, work=3 * flops, calls=n_blocks3, hbm_bytes=4 * E * HC * 4,
