@@ -618,7 +618,9 @@ def cfg4_scene_shapes():
 def run_cfg4(args):
     """One optimisation step of the reference's multi-scene learning (code/train.py:61-137): forward + ESFM loss + backward
     over every scene of the batch, gradients SUMMED over the scenes, Adam step.  Scenes are dealt to the ranks in snake
-    order (largest with smallest); the 580 MB gradient all-reduce is bucketed and overlapped with backward."""
+    order (largest with smallest).  Timed form: every local scene's forward+loss+backward replayed as a CUDA graph into one flat
+    gradient bucket, one NCCL all-reduce, Adam.  The eager forms (bucketed all-reduce overlapped with backward / one flat
+    all-reduce after backward) are timed next to it: at the shipped d = 32 they are launch-bound."""
     from gasfm_b200 import _lib
     from gasfm_b200 import dist as gdist
     from gasfm_b200.config import ConfigTree, gasfm_conf
@@ -678,16 +680,53 @@ def run_cfg4(args):
         opt.step()
         return total
 
-    l0 = _lib.launch_count
     flat_ms = timed(lambda: step(scenes_dev, overlap=False), max(2, args.steps // 2), 2, sync_dist=sync) if sync else None
     opt.zero_grad(set_to_none=True)
     launches_probe = _lib.launch_count
     step(scenes_dev)
     launches = _lib.launch_count - launches_probe
+    eager_ms = timed(lambda: step(scenes_dev), max(2, args.steps // 2), 2, sync_dist=sync)
+
+    # graph replay: forward + loss + backward of every local scene captured once (no collective inside a capture); the
+    # gradients of all scenes accumulate in ONE flat bucket, which a single NCCL all-reduce sums over the ranks afterwards
+    graphed, replay_step = False, None
+    if not args.no_graph:
+        ok = 1
+        try:
+            from gasfm_b200.graphs import GraphedStep
+            if reducer is not None:
+                reducer.enabled = False                       # the bucket hooks must not fire inside a capture
+            flat = gdist.LocalGradBucket(model, select=lambda name: True)
+            graphs = [GraphedStep(model, sc, (lambda out, sc=sc: loss_fn(out, sc)), warmup=2,
+                                  before_forward=flat.prepare if i == 0 else flat.attach) for i, sc in enumerate(scenes_dev)]
+
+            def replay_step():
+                total = None
+                for g in graphs:
+                    loss = g()
+                    total = loss.detach() if total is None else total + loss.detach()
+                if sync:
+                    flat.allreduce_nccl()
+                opt.step()
+                return total
+        except Exception as exc:
+            print(f"[bench] rank {rank}: CUDA graph capture failed, timing eagerly: {exc}", file=sys.stderr)
+            ok = 0
+        if sync:
+            flag = torch.tensor([ok], device=dev)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+            ok = int(flag.item())
+        graphed = bool(ok)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms = timed(lambda: step(scenes_dev), args.steps, args.warmup, sync_dist=sync)
+    ms = timed(replay_step if graphed else (lambda: step(scenes_dev)), args.steps, args.warmup, sync_dist=sync)
     clocks = sampler.stop()
+    if graphed:
+        del graphs
+        flat.attach()                                         # leave .grad pointing at live memory for the eager e2e steps
+        if reducer is not None:
+            reducer.enabled = True
+    torch.cuda.empty_cache()
     holder = {}
 
     def step_e2e():
@@ -698,7 +737,6 @@ def run_cfg4(args):
     if sync:
         torch.distributed.all_reduce(t)
     E_total, h2d, launches_all = int(t[0].item()), int(t[1].item()), int(t[2].item())
-    del l0
     if rank == 0:
         n_gat = 2 * (12 + 1)
         line = {"metric": METRIC, "value": E_total * n_gat / (ms / 1e3), "unit": "edges/s", "n_gpus": world, "steps": args.steps,
@@ -706,16 +744,17 @@ def run_cfg4(args):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"cfg4: multi-scene training step over {CFG4_SCENES} synthetic scenes (100..500 views, 60 tracks per view, "
                                        f"3% density, E={E_total} observations in total), shipped GASFM model ({n_params} parameters) replicated, "
-                                       "sparse ESFM loss, SUM gradient all-reduce (NCCL, bucketed, overlapped with backward), Adam step",
+                                       "sparse ESFM loss, gradients SUMMED over scenes and ranks (one NCCL all-reduce of a flat bucket after the graph replays), Adam step",
                            "edge_level_gats_per_step": n_gat * CFG4_SCENES, "parallelism": f"{CFG4_SCENES} scenes dealt to {world} GPU(s)",
-                           "cache": "eager steps; inputs re-read every step"},
+                           "cache": "per-scene forward+backward replayed as CUDA graphs, one NCCL all-reduce of the flat gradient bucket, Adam"},
                 "scenes_per_s": CFG4_SCENES / (ms / 1e3),
-                "grad_allreduce": None if not sync else {"bytes": n_params * 4, "ms_per_step_flat_after_backward": flat_ms,
-                                                         "ms_per_step_bucketed_overlapped": ms},
+                "eager_ms_per_step": eager_ms,
+                "grad_allreduce": None if not sync else {"bytes": n_params * 4, "eager_ms_per_step_flat_after_backward": flat_ms,
+                                                         "eager_ms_per_step_bucketed_overlapped": eager_ms},
                 "e2e": {"value": E_total * n_gat / (e2e_ms / 1e3), "unit": "edges/s", "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world},
                 "gpu_launches": launches_all * args.steps, "gpu_launches_per_step": launches_all, "clocks": clocks,
-                "cuda_graph": False, "roofline": None, "cpu_baseline": None, "parity": None}
+                "cuda_graph": graphed, "roofline": None, "cpu_baseline": None, "parity": None}
         print(json.dumps(line))
     if sync:
         torch.distributed.barrier()

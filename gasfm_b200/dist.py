@@ -374,14 +374,18 @@ def is_local_parameter(name):
 
 
 class LocalGradBucket:
-    """Persistent flat buffer behind the ``.grad`` of every local parameter: autograd accumulates into views of it,
-    and one in-place exchange per step completes the partial sums (no per-step ``torch.cat``)."""
+    """Persistent flat buffer behind the ``.grad`` of every selected parameter: autograd accumulates into views of it, and one
+    in-place exchange per step completes the partial sums (no per-step ``torch.cat``).
 
-    def __init__(self, model, exchange):
+    Track-sharded scenes: ``select`` = ``is_local_parameter`` (default), ``exchange`` = the peer-memory exchange.
+    Scene-per-GPU training with graph-replayed per-scene steps: ``select=lambda name: True`` and ``allreduce_nccl`` after
+    the replays (every gradient is a per-rank partial there)."""
+
+    def __init__(self, model, exchange=None, select=is_local_parameter):
         self.exchange = exchange
         named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]
-        self.local = [p for k, p in named if is_local_parameter(k)]
-        self.replicated = [p for k, p in named if not is_local_parameter(k)]
+        self.local = [p for k, p in named if select(k)]
+        self.replicated = [p for k, p in named if not select(k)]
         total = _pad4(sum(p.numel() for p in self.local))
         dev = self.local[0].device if self.local else torch.device("cpu")
         self.flat = torch.zeros(max(total, 4), dtype=torch.float32, device=dev)
@@ -390,17 +394,25 @@ class LocalGradBucket:
             self.views.append(self.flat[off:off + p.numel()].view_as(p))
             off += p.numel()
 
-    def prepare(self):
-        """Before forward: zero the bucket, point the local ``.grad``s at it, drop the replicated ones."""
-        self.flat.zero_()
+    def attach(self):
+        """Point the selected ``.grad``s at the bucket (without zeroing it) and drop the others."""
         for p, v in zip(self.local, self.views):
             p.grad = v
         for p in self.replicated:
             p.grad = None
 
+    def prepare(self):
+        """Before forward: zero the bucket, point the local ``.grad``s at it, drop the replicated ones."""
+        self.flat.zero_()
+        self.attach()
+
     def allreduce(self):
-        """After backward: complete the local gradients (in place)."""
+        """After backward: complete the local gradients (in place) through the peer-memory exchange."""
         self.exchange.allreduce_sum(self.flat, out=self.flat)
+
+    def allreduce_nccl(self, group=None):
+        """One NCCL SUM all-reduce over the whole bucket (scene-per-GPU training)."""
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
 
 
 class BucketedGradReducer:
