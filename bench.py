@@ -209,10 +209,14 @@ def kernel_roofline(cfg, peaks, peak_kind, forward_ms=None):
         gemm_ms = timed_batches(lambda: ops.gemm_tc(XL, W))
         if f16:
             grp_ms = timed_batches(lambda: ops.gemm_f16x2_groups(XL, [W, W, W], [None, None, None]))
+            # write_frac: the bytes this kernel WRITES against the write half of the measured copy bandwidth -- a copy moves
+            # hbm_gbs / 2 in each direction, which is also the most one SM-side store stream was seen to sustain (~22 B/ns per SM)
             res["gemm_f16x2 x3 groups (forward projections)"] = dict(
-                bound="hbm", ms=grp_ms, work=4 * E * HC * 4, calls=n_blocks3, pipe_util=9 * flops / grp_ms / 1e9 / (2.0 * peak_tf32))
+                bound="hbm", ms=grp_ms, work=4 * E * HC * 4, calls=n_blocks3, pipe_util=9 * flops / grp_ms / 1e9 / (2.0 * peak_tf32),
+                write_frac=3 * E * HC * 4 / grp_ms / 1e6 / (peak_gbs / 2))
             res["gemm_f16x2 (single projection)"] = dict(bound="hbm", ms=gemm_ms, work=io_bytes, calls=2,
-                                                         pipe_util=3 * flops / gemm_ms / 1e9 / (2.0 * peak_tf32))
+                                                         pipe_util=3 * flops / gemm_ms / 1e9 / (2.0 * peak_tf32),
+                                                         write_frac=E * HC * 4 / gemm_ms / 1e6 / (peak_gbs / 2))
         else:
             res["gemm_tf32x3 (forward projections)"] = dict(bound="tensor", ms=gemm_ms, work=flops, calls=n_gemm, hbm_bytes=io_bytes,
                                                             pipe_util=3 * flops / gemm_ms / 1e9 / peak_tf32)
@@ -261,7 +265,8 @@ def kernel_roofline(cfg, peaks, peak_kind, forward_ms=None):
             "all_kernels": {k: {"bound": v["bound"], "ms": round(v["ms"], 4), "calls_per_step": v["calls"],
                                 "achieved": round(v["achieved"], 1), "unit": v["unit"], "frac": round(v["frac"], 4),
                                 **({"hbm_frac": v["hbm_frac"]} if "hbm_frac" in v else {}),
-                                **({"pipe_util": round(v["pipe_util"], 4)} if "pipe_util" in v else {})}
+                                **({"pipe_util": round(v["pipe_util"], 4)} if "pipe_util" in v else {}),
+                                **({"write_frac": round(v["write_frac"], 4)} if "write_frac" in v else {})}
                             for k, v in res.items()}}
     if forward_ms:
         # fused-layer floor of SURVEY.md 8d: x read once, x_out written once, the per-edge index once -- per block
