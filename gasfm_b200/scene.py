@@ -136,3 +136,85 @@ def sample_data(data, num_views, consecutive_views=True):
     ``dataset_utils.sample_indices``), built sparsely on the scene's own device."""
     indices = dataset_utils.sample_indices(data.x.shape[0], num_views, adjacent=consecutive_views)
     return data.subset_views(indices)
+
+
+def get_subset(data, subset_size):
+    """``SceneData.get_subset`` (SceneData.py:529-583): greedy choice of ``subset_size`` views -- start with the view that sees the
+    most points, then repeatedly add the view sharing the most points with those seen so far (first index on ties, selected
+    views count as sharing nothing) -- evaluated on the observation list (one bincount over the edges per added view instead
+    of a dense ``[m, n]`` mask product).  -> (Scene restricted to the chosen views, chosen view ids in selection order)."""
+    m, n = data.x.shape[0], data.x.shape[1]
+    rows, cols = data.x.indices[0], data.x.indices[1]
+    dev = rows.device
+    available = torch.ones(m, dtype=torch.bool, device=dev)
+    first = int(torch.bincount(rows, minlength=m).argmax().item())
+    seen = torch.zeros(n, dtype=torch.bool, device=dev)
+    seen[cols[rows == first]] = True
+    available[first] = False
+    chosen = [first]
+    for _ in range(subset_size - 1):
+        shared = torch.bincount(rows, weights=(seen[cols] & available[rows]).to(torch.float64), minlength=m)
+        nxt = int(shared.argmax().item())
+        seen[cols[(rows == nxt) & available[rows]]] = True
+        available[nxt] = False
+        chosen.append(nxt)
+    return data.subset_views(np.sort(np.asarray(chosen, dtype=np.int64))), chosen
+
+
+def apply_rotational_homography_aug(data, inplane_rot_aug_max_angle=None, tilt_rot_aug_max_angle=None):
+    """``SceneData.apply_rotational_homography_aug`` (SceneData.py:358-453): a random in-plane and / or tilt rotation per view,
+    applied to the cameras (``y <- Ns^-1 R Ns y``) and to the image points (``pflat(Ns^-1 R Ns [x; y; 1])``), on the E observed
+    points only (the reference transforms the dense ``[m, 3, n]`` array).  Draws the same ``torch.rand`` numbers in the same
+    order as the reference, so equal seeds on the same device give equal augmentations.  Needs ``Scene.obs`` and ``Scene.Ns``."""
+    import math
+
+    if inplane_rot_aug_max_angle is None and tilt_rot_aug_max_angle is None:
+        return data
+    if data.obs is None or data.Ns is None:
+        raise ValueError("the rotational augmentation needs the raw image points and Ns (Scene.obs / Scene.Ns)")
+    dev = data.obs.device
+    m, n = data.x.shape[0], data.x.shape[1]
+    R = torch.eye(3, device=dev)[None].repeat(m, 1, 1)
+    inplane = inplane_rot_aug_max_angle or 0
+    assert inplane >= 0
+    if inplane > 0:
+        angle = inplane * (2 * torch.rand((m,), dtype=torch.float32, device=dev) - 1)
+        rotvec = torch.zeros((m, 3), dtype=torch.float32, device=dev)
+        rotvec[:, 2] = angle / 180. * math.pi
+        R = _axis_angle_to_matrix(rotvec) @ R
+    tilt = tilt_rot_aug_max_angle or 0
+    assert tilt >= 0
+    if tilt > 0:
+        angle = tilt * (2 * torch.rand((m,), dtype=torch.float32, device=dev) - 1)
+        alpha = torch.rand((m,), dtype=torch.float32, device=dev) * 2 * math.pi
+        axis = torch.zeros((m, 3), dtype=torch.float32, device=dev)
+        axis[:, 0], axis[:, 1] = torch.cos(alpha), torch.sin(alpha)
+        R = _axis_angle_to_matrix(axis * angle[:, None] / 180. * math.pi) @ R
+    Ns = data.Ns.to(dev)
+    Ns_inv = torch.linalg.inv(Ns)
+    y = None if data.y is None else (Ns_inv @ R @ Ns) @ data.y.to(dev)
+    rows = data.x.indices[0]
+    hom = torch.cat((data.obs, torch.ones_like(data.obs[:, :1])), dim=1)                   # old pixel coordinates [E,3]
+    norm_old = torch.einsum("eij,ej->ei", Ns[rows], hom)
+    norm_new = torch.einsum("eij,ej->ei", R[rows], norm_old)
+    pix_new = torch.einsum("eij,ej->ei", Ns_inv[rows], norm_new)
+    obs = pix_new[:, :2] / pix_new[:, 2:3]                                                 # geo_utils.batch_pflat
+    values = torch.einsum("eij,ej->ei", Ns[rows][:, :2, :], torch.cat((obs, torch.ones_like(obs[:, :1])), dim=1))
+    x = SparseMat(values, data.x.indices, data.x.cam_per_pts, data.x.pts_per_cam, tuple(data.x.shape),
+                  _index=getattr(data.x, "_gasfm_b200_index", None))
+    return Scene(x, data.scene_name, y, data.Ns, obs, data.calibrated)
+
+
+def _axis_angle_to_matrix(axis_angle):
+    """pytorch3d.transforms.axis_angle_to_matrix (Rodrigues via quaternions, as pytorch3d does it)."""
+    angles = torch.norm(axis_angle, p=2, dim=-1, keepdim=True)
+    half = angles * 0.5
+    small = angles.abs() < 1e-6
+    sin_half_over_angle = torch.where(small, 0.5 - (angles * angles) / 48, torch.sin(half) / torch.where(small, torch.ones_like(angles), angles))
+    q = torch.cat((torch.cos(half), axis_angle * sin_half_over_angle), dim=-1)
+    r, i, j, k = torch.unbind(q, -1)
+    two_s = 2.0 / (q * q).sum(-1)
+    o = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
+    return o.reshape(q.shape[:-1] + (3, 3))

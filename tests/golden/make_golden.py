@@ -231,6 +231,27 @@ def make_metric_and_sampling(ref):
         fix[f"{name}.Ns"] = sub.Ns
         for key, w in sub.graph_wrappers.items():
             fix[f"{name}.graph.{key}"] = w.edge_index
+    # greedy subset (SceneData.get_subset) and the rotational homography augmentation, same fixture file
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        sub = ref.SceneData.get_subset(data, 5)
+    name = "subset5"
+    fix[f"{name}.view_ids"] = sub.y[:, 0, 0].to(torch.int64)
+    fix[f"{name}.indices"], fix[f"{name}.values"] = sub.x.indices, sub.x.values
+    fix[f"{name}.cam_per_pts"], fix[f"{name}.pts_per_cam"] = sub.x.cam_per_pts, sub.x.pts_per_cam
+    fix[f"{name}.shape"] = np.array(sub.x.shape)
+    fix[f"{name}.Ns"] = sub.Ns
+    for key, w in sub.graph_wrappers.items():
+        fix[f"{name}.graph.{key}"] = w.edge_index
+    g2 = torch.Generator().manual_seed(9)
+    data_aug_src = ref.SceneData.SceneData(M, Ns, torch.randn(m, 3, 4, generator=g2), "aug", calibrated=True)
+    fix["aug.y_in"] = data_aug_src.y
+    for name, inplane, tilt, seed in (("aug_both", 15, 20, 4), ("aug_inplane", 30, None, 5), ("aug_tilt", None, 10, 6)):
+        torch.manual_seed(seed)
+        aug = ref.SceneData.apply_rotational_homography_aug(data_aug_src, inplane_rot_aug_max_angle=inplane, tilt_rot_aug_max_angle=tilt)
+        fix[f"{name}.args"] = np.array([-1 if inplane is None else inplane, -1 if tilt is None else tilt, seed], dtype=np.float64)
+        fix[f"{name}.indices"], fix[f"{name}.values"], fix[f"{name}.y"], fix[f"{name}.M"] = aug.x.indices, aug.x.values, aug.y, aug.M
     np.savez_compressed(os.path.join(HERE, "sample_data.npz"), **to_np(fix))
     print("sample_data ok:", {k: fix[k].tolist() for k in fix if k.endswith("view_ids")})
 

@@ -83,3 +83,38 @@ def test_core_errors_metric_matches_reference_golden():
     d = DenseData()
     d.x, d.M, d.Ns_invT = scene.x, torch.from_numpy(g["M"]).to(dev), scene.Ns_invT
     assert abs(float(compute_core_errors(d, pred, conf)["our_repro"]) - want) < 1e-5 * want
+
+
+def _host_scene(g, y_key="y"):
+    M, Ns, y = torch.from_numpy(g["M"]), torch.from_numpy(g["Ns"]), torch.from_numpy(g[y_key])
+    norm, raw = gasfm_cpu.observation_index(M, Ns), gasfm_cpu.observation_index(M)
+    m, n, _ = norm["shape"]
+    return Scene.from_observations(norm["indices"], norm["values"], m, n, Ns=Ns, obs=raw["values"], y=y)
+
+
+def test_get_subset_matches_reference_golden():
+    """SceneData.get_subset (code/datasets/SceneData.py:529-583): the greedy view choice on the observation list."""
+    from gasfm_b200.scene import get_subset
+    g = load_golden("sample_data")
+    sub, chosen = get_subset(_host_scene(g), 5)
+    assert sorted(chosen) == g["subset5.view_ids"].tolist()
+    _check(sub, g, "subset5")
+
+
+@pytest.mark.parametrize("name", ["aug_both", "aug_inplane", "aug_tilt"])
+def test_rotational_homography_aug_matches_reference_golden(name):
+    """SceneData.apply_rotational_homography_aug (code/datasets/SceneData.py:358-453) on the observed points only: same random
+    rotations for the same torch seed, cameras and (re-normalised) image points as the reference's dense computation."""
+    from gasfm_b200.scene import apply_rotational_homography_aug
+    g = load_golden("sample_data")
+    scene = _host_scene(g, "aug.y_in")
+    inplane, tilt, seed = g[f"{name}.args"]
+    torch.manual_seed(int(seed))
+    aug = apply_rotational_homography_aug(scene, None if inplane < 0 else float(inplane), None if tilt < 0 else float(tilt))
+    assert np.array_equal(aug.x.indices.numpy(), g[f"{name}.indices"])
+    assert np.abs(aug.y.numpy() - g[f"{name}.y"]).max() < 1e-4 * max(1.0, np.abs(g[f"{name}.y"]).max())
+    assert np.abs(aug.x.values.numpy() - g[f"{name}.values"]).max() < 2e-5
+    M = g[f"{name}.M"]
+    rows, cols = aug.x.indices[0].numpy(), aug.x.indices[1].numpy()
+    pix = np.stack((M[2 * rows, cols], M[2 * rows + 1, cols]), axis=1)
+    assert np.abs(aug.obs.numpy() - pix).max() < 1e-2          # pixel coordinates (~1e3) in fp32
