@@ -541,6 +541,25 @@ def parity_sharded_vs_single(dev, rank, world, exchange):
     return res
 
 
+def exchange_timings(dev, world, exchange, m, hc=256, heads=4):
+    """The cross-GPU exchange kernels alone (CUDA events, max over ranks): one log-sum-exp merge of [m, hc] partials, one sum of an
+    [m, hc] gradient and one of a 4.5 M-float bucket -- with the NVLink bound next to them: every rank pushes its payload to
+    world - 1 peers, bytes / 770 GB/s (measured peer-copy bandwidth per direction, /opt/skills/guides/B200_PROFILING.md)."""
+    torch.manual_seed(0)
+    acc = torch.randn(m, hc, device=dev)
+    mx, sm = torch.randn(m, heads, device=dev), torch.rand(m, heads, device=dev) + 1.0
+    grad = torch.randn(m, hc, device=dev)
+    bucket = torch.randn(4_500_000, device=dev)
+    res = {}
+    for name, fn, floats in (("lse_merge", lambda: exchange.lse_merge(acc, mx, sm, heads), m * (hc + 2 * heads)),
+                             ("allreduce_sum [m, d]", lambda: exchange.allreduce_sum(grad), m * hc),
+                             ("allreduce_sum local-gradient bucket", lambda: exchange.allreduce_sum(bucket), bucket.numel())):
+        us = 1e3 * timed(fn, 20, 5, sync_dist=True)
+        pushed = floats * 4 * (world - 1)
+        res[name] = {"us": round(us, 1), "bytes_pushed_per_rank": pushed, "nvlink_bound_us": round(pushed / 770e3, 1)}
+    return res
+
+
 def run_ours(args):
     from gasfm_b200 import _lib
     from gasfm_b200 import dist as gdist
@@ -568,6 +587,7 @@ def run_ours(args):
 
     r = measure_workload(cfg, args, dev, rank, world, exchange, args.scaling)
     parity = parity_sharded_vs_single(dev, rank, world, exchange) if world > 1 else None
+    exch = exchange_timings(dev, world, exchange, cfg["m"]) if world > 1 else None
     if rank != 0:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -578,7 +598,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wc,
             "forward_ms_per_scene": r["forward_ms"], "cuda_graph": r["graphed"], "eager_ms_per_step": r["eager_ms"],
-            "activation_recompute": r["recompute"], "exchange": exchange_kind,
+            "activation_recompute": r["recompute"], "exchange": exchange_kind, "exchange_kernels": exch,
             "e2e": {"value": r["e2e_value"], "unit": "edges/s", "ms_per_step": r["e2e_ms"],
                     "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
             "gpu_launches": r["launches"] * args.steps, "gpu_launches_per_step": r["launches"],
