@@ -93,6 +93,8 @@ def shard_scene(indices, values, m, n, rank, world, exchange=None, bounds=None):
     scenepoint2global graphs are flagged so that the model merges their partials through ``exchange``."""
     indices = np.asarray(indices)
     local_idx, local_vals, lo, hi = shard_observations(indices, values, m, n, rank, world, bounds)
+    if local_idx.shape[1] == 0:
+        raise ValueError(f"rank {rank} of {world} would hold no observations ({n} tracks): use fewer ranks for this scene")
     scene = Scene.from_observations(local_idx, local_vals, m, hi - lo)
     pts_per_view = np.bincount(indices[0], minlength=m)
     scene.x.pts_per_cam = torch.from_numpy(pts_per_view).unsqueeze(1)       # global counts (replicated)

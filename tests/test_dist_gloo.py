@@ -291,3 +291,11 @@ def test_bucketed_grad_reducer_sums_over_ranks_and_scenes():
         for r in res:
             assert torch.allclose(r[k], p.grad, rtol=1e-5, atol=1e-6), k
     assert torch.equal(res[0]["unused.weight"], torch.zeros(2, 2))
+
+
+def test_shard_scene_rejects_empty_shards():
+    import pytest
+    idx, vals = gasfm_cpu.synthetic_observations(8, 3, 20, seed=0)          # 3 tracks cannot feed 8 ranks
+    with pytest.raises(ValueError, match="no observations"):
+        for rank in range(8):
+            gdist.shard_scene(idx, vals, 8, 3, rank, 8)
