@@ -295,7 +295,8 @@ def test_bucketed_grad_reducer_sums_over_ranks_and_scenes():
 
 def test_shard_scene_rejects_empty_shards():
     import pytest
-    idx, vals = gasfm_cpu.synthetic_observations(8, 3, 20, seed=0)          # 3 tracks cannot feed 8 ranks
+    idx = np.array([[0, 0, 1, 1, 2, 2], [0, 1, 0, 2, 1, 2]], dtype=np.int64)        # 3 tracks cannot feed 8 ranks
+    vals = np.zeros((6, 2), dtype=np.float32)
     with pytest.raises(ValueError, match="no observations"):
         for rank in range(8):
-            gdist.shard_scene(idx, vals, 8, 3, rank, 8)
+            gdist.shard_scene(idx, vals, 3, 3, rank, 8)
