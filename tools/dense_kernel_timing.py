@@ -1,3 +1,6 @@
+"""CUDA-event timings of the dense kernels of one GASFM block at d = 256 (weight gradient single / batched, forward projections,
+concatenated input gradient in its 3xTF32 / fp16 two-pass / fp16 one-pass forms).  Usage: python tools/dense_kernel_timing.py [E]
+(A/B switches: GASFM_WGRAD_LEAN=0, GASFM_GEMM_DEBUG=32.)"""
 import os, sys, json, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
