@@ -1,5 +1,5 @@
 """A few launches of selected hot kernels at the cfg-2 shape, for `ncu --set full -k regex:<name>` (short on purpose).
-Usage: python tools/kernel_probe.py [dx_f16] [dx_tf32] [wgrad_multi] [gemm3] [peer]"""
+Usage: python tools/kernel_probe.py [E] [dx_f16] [dx_f16_rm] [dx_tf32] [wgrad_multi] [gemm3] [peer]"""
 import os
 import sys
 
@@ -8,8 +8,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gasfm_b200 import ops  # noqa: E402
 
-which = sys.argv[1:] or ["dx_f16", "wgrad_multi"]
-E, d = 495592, 256
+which = [a for a in sys.argv[1:] if not a.isdigit()] or ["dx_f16", "wgrad_multi"]
+E, d = next((int(a) for a in sys.argv[1:] if a.isdigit()), 495592), 256
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 x = torch.relu(torch.randn(E, d, device=dev))
