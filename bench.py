@@ -268,6 +268,13 @@ def kernel_roofline(cfg, peaks, peak_kind, forward_ms=None):
                                 **({"pipe_util": round(v["pipe_util"], 4)} if "pipe_util" in v else {}),
                                 **({"write_frac": round(v["write_frac"], 4)} if "write_frac" in v else {})}
                             for k, v in res.items()}}
+    try:   # DRAM traffic of the dominant kernel from the committed ncu capture of this shape, when there is one
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            t = json.load(f).get(cfg["name"], {}).get(dom)
+        if t:
+            roof["traffic"], roof["traffic_source"] = t["bytes"], t["source"]
+    except Exception:
+        pass
     if forward_ms:
         # fused-layer floor of SURVEY.md 8d: x read once, x_out written once, the per-edge index once -- per block
         floor_bytes = E * ((HC + HC) * 4 + 8) * L
