@@ -446,7 +446,7 @@ struct BwdSeg {
   }
 };
 
-template <class L, bool BF = false>
+template <class L, bool BF = false, bool RM = false>   // RM: also emit the row maxima of dXL (p.dxl_rowmax)
 __device__ __forceinline__ void bwd_rows(const GatBwdArgs& p, int begin, int end, int step, int lir,
                                          unsigned mask, const BwdSeg<L>& sg, const float4 (&att)[L::NV],
                                          float4 (&dxr)[L::NV], float4 (&datt)[L::NV]) {
@@ -499,9 +499,9 @@ __device__ __forceinline__ void bwd_rows(const GatBwdArgs& p, int begin, int end
           comp(datt[v], k) = fmaf(ds[s], leaky(z, p.slope), comp(datt[v], k));
         }
         if (valid) store_dxl4<BF>(p.dXL, eid[u], p.lddxl, 4 * lir + 4 * L::LPR * v, g);
-        rmax = fmaxf(rmax, fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fmaxf(fabsf(g.z), fabsf(g.w))));
+        if constexpr (RM) rmax = fmaxf(rmax, fmaxf(fmaxf(fabsf(g.x), fabsf(g.y)), fmaxf(fabsf(g.z), fabsf(g.w))));
       }
-      if (p.dxl_rowmax != nullptr) {
+      if constexpr (RM) {
 #pragma unroll
         for (int off = L::LPR / 2; off > 0; off >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(mask, rmax, off));
         if (lir == 0 && valid) p.dxl_rowmax[eid[u]] = rmax;
@@ -526,7 +526,7 @@ __device__ __forceinline__ void sum_across_groups(float4 (&a)[L::NV]) {
   }
 }
 
-template <int H, int C, bool CHUNKED, bool BF = false>
+template <int H, int C, bool CHUNKED, bool BF = false, bool RM = false>
 __global__ void __launch_bounds__(kBwdThreads, (H * C <= 256) ? (CHUNKED ? 2 : 3) : 1) gat_bwd_kernel(GatBwdArgs p) {
   using L = Lay<H, C>;
   constexpr int NW = kBwdThreads / 32;
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(kBwdThreads, (H * C <= 256) ? (CHUNKED ? 2 : 3
       float4 dxr[L::NV];
 #pragma unroll
       for (int v = 0; v < L::NV; ++v) dxr[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      bwd_rows<L, BF>(p, __ldg(p.seg_ptr + t), __ldg(p.seg_ptr + t + 1), 1, lir, gmask, sg, att, dxr, datt);
+      bwd_rows<L, BF, RM>(p, __ldg(p.seg_ptr + t), __ldg(p.seg_ptr + t + 1), 1, lir, gmask, sg, att, dxr, datt);
       float* xrow = p.dXR + (int64_t)t * L::HC + 4 * lir;
 #pragma unroll
       for (int v = 0; v < L::NV; ++v) st4(xrow + 4 * L::LPR * v, dxr[v]);
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(kBwdThreads, (H * C <= 256) ? (CHUNKED ? 2 : 3
       float4 dxr[L::NV];
 #pragma unroll
       for (int v = 0; v < L::NV; ++v) dxr[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      bwd_rows<L, BF>(p, b + grp, e, L::RPW, lir, gmask, sg, att, dxr, datt);
+      bwd_rows<L, BF, RM>(p, b + grp, e, L::RPW, lir, gmask, sg, att, dxr, datt);
       __syncwarp();
       sum_across_groups<L>(dxr);
       if (grp == 0) {
@@ -842,16 +842,16 @@ static int launch_fwd(const GatFwdArgs& a, cudaStream_t st) {
   return check_launch("gat_edge_fwd");
 }
 
-template <int H, int C, bool BF = false>
+template <int H, int C, bool BF = false, bool RM = false>
 static int launch_bwd(const GatBwdArgs& a, int* n_blocks_out, cudaStream_t st) {
   using L = Lay<H, C>;
   int blocks;
   if (a.chunk == 0) {
     blocks = bwd_grid_blocks(((int64_t)a.n_seg + L::RPW - 1) / L::RPW, kBwdThreads / 32);
-    gat_bwd_kernel<H, C, false, BF><<<blocks, kBwdThreads, 0, st>>>(a);
+    gat_bwd_kernel<H, C, false, BF, RM><<<blocks, kBwdThreads, 0, st>>>(a);
   } else {
     blocks = bwd_grid_blocks(a.max_chunks, kBwdThreads / 32);
-    gat_bwd_kernel<H, C, true, BF><<<blocks, kBwdThreads, 0, st>>>(a);
+    gat_bwd_kernel<H, C, true, BF, RM><<<blocks, kBwdThreads, 0, st>>>(a);
     if (a.n_seg > 0) gat_bwd_merge_kernel<<<dim3(a.n_seg, (H * C + 31) / 32), 256, 0, st>>>(a, H * C);
   }
   *n_blocks_out = blocks;
@@ -988,6 +988,12 @@ static int gat_edge_bwd_impl(bool bf16, float* dxl_rowmax, const float* XL, int6
     if (bf16) {
       GASFM_REQUIRE(heads == 4 && (head_dim == 32 || head_dim == 64), "gat_edge_bwd_bf16: head shapes 4 x 32 and 4 x 64 only");
       rc = head_dim == 32 ? launch_bwd<4, 32, true>(a, &blocks, st) : launch_bwd<4, 64, true>(a, &blocks, st);
+    } else if (dxl_rowmax != nullptr) {
+      switch (head_dim) {                          // row maxima: the widths the fp16 input-gradient GEMM takes (segments of 128 / 256)
+        case 32: rc = launch_bwd<4, 32, false, true>(a, &blocks, st); break;
+        case 64: rc = launch_bwd<4, 64, false, true>(a, &blocks, st); break;
+        default: set_error("gat_edge_bwd_rowmax: head shapes 4 x 32 and 4 x 64 only"); rc = 1; break;
+      }
     } else {
       GASFM_DISPATCH_C(launch_bwd, a, &blocks, st);
     }
@@ -1023,7 +1029,7 @@ extern "C" int gasfm_gat_edge_bwd(const float* XL, int64_t ldxl, const float* XR
                            chunk_ptr, chunk_seg, max_chunks, heads, head_dim, slope, dXL, lddxl, dXR, datt, ws, stream);
 }
 
-extern "C" int gasfm_gat_edge_bwd_rowmax_supported(int heads, int head_dim) { return has_fast_path(heads, head_dim) ? 1 : 0; }
+extern "C" int gasfm_gat_edge_bwd_rowmax_supported(int heads, int head_dim) { return (heads == 4 && (head_dim == 32 || head_dim == 64)) ? 1 : 0; }
 
 extern "C" int gasfm_gat_edge_bwd_rowmax(const float* XL, int64_t ldxl, const float* XR, int64_t ldxr,
                                          const float* att, const float* out_nobias, const float* seg_max,
@@ -1032,7 +1038,7 @@ extern "C" int gasfm_gat_edge_bwd_rowmax(const float* XL, int64_t ldxl, const fl
                                          const int32_t* chunk_seg, int max_chunks, int heads, int head_dim,
                                          float slope, float* dXL, int64_t lddxl, float* dXR, float* datt,
                                          float* dxl_rowmax, void* ws, void* stream) {
-  GASFM_REQUIRE(dxl_rowmax != nullptr && has_fast_path(heads, head_dim), "gat_edge_bwd_rowmax: needs the vectorised head shapes (4 x 2^k)");
+  GASFM_REQUIRE(dxl_rowmax != nullptr && gasfm_gat_edge_bwd_rowmax_supported(heads, head_dim), "gat_edge_bwd_rowmax: head shapes 4 x 32 and 4 x 64 only");
   return gat_edge_bwd_impl(false, dxl_rowmax, XL, ldxl, XR, ldxr, att, out_nobias, seg_max, seg_sum, dOut, seg_ptr, perm, n_seg, chunk,
                            chunk_ptr, chunk_seg, max_chunks, heads, head_dim, slope, dXL, lddxl, dXR, datt, ws, stream);
 }

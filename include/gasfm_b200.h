@@ -125,8 +125,8 @@ GASFM_API int gasfm_gat_edge_bwd(const float* XL, int64_t ldxl, const float* XR,
                        int heads, int head_dim, float slope,
                        float* dXL, int64_t lddxl, float* dXR, float* datt, void* ws, void* stream);
 
-/* gasfm_gat_edge_bwd that also writes dxl_rowmax[E] = max |dXL[e, :]| of every edge row it produces (vectorised head shapes
- * only, gasfm_gat_edge_bwd_rowmax_supported): the row scale of the fp16 input-gradient GEMM that consumes dXL next. */
+/* gasfm_gat_edge_bwd that also writes dxl_rowmax[E] = max |dXL[e, :]| of every edge row it produces (head shapes 4 x 32 and
+ * 4 x 64, gasfm_gat_edge_bwd_rowmax_supported): the row scale of the fp16 input-gradient GEMM that consumes dXL next. */
 GASFM_API int gasfm_gat_edge_bwd_rowmax_supported(int heads, int head_dim);
 GASFM_API int gasfm_gat_edge_bwd_rowmax(const float* XL, int64_t ldxl, const float* XR, int64_t ldxr,
                        const float* att, const float* out_nobias, const float* seg_max,
