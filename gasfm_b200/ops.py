@@ -345,26 +345,33 @@ class _EdgeUpdate(torch.autograd.Function):
         d_out = d_out.contiguous()
         dP = d_out if ctx.pscale == 1.0 else d_out * ctx.pscale
         dS = seg_sum_raw(d_out, index.by_track, scale) if (has_S and ctx.needs_input_grad[3]) else None
-        dV = None
-        if (has_V and ctx.needs_input_grad[4]) or (has_g and ctx.needs_input_grad[5]):
-            dV = seg_sum_raw(d_out, index.by_view, scale)
+        E, w = d_out.shape
+        need_dV = (has_V and ctx.needs_input_grad[4]) or (has_g and ctx.needs_input_grad[5])
+        need_x0 = x0 is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        x0_kernel = need_x0 and w % 4 == 0 and w <= 1024 and 1 <= x0.shape[1] <= 4
+        slot = ctx.rowmax_slot if ctx.pscale == 1.0 else None            # dP is d_out itself only then
+        dV = dx0 = dW0 = None
+        if need_dV and x0_kernel and UPDATE_BWD_FUSED and index.by_view.chunk > 0:
+            # ONE storage-order pass over d_out: per-view sums, the rank-d0 term's gradients and the row maxima
+            dV, dx0, dW0, rowmax = _update_backward_views(d_out, x0, W0, scale, index.by_view, want_rowmax=slot is not None)
+            if slot is not None:
+                slot[0].note_rowmax(slot[1], d_out, rowmax)
+        else:
+            if need_dV:
+                dV = seg_sum_raw(d_out, index.by_view, scale)
+            if x0_kernel:
+                dx0, dW0, rowmax = _x0_backward(d_out, x0, W0, scale, want_rowmax=slot is not None)
+                if slot is not None:
+                    slot[0].note_rowmax(slot[1], d_out, rowmax)
+            elif need_x0:
+                dx0 = torch.mm(d_out, W0).mul_(scale)
+                dW0 = torch.mm(d_out.t(), x0).mul_(scale)
+        if dV is not None:
             shard = getattr(index, "shard", None)
             if shard is not None and shard.world > 1:
                 # track-sharded scene: V and g are replicated, this rank saw only its own observations of every view
                 dV = shard.exchange.allreduce_sum(dV)
         dg = col_sum(dV, keepdim=True) if (has_g and ctx.needs_input_grad[5]) else None
-        dx0 = dW0 = None
-        if x0 is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
-            E, w = d_out.shape
-            d0 = x0.shape[1]
-            if w % 4 == 0 and w <= 1024 and 1 <= d0 <= 4:
-                slot = ctx.rowmax_slot if ctx.pscale == 1.0 else None        # dP is d_out itself only then
-                dx0, dW0, rowmax = _x0_backward(d_out, x0, W0, scale, want_rowmax=slot is not None)
-                if slot is not None:
-                    slot[0].note_rowmax(slot[1], d_out, rowmax)
-            else:
-                dx0 = torch.mm(d_out, W0).mul_(scale)
-                dW0 = torch.mm(d_out.t(), x0).mul_(scale)
         return (dP, dx0, dW0, dS, dV if has_V else None, dg, d_out if has_skip else None, None, None, None, None)
 
 
@@ -870,6 +877,27 @@ class _EdgeBlockProject(torch.autograd.Function):
 def edge_block_project(x_raw, gamma, beta, eps, rc, weights_and_biases):
     flat = [t for wb in weights_and_biases for t in wb]
     return _EdgeBlockProject.apply(x_raw, gamma, beta, eps, rc, *flat)
+
+
+UPDATE_BWD_FUSED = os.environ.get("GASFM_UPDATE_BWD_FUSED", "1") != "0"    # A/B switch
+
+
+def _update_backward_views(d_out, x0, W0, scale, plan, want_rowmax=False):
+    """The observation update's backward in one storage-order pass over d_out [E,w]: dV[m,w] = scale * per-view sums,
+    dx0[E,d0] = scale * d_out W0, dW0[w,d0] = scale * d_out^T x0 and (optionally) max |d_out[e,:]| per row."""
+    E, w = d_out.shape
+    d0 = x0.shape[1]
+    dev = d_out.device
+    dV = torch.empty((plan.n_seg, w), dtype=torch.float32, device=dev)
+    dx0 = torch.empty((E, d0), dtype=torch.float32, device=dev)
+    dW0 = torch.empty((w, d0), dtype=torch.float32, device=dev)
+    rowmax = torch.empty(E, dtype=torch.float32, device=dev) if want_rowmax else None
+    ws = torch.empty(max(1, _lib.size_query("gasfm_update_bwd_views_ws_bytes", plan.max_chunks, w) // 4), dtype=torch.float32, device=dev)
+    with _lib.device_guard(dev):
+        _lib.call("gasfm_update_bwd_views", _lib.ptr(d_out), E, w, _lib.ptr(x0), _lib.ptr(W0), d0, float(scale),
+                  _lib.ptr(plan.seg_ptr), plan.n_seg, plan.chunk, _lib.ptr(plan.chunk_ptr), _lib.ptr(plan.chunk_seg), plan.max_chunks,
+                  _lib.ptr(dV), _lib.ptr(dx0), _lib.ptr(dW0), _lib.ptr(rowmax), _lib.ptr(ws), _lib.stream_ptr())
+    return dV, dx0, dW0, rowmax
 
 
 def _x0_backward(d_out, x0, W0, scale, want_rowmax=False):

@@ -319,6 +319,16 @@ GASFM_API int gasfm_x0_bwd(const float* dOut, int64_t E, int width, const float*
 GASFM_API int gasfm_x0_bwd_rowmax(const float* dOut, int64_t E, int width, const float* x0, const float* W0, int d0,
                                   float scale, float* dx0, float* dW0, void* ws, float* rowmax, void* stream);
 
+/* The whole backward of gasfm_edge_update_fwd that runs in storage order, in ONE pass over dOut[E,width] (the reference's autograd
+ * makes one scatter-add per gathered term, models/layers.py:941-945): dV[n_seg,width] = scale * sum over the view's rows of dOut
+ * (gradient of V[row]; seg_ptr / chunk tables of the view plan, chunk > 0), dx0 / dW0 as gasfm_x0_bwd, and rowmax[E] (optional).
+ * ws: gasfm_update_bwd_views_ws_bytes(max_chunks, width). */
+GASFM_API size_t gasfm_update_bwd_views_ws_bytes(int max_chunks, int width);
+GASFM_API int gasfm_update_bwd_views(const float* dOut, int64_t E, int width, const float* x0, const float* W0, int d0,
+                                     float scale, const int32_t* seg_ptr, int n_seg, int chunk, const int32_t* chunk_ptr,
+                                     const int32_t* chunk_seg, int max_chunks, float* dV, float* dx0, float* dW0,
+                                     float* rowmax, void* ws, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Sparse ESFM reprojection loss over the E observed (view, point) pairs (ESFMLoss.forward,
  * loss_functions.py:85-123, without the dense [m,3,n] tensors).  Ps[m,3,4], pts3D[4,n] (row-major), obs[E,2]

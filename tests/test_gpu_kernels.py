@@ -757,3 +757,25 @@ def test_row_maxima_from_upstream_kernels_feed_the_one_pass_fp16_input_gradient(
     ref = torch.cat([g.double() for g in grads], dim=1) @ w.double().t()
     scale = torch.cat(grads, dim=1).double().norm(dim=1, keepdim=True) * w.double().norm(dim=1).unsqueeze(0) + 1e-30
     assert float(((one_pass.double() - ref).abs() / scale).max()) < 2e-6
+
+
+@pytest.mark.parametrize("w,d0", [(256, 2), (32, 2), (64, 3), (128, 1)])
+def test_update_backward_views_fused_pass(w, d0):
+    """One storage-order pass over dOut for the update's backward: per-view sums, the x0 term's gradients and the row maxima
+    must equal the separate kernels (segment sums up to summation order), views without observations included."""
+    m, n = 14, 900
+    idx_np, _ = gasfm_cpu.synthetic_observations(m, n, 9000, seed=w + d0)
+    E = idx_np.shape[1]
+    oi = ObservationIndex(torch.from_numpy(idx_np).to(DEV), m + 2, n)      # two trailing views without observations
+    assert oi.by_view.chunk > 0
+    torch.manual_seed(w)
+    d_out = torch.randn(E, w, device=DEV) * 10.0 ** torch.randint(-3, 2, (E, 1), device=DEV).float()
+    x0, W0 = torch.randn(E, d0, device=DEV), torch.randn(w, d0, device=DEV)
+    dV, dx0, dW0, rm = ops._update_backward_views(d_out, x0, W0, 0.25, oi.by_view, want_rowmax=True)
+    dV_ref = ops.seg_sum_raw(d_out, oi.by_view, 0.25)
+    dx0_ref, dW0_ref, rm_ref = ops._x0_backward(d_out, x0, W0, 0.25, want_rowmax=True)
+    assert torch.equal(rm, rm_ref) and torch.equal(dx0, dx0_ref)
+    assert rel_err(dV, dV_ref.double().cpu().numpy()) < 2e-6 and torch.equal(dV[-2:], torch.zeros(2, w, device=DEV))
+    ref_w = 0.25 * d_out.double().t() @ x0.double()
+    assert rel_err(dW0, ref_w.cpu().numpy()) < 5e-6 and rel_err(dW0_ref, ref_w.cpu().numpy()) < 5e-6
+    assert rel_err(dV, (0.25 * torch.zeros(m + 2, w, dtype=torch.float64, device=DEV).index_add_(0, oi.row_idx.long(), d_out.double())).cpu().numpy()) < 2e-6
