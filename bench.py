@@ -491,7 +491,31 @@ def measure_workload(cfg, args, dev, rank, world, exchange, scaling):
         holder["loss"] = float(loss.detach())
     del scene_dev
     torch.cuda.empty_cache()
-    e2e_ms = timed(step_e2e, max(3, args.steps // 2), 2, sync_dist=sync)
+    e2e_eager_ms = timed(step_e2e, max(3, args.steps // 2), 2, sync_dist=sync)
+    e2e_ms, e2e_graphed = e2e_eager_ms, False
+    if not args.no_graph and (not sync or isinstance(exchange, gdist.PeerExchange)):
+        # the same host-to-host step with the index build inside ONE captured graph (gasfm_b200.graphs.StreamedStep): per step
+        # the pinned host scene is copied into the captured buffers, the graph replayed, predictions + loss + index status read back
+        from gasfm_b200.graphs import StreamedStep
+        ok, streamed = 1, None
+        try:
+            streamed = StreamedStep(model, scene_host, loss_fn, outputs=("Ps_norm", "pts3D"), device=dev,
+                                    before_forward=bucket.prepare if bucket else None,
+                                    after_backward=bucket.allreduce if bucket else None)
+        except Exception as exc:
+            print(f"[bench] rank {rank}: streamed-step capture failed, e2e stays eager: {exc}", file=sys.stderr)
+            ok = 0
+        if sync:
+            flag = torch.tensor([ok], device=dev)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+            ok = int(flag.item())
+        if ok:
+            def step_streamed():
+                holder.update(streamed(scene_host))
+            e2e_ms, e2e_graphed = timed(step_streamed, max(3, args.steps // 2), 2, sync_dist=sync), True
+            holder["Ps"], holder["pts"] = holder["Ps_norm"], holder["pts3D"]
+        del streamed
+        torch.cuda.empty_cache()
     h2d = (scene_host.x.values.numel() * 4 + scene_host.x.indices.numel() * 8 +
            scene_host.x.cam_per_pts.numel() * 8 + scene_host.x.pts_per_cam.numel() * 8 +
            sum(w.valid_indices.numel() * 8 for k, w in scene_host.graph_wrappers.items() if k.endswith("2global")))
@@ -504,7 +528,8 @@ def measure_workload(cfg, args, dev, rank, world, exchange, scaling):
         exchange.check()
     return {"E": E_total, "n_total": n_total, "ms": ms, "value": E_total * n_gat / (ms / 1e3), "eager_ms": eager_ms,
             "forward_ms": fwd_ms, "e2e_ms": e2e_ms, "e2e_value": E_total * n_gat / (e2e_ms / 1e3), "h2d": int(h2d), "d2h": int(d2h),
-            "launches": int(launches), "graphed": graphed, "clocks": clocks, "recompute": recompute}
+            "launches": int(launches), "graphed": graphed, "clocks": clocks, "recompute": recompute,
+            "e2e_graphed": e2e_graphed, "e2e_eager_ms": e2e_eager_ms}
 
 
 def parity_sharded_vs_single(dev, rank, world, exchange):
@@ -607,7 +632,8 @@ def run_ours(args):
             "forward_ms_per_scene": r["forward_ms"], "cuda_graph": r["graphed"], "eager_ms_per_step": r["eager_ms"],
             "activation_recompute": r["recompute"], "exchange": exchange_kind, "exchange_kernels": exch,
             "e2e": {"value": r["e2e_value"], "unit": "edges/s", "ms_per_step": r["e2e_ms"],
-                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                    "cuda_graph": r["e2e_graphed"], "eager_ms_per_step": r["e2e_eager_ms"]},
             "gpu_launches": r["launches"] * args.steps, "gpu_launches_per_step": r["launches"],
             "clocks": r["clocks"], "roofline": None, "cpu_baseline": None, "parity": parity}
     if world == 1:
@@ -624,7 +650,8 @@ def run_ours(args):
             line["cfg2"] = {"workload": workload_config(CFG2, r2["E"], 1, "strong")["workload"], "value": r2["value"], "unit": "edges/s",
                             "ms_per_step": r2["ms"], "eager_ms_per_step": r2["eager_ms"], "forward_ms_per_scene": r2["forward_ms"],
                             "e2e": {"value": r2["e2e_value"], "ms_per_step": r2["e2e_ms"], "h2d_bytes_per_step": r2["h2d"],
-                                    "d2h_bytes_per_step": r2["d2h"]},
+                                    "d2h_bytes_per_step": r2["d2h"], "cuda_graph": r2["e2e_graphed"],
+                                    "eager_ms_per_step": r2["e2e_eager_ms"]},
                             "gpu_launches_per_step": r2["launches"], "cuda_graph": r2["graphed"], "activation_recompute": r2["recompute"]}
     print(json.dumps(line))
     if world > 1:

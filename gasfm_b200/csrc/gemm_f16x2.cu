@@ -526,6 +526,318 @@ gemm_f16x2_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// cta_group::2 form of the same product for the shipped block shape N = K = 256 (the three grouped projections of a block,
+// lin_r, the single projections): a CTA PAIR works on 256 rows with ONE tcgen05.mma.cta_group::2 stream (M = 256).
+//
+// Why: ncu on the cta_group::1 kernel above (profiles/r02_gemm_pair.md) shows the SM's shared-memory data pipe saturated --
+// LSU wavefronts 68 % + tensor-core operand wavefronts 32 % of the cycles, 14.2 k wavefronts per 128 x 256 output tile against
+// 6.1 k cycles of MMA -- not HBM (39 %) and not the tensor pipe (44 %).  Per tile the pipe carried: operand reads of the MMAs
+// (12 KB per instruction: 4.6 k), the fp16 hi/lo planes of A written once PER GROUP (1.0 k), the epilogue's staging round trip
+// (2.0 k), 16 broadcast loads of column scale / bias per 32-column chunk (1.0 k), global loads / stores (1.4 k), plus the
+// cycles lost when those clients collide.  This kernel removes what can be removed:
+//   * cta_group::2: each SM feeds its 128 rows of A and HALF of the weights' K block; the pair shares the halves, so an
+//     instruction reads 8 KB per SM instead of 12, and the TMA writes half as much B into each SM;
+//   * the halved B stages leave room for the whole fp16 A tile (4 K blocks x hi/lo = 128 KB) to stay resident: A is converted
+//     ONCE per tile and reused by every group (slot kb is refilled with the next tile as soon as the last group has used it);
+//   * column scale and bias are applied after the staging transposition, where a lane owns 8 columns: 4 loads per chunk.
+// Roles per CTA (16 warps, setmaxnreg as above): warp 0 TMA of this CTA's B half; warp 1 MMA issue (leader CTA) or relay
+// (peer CTA: forwards "my half is in place" to the leader, one remote arrive per K block); warps 4-11 A producers; warps 12-15
+// epilogue of this CTA's 128 accumulator rows.
+constexpr int kPKB = 4;                                   // K blocks of 64 (K = 256)
+constexpr int kPN = 256;
+constexpr int kPSlotBytes = 2 * kFATileBytes;             // A slot: hi | lo planes of one K block (32 KB)
+constexpr int kPBPlaneBytes = (kPN / 2) * kFBlockK * 2;   // this CTA's 128 weight rows of one K block, one plane (16 KB)
+constexpr int kPBStageBytes = 2 * kPBPlaneBytes;          // hi | lo
+constexpr int kPBStages = 2;
+constexpr size_t kPSmemBytes = (size_t)kPKB * kPSlotBytes + (size_t)kPBStages * kPBStageBytes + 4 * 4096 + 1024;
+
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {     // observes arrivals made by the peer CTA
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// arrive on the barrier at this shared-memory offset in CTA ``rank`` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {      // arrives on this barrier in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1)
+gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, GemmF16Args p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_ring = smem;                                           // [kb][hi 16 KB | lo 16 KB]
+  uint8_t* b_ring = smem + (size_t)kPKB * kPSlotBytes;              // [stage][hi 16 KB | lo 16 KB], 128 weight rows each
+  uint8_t* c_stage = b_ring + (size_t)kPBStages * kPBStageBytes;    // 4 epilogue warps x [32 rows x 128 B]
+  __shared__ uint64_t a_full[kPKB], a_empty[kPKB], b_full[kPBStages], b_empty[kPBStages], peer_bar[kPBStages];
+  __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float bias_s[kFMaxGroups * kPN], bscale_s[kFMaxGroups * kPN];
+  __shared__ float row_descale[kFScaleSlots][kFBlockM];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int64_t num_pair_tiles = (p.M + 2 * kFBlockM - 1) / (2 * kFBlockM);
+  const int64_t num_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+  const int64_t my_steps = cluster_id < num_pair_tiles ? (num_pair_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
+  const int groups = p.groups;
+
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < kPKB; ++k) { mbar_init(&a_full[k], 256); mbar_init(&a_empty[k], 1); }
+    for (int s = 0; s < kPBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); mbar_init(&peer_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }   // 4 epilogue warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int j = threadIdx.x; j < groups * kPN; j += kFThreads) {
+    bias_s[j] = p.bias ? p.bias[j] : 0.f;
+    bscale_s[j] = p.b_scale[j];
+  }
+  if (warp == 1) {        // one warp of EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA: this CTA's 128 rows of the group's weights, K block by K block =====================
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t vt = 0; vt < my_steps * groups; ++vt) {
+        const int b_row0 = (int)(vt % groups) * kPN + (int)cta_rank * (kPN / 2);
+        for (int kb = 0; kb < kPKB; ++kb) {
+          mbar_wait(&b_empty[stage], phase ^ 1);
+          uint8_t* st = b_ring + (size_t)stage * kPBStageBytes;
+          mbar_expect_tx(&b_full[stage], kPBStageBytes);
+          tma_load_2d(st, &map_bhi, &b_full[stage], kb * kFBlockK, b_row0);
+          tma_load_2d(st + kPBPlaneBytes, &map_blo, &b_full[stage], kb * kFBlockK, b_row0);
+          if (++stage == kPBStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      if (cta_rank != 0) {
+        // ===================== relay (peer CTA): "my B half and my A block are in place" -> the leader =====================
+        for (int64_t it = 0; it < my_steps; ++it) {
+          for (int g = 0; g < groups; ++g) {
+            for (int kb = 0; kb < kPKB; ++kb) {
+              mbar_wait(&b_full[stage], phase);
+              if (g == 0) mbar_wait(&a_full[kb], (uint32_t)(it & 1));
+              asm volatile("fence.acq_rel.cluster;" ::: "memory");
+              mbar_arrive_remote(&peer_bar[stage], 0);
+              if (++stage == kPBStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      } else {
+        // ===================== MMA issuer (leader CTA), M = 256 over the pair =====================
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(kPN >> 3) << 17) | ((uint32_t)((2 * kFBlockM) >> 4) << 24);
+        int acc = 0; uint32_t acc_phase = 0;
+        const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_ring);
+        for (int64_t it = 0; it < my_steps; ++it) {
+          for (int g = 0; g < groups; ++g) {
+            mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kPN);
+            for (int kb = 0; kb < kPKB; ++kb) {
+              mbar_wait(&b_full[stage], phase);
+              if (g == 0) mbar_wait(&a_full[kb], (uint32_t)(it & 1));
+              mbar_wait_cluster(&peer_bar[stage], phase);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t a_hi = a_base + (uint32_t)kb * kPSlotBytes, a_lo = a_hi + kFATileBytes;
+              const uint32_t b_hi = b_base + (uint32_t)stage * kPBStageBytes, b_lo = b_hi + kPBPlaneBytes;
+#pragma unroll
+              for (int k = 0; k < kFBlockK / kFUmmaK; ++k) {
+                const uint32_t koff = k * kFUmmaK * 2;
+                umma_f16_pair(d_tmem, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, (kb == 0 && k == 0) ? 0u : 1u);
+                umma_f16_pair(d_tmem, make_desc(a_lo + koff), make_desc(b_hi + koff), idesc, 1u);
+                umma_f16_pair(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), idesc, 1u);
+              }
+              umma_commit_pair(&b_empty[stage]);
+              if (g == groups - 1) umma_commit_pair(&a_empty[kb]);      // the last group is done with this K block of A
+              if (kb == kPKB - 1) umma_commit_pair(&tmem_full_bar[acc]);
+              if (++stage == kPBStages) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp < 12) {
+    // ===================== A producers: this CTA's 128 rows, converted once per tile =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;" ::: "memory");
+    const int t = threadIdx.x - 128;
+    const int q = t & 15, rg = t >> 4;
+    uint32_t soff[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = rg + 16 * i;
+      soff[i] = (uint32_t)(row * 128 + ((((q >> 1) ^ (row & 7))) << 4) + ((q & 1) << 3));
+    }
+    const uint32_t ring_base = smem_u32(a_ring);
+    const uint32_t toff = (uint32_t)(rg * p.lda + q * 4), tstep = (uint32_t)(16 * p.lda);
+    float4 buf[kPKB][8];
+    auto load_block = [&](int64_t it, int kb, float4 (&v)[8]) {
+      const int64_t row0 = ((cluster_id + it * num_clusters) * 2 + cta_rank) * kFBlockM;
+      if (it < my_steps && row0 + kFBlockM <= p.M) {
+        const float* base = p.A + row0 * p.lda + kb * kFBlockK;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = ld_stream4(base + (toff + (uint32_t)i * tstep));
+        return;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t row = row0 + rg + 16 * i;
+        v[i] = (it < my_steps && row < p.M) ? ld_stream4(p.A + row * p.lda + kb * kFBlockK + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+#pragma unroll
+    for (int kb = 0; kb < kPKB; ++kb) load_block(0, kb, buf[kb]);
+    float seen_max = 0.f;
+    for (int64_t it = 0; it < my_steps; ++it) {
+      float scale[8];
+      float* descale_slot = row_descale[it & (kFScaleSlots - 1)];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float m = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < kPKB; ++kb)
+          m = fmaxf(m, fmaxf(fmaxf(fabsf(buf[kb][i].x), fabsf(buf[kb][i].y)), fmaxf(fabsf(buf[kb][i].z), fabsf(buf[kb][i].w))));
+#pragma unroll
+        for (int off = 1; off < 16; off <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        float descale;
+        seen_max = fmaxf(seen_max, m);
+        row_scale_from_amax(m, scale[i], descale);
+        if (q == 0) descale_slot[rg + 16 * i] = descale;
+      }
+#pragma unroll
+      for (int kb = 0; kb < kPKB; ++kb) {
+        mbar_wait(&a_empty[kb], (uint32_t)((it & 1) ^ 1));       // every group of the previous tile has read this slot
+        const uint32_t sb = ring_base + (uint32_t)kb * kPSlotBytes;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float s = scale[i];
+          const float x0 = buf[kb][i].x * s, x1 = buf[kb][i].y * s, x2 = buf[kb][i].z * s, x3 = buf[kb][i].w * s;
+          const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+          const uint32_t addr = sb + soff[i];
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
+                       "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
+          asm volatile("st.shared.v2.b32 [%0+%3], {%1, %2};" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&l01)),
+                       "r"(*reinterpret_cast<const uint32_t*>(&l23)), "n"(kFATileBytes) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&a_full[kb]);
+        load_block(it + 1, kb, buf[kb]);                         // the freed registers take the next tile's K block
+      }
+    }
+    if (p.a_amax != nullptr) warp_amax_to_global(seen_max, p.a_amax);
+  } else {
+    // ===================== epilogue: this CTA's 128 accumulator rows (warp -> TMEM lane quarter) =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");
+    const int quarter = warp & 3;
+    const uint32_t stg = smem_u32(c_stage + (warp - 12) * 4096);   // [32 rows x 128 B], 16-byte chunk ^= row % 8
+    const int pc = lane & 3, rsub = lane >> 2;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int64_t it = 0; it < my_steps; ++it) {
+      const int64_t row0 = ((cluster_id + it * num_clusters) * 2 + cta_rank) * kFBlockM + quarter * 32;
+      for (int g = 0; g < groups; ++g) {
+        const float* bias_g = bias_s + g * kPN;
+        const float* bscale_g = bscale_s + g * kPN;
+        float* c_grp = p.C + (int64_t)g * kPN;
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float rs[4];                                             // row descale of the 4 rows this lane stores
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rs[i] = row_descale[it & (kFScaleSlots - 1)][quarter * 32 + 8 * i + rsub];
+        const uint32_t taddr0 = tmem_base + (uint32_t)(acc * kPN) + ((uint32_t)(quarter * 32) << 16);
+        for (int c0 = 0; c0 < kPN; c0 += 32) {
+          uint32_t r[32];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr0 + (uint32_t)c0));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          __syncwarp();                                  // the previous chunk's read-back is complete
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)                // lane = row: raw accumulators into the swizzled staging tile
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + (uint32_t)(lane * 128 + ((((j >> 2) ^ (lane & 7))) << 4))),
+                         "r"(r[j]), "r"(r[j + 1]), "r"(r[j + 2]), "r"(r[j + 3]) : "memory");
+          __syncwarp();
+          // lane = (row rsub + 8 i, columns col .. col + 7): descale by row and column, add the bias, 256-bit stores
+          const int col = c0 + 8 * pc;
+          const float4 cs0 = *reinterpret_cast<const float4*>(&bscale_g[col]), cs1 = *reinterpret_cast<const float4*>(&bscale_g[col + 4]);
+          const float4 bs0 = *reinterpret_cast<const float4*>(&bias_g[col]), bs1 = *reinterpret_cast<const float4*>(&bias_g[col + 4]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + rsub;
+            const int64_t grow = row0 + rr;
+            float4 v, w;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"(stg + (uint32_t)(rr * 128 + (((2 * pc) ^ (rr & 7)) << 4))) : "memory");
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
+                         : "r"(stg + (uint32_t)(rr * 128 + (((2 * pc + 1) ^ (rr & 7)) << 4))) : "memory");
+            if (grow < p.M) {
+              const float f = rs[i];
+              float* dst = c_grp + grow * p.ldc + col;
+              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(fmaf(v.x, f * cs0.x, bs0.x)),
+                           "f"(fmaf(v.y, f * cs0.y, bs0.y)), "f"(fmaf(v.z, f * cs0.z, bs0.z)), "f"(fmaf(v.w, f * cs0.w, bs0.w)),
+                           "f"(fmaf(w.x, f * cs1.x, bs1.x)), "f"(fmaf(w.y, f * cs1.y, bs1.y)), "f"(fmaf(w.z, f * cs1.z, bs1.z)),
+                           "f"(fmaf(w.w, f * cs1.w, bs1.w))
+                           : "memory");
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[acc], 0);       // the leader's MMA thread owns the accumulator hand-back
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+  __syncthreads();
+  cluster_sync();                            // neither CTA leaves (or frees TMEM) while the pair's MMAs / remote arrives are in flight
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // One warp per weight row n: t_n = 2^(14 - floor(log2 max_k |W[n,k]|)); hi = fp16(t W), lo = fp16(t W - hi); descale[n] = 1/t_n
 __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ w, int n_rows, int k, __half* __restrict__ hi,
                                                         __half* __restrict__ lo, float* __restrict__ descale) {
@@ -592,11 +904,26 @@ static int linear_f16x2_impl(const float* A, int64_t lda, const void* B_hi, cons
   const int grid = (int)(pairs < kNumSMs / kFCluster ? pairs : kNumSMs / kFCluster) * kFCluster;
   static int debug = -1;
   if (debug < 0) { const char* env = getenv("GASFM_GEMM_DEBUG"); debug = env ? atoi(env) : 0; }
+  static int use_pair = -1;                   // GASFM_GEMM_PAIR=0: the cta_group::1 kernel for every shape (A/B switch)
+  if (use_pair < 0) { const char* env = getenv("GASFM_GEMM_PAIR"); use_pair = env ? atoi(env) : 1; }
   if (a_amax != nullptr) cudaMemsetAsync(a_amax, 0, sizeof(float), (cudaStream_t)stream);
   GemmF16Args args{};
   args.A = A; args.lda = lda; args.b_scale = b_descale; args.bias = bias; args.C = C; args.ldc = ldc; args.M = M; args.N = N; args.K = K;
   args.groups = groups; args.tmem_cols = tmem_cols; args.accumulate = accumulate; args.debug = debug; args.a_amax = a_amax;
   args.ln_gamma = ln_gamma; args.ln_beta = ln_beta; args.ln_eps = ln_eps; args.ln_mean = ln_mean; args.ln_rstd = ln_rstd; args.trace = g_trace;
+  if (use_pair && !ln && !accumulate && N == kPN && K == kPKB * kFBlockK && ldc % 8 == 0 && (uintptr_t)C % 32 == 0 && debug == 0 &&
+      g_trace == nullptr) {
+    // the shipped block shape: CTA pairs on one cta_group::2 MMA stream, A converted once per tile for all groups
+    const int64_t pair_tiles = (M + 2 * kFBlockM - 1) / (2 * kFBlockM);
+    const int pgrid = (int)(pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2) * 2;
+    cudaError_t e = cudaFuncSetAttribute(gemm_f16x2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("linear_f16x2: cannot reserve %zu bytes of shared memory (%s)", kPSmemBytes, cudaGetErrorString(e));
+      return (int)e;
+    }
+    gemm_f16x2_pair_kernel<<<pgrid, kFThreads, kPSmemBytes, (cudaStream_t)stream>>>(mh, ml, args);
+    return check_launch("linear_f16x2 (pair)");
+  }
 #define LAUNCH_F16(KB, LNV)                                                                                                \
   do {                                                                                                                     \
     /* per-device attribute: set on every call (static smem -- barriers, scales -- also counts against the 227 KB limit) */ \

@@ -22,6 +22,43 @@ def _pow2ceil(x):
     return p
 
 
+class _DeferredValidation:
+    """While active, ``ObservationIndex`` does not read its status word back (no host synchronisation, so the build can be
+    captured into a CUDA graph); the status tensors are collected here and checked later with ``check``."""
+    active = None
+
+    def __init__(self):
+        self.entries = []          # (status tensor, m, n)
+
+    def __enter__(self):
+        self._outer, _DeferredValidation.active = _DeferredValidation.active, self
+        return self
+
+    def __exit__(self, *exc):
+        _DeferredValidation.active = self._outer
+        return False
+
+
+def deferred_validation():
+    return _DeferredValidation()
+
+
+def raise_for_status(st, m, n):
+    if st & 1:
+        raise ValueError("observation indices out of range for an (m=%d, n=%d) scene" % (m, n))
+    if st & 2:
+        raise ValueError("observation indices must be row-major sorted without duplicates "
+                         "(the order np.nonzero / coalesce() produce)")
+
+
+def one_segment_ptr(k, device):
+    """int32 [0, k] built by device fills (``torch.tensor([0, k], device=...)`` is a pageable host copy, which a stream
+    capture refuses)."""
+    seg_ptr = torch.full((2,), int(k), dtype=torch.int32, device=device)
+    seg_ptr[:1].zero_()
+    return seg_ptr
+
+
 class SegmentPlan:
     """One aggregation graph as segments over observation rows (see include/gasfm_b200.h)."""
 
@@ -98,13 +135,11 @@ class ObservationIndex:
             _lib.call("gasfm_csr_build", _lib.ptr(indices), E, self.m, self.n, _lib.ptr(self.row_idx),
                       _lib.ptr(self.col_idx), _lib.ptr(self.row_ptr), _lib.ptr(self.col_ptr),
                       _lib.ptr(self.csc_perm), _lib.ptr(status), _lib.ptr(ws), _lib.stream_ptr())
-            if validate:
-                st = int(status.item())
-                if st & 1:
-                    raise ValueError("observation indices out of range for an (m=%d, n=%d) scene" % (m, n))
-                if st & 2:
-                    raise ValueError("observation indices must be row-major sorted without duplicates "
-                                     "(the order np.nonzero / coalesce() produce)")
+            self.status = status
+            if _DeferredValidation.active is not None:
+                _DeferredValidation.active.entries.append((status, self.m, self.n))
+            elif validate:
+                raise_for_status(int(status.item()), self.m, self.n)
             # views: long contiguous segments -> chunked; tracks: short gathered segments
             self.by_view = SegmentPlan(self.row_ptr, None, self.m, E, csr_chunk(E), dev)
             self.by_track = SegmentPlan(self.col_ptr, self.csc_perm, self.n, E, 0, dev)
@@ -121,7 +156,7 @@ class ObservationIndex:
             dev = self.device
             k = int(valid_ids.numel())
             total = self.m if kind == "view" else self.n
-            seg_ptr = torch.tensor([0, k], dtype=torch.int32, device=dev)
+            seg_ptr = one_segment_ptr(k, dev)
             perm = None if k == total else valid_ids.to(torch.int32)
             with _lib.device_guard(dev):
                 plan = SegmentPlan(seg_ptr, perm, 1, k, single_segment_chunk(k), dev)

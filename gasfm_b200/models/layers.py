@@ -19,7 +19,7 @@ from torch.nn import ReLU, Sequential, Module, Identity
 from torch.nn import functional as F
 
 from .. import _lib, ops
-from ..index import SegmentPlan, index_for, single_segment_chunk
+from ..index import SegmentPlan, index_for, one_segment_ptr, single_segment_chunk
 from ..utils.sparse_utils import SparseMat
 from ..utils import sparse_utils
 from ..utils.pos_enc_utils import get_embedder
@@ -108,7 +108,7 @@ def plan_for(graph_wrapper, proj_features=None):
             dev = ids.device
             k = int(ids.numel())
             n_src = graph_wrapper.m if graph_wrapper.agg_dim == 0 else graph_wrapper.n
-            seg_ptr = torch.tensor([0, k], dtype=torch.int32, device=dev)
+            seg_ptr = one_segment_ptr(k, dev)
             perm = None if k == n_src else ids.to(torch.int32).contiguous()
             with _lib.device_guard(dev):
                 plan = SegmentPlan(seg_ptr, perm, 1, k, single_segment_chunk(k), dev)

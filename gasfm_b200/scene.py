@@ -54,7 +54,15 @@ class Scene:
         kwargs.pop("dense_on_demand", None)
         ret = copy.copy(self)
         ret.x = self.x.to(device, **kwargs)
-        ret.graph_wrappers = {k: w.to(device, **kwargs) for k, w in self.graph_wrappers.items()}
+        ret.graph_wrappers = {}
+        for k, w in self.graph_wrappers.items():
+            if w.valid_indices is self.x.indices:
+                # proj2view / proj2scenepoint list the observations themselves: share the moved tensor, do not copy it again
+                w = copy.copy(w)
+                w.device, w.valid_indices, w._edge_index = device, ret.x.indices, None
+                ret.graph_wrappers[k] = w
+            else:
+                ret.graph_wrappers[k] = w.to(device, **kwargs)
         for key in ("y", "Ns", "obs"):
             v = getattr(self, key)
             if torch.is_tensor(v):
@@ -73,6 +81,45 @@ class Scene:
         idx.shard = getattr(self, "shard", None)
         for key in ("view2global", "scenepoint2global"):
             plan_for(self.graph_wrappers[key])
+        return self
+
+    def _buffers(self):
+        """The tensors a step reads from the scene, by name (aliases of ``x.indices`` listed once)."""
+        out = {"values": self.x.values, "indices": self.x.indices, "cam_per_pts": self.x.cam_per_pts, "pts_per_cam": self.x.pts_per_cam}
+        for k in ("view2global", "scenepoint2global"):
+            out[k] = self.graph_wrappers[k].valid_indices
+        for k in ("y", "Ns", "obs"):
+            if torch.is_tensor(getattr(self, k)):
+                out[k] = getattr(self, k)
+        return out
+
+    def signature(self):
+        """What has to agree for one scene to be written over another in place (``copy_from``): the shapes of every
+        buffer -- i.e. (m, n, E) and the number of valid views / tracks of the two global graphs."""
+        return tuple(self.x.shape) + tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(self._buffers().items()))
+
+    def copy_from(self, other, non_blocking=True):
+        """Overwrite this scene's tensors IN PLACE with ``other``'s (same ``signature()``; typically a pinned host scene
+        into the device scene a captured step reads, ``gasfm_b200.graphs.StreamedStep``).  Cached indices / plans on this
+        scene become stale: the captured step rebuilds them at the same addresses."""
+        if self.signature() != other.signature():
+            raise ValueError("Scene.copy_from: the scenes differ in shape (m, n, E or the number of valid views / tracks)")
+        src = other._buffers()
+        for k, dst in self._buffers().items():
+            dst.copy_(src[k], non_blocking=non_blocking)
+        self.scene_name = other.scene_name
+        return self
+
+    def invalidate(self):
+        """Forget the cached observation index and global plans (after the index tensors were rewritten in place)."""
+        from .index import _INDEX_ATTR
+        from .models.layers import _PLAN_ATTR
+        for holder in (self, self.x):
+            if hasattr(holder, _INDEX_ATTR):
+                delattr(holder, _INDEX_ATTR)
+        for w in self.graph_wrappers.values():
+            if hasattr(w, _PLAN_ATTR):
+                delattr(w, _PLAN_ATTR)
         return self
 
     def pin_memory(self):

@@ -208,3 +208,55 @@ def test_activation_recompute_gives_identical_results(ln_fused, monkeypatch):
         assert torch.equal(g, res["on"][2][k]), k
     # activations held between forward and backward: each of the two fused blocks drops its three projections (and relu(LN(x)))
     assert res["off"][3] - res["on"][3] > 2 * 2.5 * idx.shape[1] * 128 * 4
+
+
+def _mirrored_tracks(idx, vals, n):
+    """The same scene with the tracks renumbered back to front: same (m, n, E) and valid counts, different index arrays."""
+    cols = n - 1 - idx[1]
+    order = np.lexsort((cols, idx[0]))
+    return np.stack((idx[0][order], cols[order])), np.ascontiguousarray(vals[order])
+
+
+def test_streamed_step_serves_new_scenes_from_one_captured_graph():
+    """``StreamedStep``: host scene -> H2D into the captured buffers -> ONE graph replay (index build, forward, loss, backward)
+    -> host results.  A second scene of the same signature but different indices AND values must give what the eager model gives
+    on it (outputs, loss, every gradient); a scene of another shape and a malformed index must raise."""
+    from gasfm_b200.graphs import StreamedStep
+    conf = gasfm_conf(n_feat_proj=64, n_feat_view=64, n_feat_global=64, num_layers=2)
+    torch.manual_seed(3)
+    model = GraphAttnSfMNet(conf).to(DEV)
+    m, n = 16, 1200
+    idx_a, vals_a = gasfm_cpu.synthetic_observations(m, n, 9000, seed=5)
+    idx_b, vals_b = _mirrored_tracks(idx_a, vals_a * 0.7 + 0.05, n)
+    host_a = Scene.from_observations(idx_a, vals_a, m, n).pin_memory()
+    host_b = Scene.from_observations(idx_b, vals_b, m, n).pin_memory()
+    assert host_a.signature() == host_b.signature() and not np.array_equal(idx_a, idx_b)
+    import copy
+    eager = copy.deepcopy(model)
+    step = StreamedStep(model, host_a, _loss)
+    for host in (host_b, host_a, host_b):
+        res = step(host)
+        got = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+        eager.zero_grad(set_to_none=True)
+        out = eager(host.to(DEV))
+        loss = _loss(out)
+        loss.backward()
+        for key in ("Ps_norm", "pts3D"):
+            assert torch.equal(res[key], out[key].detach().cpu()), key
+        assert res["loss"] == float(loss.detach())
+        # a few reductions use float atomics: gradients agree up to summation order (cancelling sums over ~9k observations)
+        worst = max((float((got[k] - p.grad).abs().max()) / max(1.0, float(p.grad.abs().max())), k) for k, p in eager.named_parameters())
+        assert worst[0] < 1e-4, worst
+    assert step.h2d_bytes == idx_a.size * 8 + vals_a.size * 4 + (m + n) * 8 + \
+        sum(host_a.graph_wrappers[k].valid_indices.numel() * 8 for k in ("view2global", "scenepoint2global"))
+    # another shape: refused before anything is copied
+    idx_c, vals_c = gasfm_cpu.synthetic_observations(m, n, 8000, seed=6)
+    with pytest.raises(ValueError, match="differ in shape"):
+        step(Scene.from_observations(idx_c, vals_c, m, n))
+    # malformed index (two observations swapped: not row-major sorted): reported when the status word comes back
+    bad = Scene.from_observations(idx_a, vals_a, m, n)
+    bad.x.indices[:, [10, 11]] = bad.x.indices[:, [11, 10]]
+    with pytest.raises(ValueError, match="row-major sorted"):
+        step(bad)
+    res = step(host_a)                                       # and the step is usable afterwards
+    assert np.isfinite(res["loss"])
