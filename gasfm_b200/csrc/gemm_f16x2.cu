@@ -567,11 +567,41 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "memory");
   } while (!done);
 }
-// arrive on the barrier at this shared-memory offset in CTA ``rank`` of the cluster
+// wait with a back-off between polls: every failed try_wait is a shared-memory wavefront, and the roles that wait long
+// (A producers two thirds of the time, the TMA thread, the epilogue) polled ~290 M times per launch in the first version of
+// this kernel -- as many wavefronts as the whole epilogue read-back
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  const uint32_t addr = smem_u32(bar);
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+  }
+}
+// the same without publishing this thread's earlier writes (nothing but the arrival itself is communicated): no memory barrier
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t rank) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// arrive on the barrier at this shared-memory offset in CTA ``rank`` of the cluster.  Default semantics (release at CTA
+// scope): what is handed over lives in this CTA's shared memory and is already complete when the arrive is issued (it was
+// itself observed through an mbarrier).  A cluster-scope release compiles to MEMBAR.ALL.GPU, which waits for the SM's
+// outstanding GLOBAL stores -- the epilogue streams them continuously -- and cost ~2,600 cycles per K block on the relay
+// (device timeline, profiles/r02_gemm_pair.md).
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   uint32_t raddr;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -589,6 +619,15 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {      // arrive
                : "memory");
 }
 
+// profiling (tools/gemm_pair_trace.py): SM-clock timestamps of cluster 0, [cta 2][role 4][virtual tile 32][slot 16]
+constexpr int kPTraceTiles = 32;
+#define GASFM_PTRACE(role, vt, slot)                                                                             \
+  do {                                                                                                           \
+    if (TRACE && p.trace && blockIdx.x < 2 && (vt) < kPTraceTiles)                                               \
+      p.trace[(((int64_t)blockIdx.x * 4 + (role)) * kPTraceTiles + (vt)) * 16 + (slot)] = clock64();             \
+  } while (0)
+
+template <bool TRACE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1)
 gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, GemmF16Args p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -637,7 +676,8 @@ gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid
       for (int64_t vt = 0; vt < my_steps * groups; ++vt) {
         const int b_row0 = (int)(vt % groups) * kPN + (int)cta_rank * (kPN / 2);
         for (int kb = 0; kb < kPKB; ++kb) {
-          mbar_wait(&b_empty[stage], phase ^ 1);
+          mbar_wait_backoff(&b_empty[stage], phase ^ 1, 32);
+          GASFM_PTRACE(3, vt, kb);
           uint8_t* st = b_ring + (size_t)stage * kPBStageBytes;
           mbar_expect_tx(&b_full[stage], kPBStageBytes);
           tma_load_2d(st, &map_bhi, &b_full[stage], kb * kFBlockK, b_row0);
@@ -652,9 +692,8 @@ gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid
         for (int64_t it = 0; it < my_steps; ++it) {
           for (int g = 0; g < groups; ++g) {
             for (int kb = 0; kb < kPKB; ++kb) {
-              mbar_wait(&b_full[stage], phase);
-              if (g == 0) mbar_wait(&a_full[kb], (uint32_t)(it & 1));
-              asm volatile("fence.acq_rel.cluster;" ::: "memory");
+              mbar_wait_backoff(&b_full[stage], phase, 20);
+              if (g == 0) mbar_wait_backoff(&a_full[kb], (uint32_t)(it & 1), 20);
               mbar_arrive_remote(&peer_bar[stage], 0);
               if (++stage == kPBStages) { stage = 0; phase ^= 1; }
             }
@@ -669,11 +708,15 @@ gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid
           for (int g = 0; g < groups; ++g) {
             mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            GASFM_PTRACE(1, it * groups + g, 0);
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kPN);
             for (int kb = 0; kb < kPKB; ++kb) {
               mbar_wait(&b_full[stage], phase);
+              GASFM_PTRACE(1, it * groups + g, 1 + kb);
               if (g == 0) mbar_wait(&a_full[kb], (uint32_t)(it & 1));
+              GASFM_PTRACE(1, it * groups + g, 5 + kb);
               mbar_wait_cluster(&peer_bar[stage], phase);
+              GASFM_PTRACE(1, it * groups + g, 9 + kb);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               const uint32_t a_hi = a_base + (uint32_t)kb * kPSlotBytes, a_lo = a_hi + kFATileBytes;
               const uint32_t b_hi = b_base + (uint32_t)stage * kPBStageBytes, b_lo = b_hi + kPBPlaneBytes;
@@ -743,7 +786,11 @@ gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid
       }
 #pragma unroll
       for (int kb = 0; kb < kPKB; ++kb) {
-        mbar_wait(&a_empty[kb], (uint32_t)((it & 1) ^ 1));       // every group of the previous tile has read this slot
+        // every group of the previous tile has read this slot.  ONE lane polls the mbarrier, the other producer warps block on
+        // a named barrier (256 polling threads made 212 M shared-memory wavefronts per launch)
+        if (t == 0) mbar_wait_backoff(&a_empty[kb], (uint32_t)((it & 1) ^ 1), 64);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (t == 0) GASFM_PTRACE(0, it * groups, kb);
         const uint32_t sb = ring_base + (uint32_t)kb * kPSlotBytes;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -760,6 +807,7 @@ gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(&a_full[kb]);
+        if (t == 0) GASFM_PTRACE(0, it * groups, 4 + kb);
         load_block(it + 1, kb, buf[kb]);                         // the freed registers take the next tile's K block
       }
     }
@@ -770,63 +818,84 @@ gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid
     const int quarter = warp & 3;
     const uint32_t stg = smem_u32(c_stage + (warp - 12) * 4096);   // [32 rows x 128 B], 16-byte chunk ^= row % 8
     const int pc = lane & 3, rsub = lane >> 2;
+    // everything that does not change from chunk to chunk is computed once (the first version spent ~270 instructions per
+    // 32-column chunk, two thirds of them on addresses and predicates, and the epilogue warps' issue latency paced the kernel):
+    // write side, lane = row: 16-byte piece k of the row goes to chunk k ^ (row % 8) -> one XOR per store
+    const uint32_t sts_base = stg + (uint32_t)(lane * 128 + ((lane & 7) << 4));
+    // read side, lane = (rows rsub + 8 i, 32-byte piece pc): row % 8 == rsub for all four rows -> two bases + immediates
+    const uint32_t lds_v = stg + (uint32_t)(rsub * 128 + (((2 * pc) ^ rsub) << 4)), lds_w = lds_v ^ 16u;
+    const uint32_t cs_base = smem_u32(bscale_s) + (uint32_t)(pc * 32), bs_base = smem_u32(bias_s) + (uint32_t)(pc * 32);
     int acc = 0; uint32_t acc_phase = 0;
     for (int64_t it = 0; it < my_steps; ++it) {
       const int64_t row0 = ((cluster_id + it * num_clusters) * 2 + cta_rank) * kFBlockM + quarter * 32;
+      float rs[4];                                               // row descale of the 4 rows this lane stores
+      float* rowp[4];
+      const int rows_left = (int)((p.M - row0) < 32 ? (p.M - row0) : 32) - rsub;      // row 8 i + rsub exists iff 8 i < rows_left
       for (int g = 0; g < groups; ++g) {
-        const float* bias_g = bias_s + g * kPN;
-        const float* bscale_g = bscale_s + g * kPN;
-        float* c_grp = p.C + (int64_t)g * kPN;
-        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        mbar_wait_backoff(&tmem_full_bar[acc], acc_phase, 32);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float rs[4];                                             // row descale of the 4 rows this lane stores
+        if (warp == 12 && lane == 0) GASFM_PTRACE(2, it * groups + g, 0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rs[i] = row_descale[it & (kFScaleSlots - 1)][quarter * 32 + 8 * i + rsub];
+        for (int i = 0; i < 4; ++i) {
+          const int64_t grow = row0 + 8 * i + rsub;
+          rs[i] = row_descale[it & (kFScaleSlots - 1)][quarter * 32 + 8 * i + rsub];
+          rowp[i] = p.C + grow * p.ldc + g * kPN + 8 * pc;
+        }
+        const uint32_t csg = cs_base + (uint32_t)g * (kPN * 4), bsg = bs_base + (uint32_t)g * (kPN * 4);
         const uint32_t taddr0 = tmem_base + (uint32_t)(acc * kPN) + ((uint32_t)(quarter * 32) << 16);
+        // 32-column chunks: TMEM -> registers (lane = row) -> swizzled staging tile -> registers (lane = 8 columns of 4 rows)
+        // -> descale by row and column, bias -> 256-bit stores.  The next chunk's TMEM read is issued as soon as the registers
+        // are free, and all read-back loads of a chunk are issued before the first result is used.
+        uint32_t r[32];
+#define GASFM_TMEM_LD32(ADDR)                                                                                                  \
+        asm volatile(                                                                                                          \
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                          \
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),      \
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),           \
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),          \
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                        \
+            : "r"(ADDR))
+#define GASFM_LDS4(V, ADDR) \
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"((V).x), "=f"((V).y), "=f"((V).z), "=f"((V).w) : "r"(ADDR) : "memory")
+        GASFM_TMEM_LD32(taddr0);
+#pragma unroll
         for (int c0 = 0; c0 < kPN; c0 += 32) {
-          uint32_t r[32];
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-              : "r"(taddr0 + (uint32_t)c0));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           __syncwarp();                                  // the previous chunk's read-back is complete
+          if (warp == 12 && lane == 0) GASFM_PTRACE(2, it * groups + g, 2 + (c0 >> 5));
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)                // lane = row: raw accumulators into the swizzled staging tile
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(stg + (uint32_t)(lane * 128 + ((((j >> 2) ^ (lane & 7))) << 4))),
-                         "r"(r[j]), "r"(r[j + 1]), "r"(r[j + 2]), "r"(r[j + 3]) : "memory");
+          for (int k = 0; k < 8; ++k)                    // lane = row: raw accumulators into the swizzled staging tile
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sts_base ^ (uint32_t)(k << 4)), "r"(r[4 * k]), "r"(r[4 * k + 1]),
+                         "r"(r[4 * k + 2]), "r"(r[4 * k + 3]) : "memory");
           __syncwarp();
-          // lane = (row rsub + 8 i, columns col .. col + 7): descale by row and column, add the bias, 256-bit stores
-          const int col = c0 + 8 * pc;
-          const float4 cs0 = *reinterpret_cast<const float4*>(&bscale_g[col]), cs1 = *reinterpret_cast<const float4*>(&bscale_g[col + 4]);
-          const float4 bs0 = *reinterpret_cast<const float4*>(&bias_g[col]), bs1 = *reinterpret_cast<const float4*>(&bias_g[col + 4]);
+          if (c0 + 32 < kPN) GASFM_TMEM_LD32(taddr0 + (uint32_t)(c0 + 32));      // overlaps the read-back below
+          float4 v[4], w[4], cs0, cs1, bs0, bs1;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int rr = 8 * i + rsub;
-            const int64_t grow = row0 + rr;
-            float4 v, w;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                         : "r"(stg + (uint32_t)(rr * 128 + (((2 * pc) ^ (rr & 7)) << 4))) : "memory");
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(w.x), "=f"(w.y), "=f"(w.z), "=f"(w.w)
-                         : "r"(stg + (uint32_t)(rr * 128 + (((2 * pc + 1) ^ (rr & 7)) << 4))) : "memory");
-            if (grow < p.M) {
+            GASFM_LDS4(v[i], lds_v + (uint32_t)(i * 1024));
+            GASFM_LDS4(w[i], lds_w + (uint32_t)(i * 1024));
+          }
+          GASFM_LDS4(cs0, csg + (uint32_t)(c0 * 4)); GASFM_LDS4(cs1, csg + (uint32_t)(c0 * 4 + 16));
+          GASFM_LDS4(bs0, bsg + (uint32_t)(c0 * 4)); GASFM_LDS4(bs1, bsg + (uint32_t)(c0 * 4 + 16));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (8 * i < rows_left) {
               const float f = rs[i];
-              float* dst = c_grp + grow * p.ldc + col;
-              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(fmaf(v.x, f * cs0.x, bs0.x)),
-                           "f"(fmaf(v.y, f * cs0.y, bs0.y)), "f"(fmaf(v.z, f * cs0.z, bs0.z)), "f"(fmaf(v.w, f * cs0.w, bs0.w)),
-                           "f"(fmaf(w.x, f * cs1.x, bs1.x)), "f"(fmaf(w.y, f * cs1.y, bs1.y)), "f"(fmaf(w.z, f * cs1.z, bs1.z)),
-                           "f"(fmaf(w.w, f * cs1.w, bs1.w))
+              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(rowp[i] + c0), "f"(fmaf(v[i].x, f * cs0.x, bs0.x)),
+                           "f"(fmaf(v[i].y, f * cs0.y, bs0.y)), "f"(fmaf(v[i].z, f * cs0.z, bs0.z)), "f"(fmaf(v[i].w, f * cs0.w, bs0.w)),
+                           "f"(fmaf(w[i].x, f * cs1.x, bs1.x)), "f"(fmaf(w[i].y, f * cs1.y, bs1.y)), "f"(fmaf(w[i].z, f * cs1.z, bs1.z)),
+                           "f"(fmaf(w[i].w, f * cs1.w, bs1.w))
                            : "memory");
             }
           }
         }
+#undef GASFM_TMEM_LD32
+#undef GASFM_LDS4
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[acc], 0);       // the leader's MMA thread owns the accumulator hand-back
+        if (lane == 0) mbar_arrive_remote_relaxed(&tmem_empty_bar[acc], 0);   // the leader's MMA thread owns the accumulator hand-back
+        if (warp == 12 && lane == 0) GASFM_PTRACE(2, it * groups + g, 1);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -911,17 +980,17 @@ static int linear_f16x2_impl(const float* A, int64_t lda, const void* B_hi, cons
   args.A = A; args.lda = lda; args.b_scale = b_descale; args.bias = bias; args.C = C; args.ldc = ldc; args.M = M; args.N = N; args.K = K;
   args.groups = groups; args.tmem_cols = tmem_cols; args.accumulate = accumulate; args.debug = debug; args.a_amax = a_amax;
   args.ln_gamma = ln_gamma; args.ln_beta = ln_beta; args.ln_eps = ln_eps; args.ln_mean = ln_mean; args.ln_rstd = ln_rstd; args.trace = g_trace;
-  if (use_pair && !ln && !accumulate && N == kPN && K == kPKB * kFBlockK && ldc % 8 == 0 && (uintptr_t)C % 32 == 0 && debug == 0 &&
-      g_trace == nullptr) {
+  if (use_pair && !ln && !accumulate && N == kPN && K == kPKB * kFBlockK && ldc % 8 == 0 && (uintptr_t)C % 32 == 0 && debug == 0) {
     // the shipped block shape: CTA pairs on one cta_group::2 MMA stream, A converted once per tile for all groups
     const int64_t pair_tiles = (M + 2 * kFBlockM - 1) / (2 * kFBlockM);
     const int pgrid = (int)(pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2) * 2;
-    cudaError_t e = cudaFuncSetAttribute(gemm_f16x2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmemBytes);
+    auto kernel = g_trace ? gemm_f16x2_pair_kernel<true> : gemm_f16x2_pair_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmemBytes);
     if (e != cudaSuccess) {
       set_error("linear_f16x2: cannot reserve %zu bytes of shared memory (%s)", kPSmemBytes, cudaGetErrorString(e));
       return (int)e;
     }
-    gemm_f16x2_pair_kernel<<<pgrid, kFThreads, kPSmemBytes, (cudaStream_t)stream>>>(mh, ml, args);
+    kernel<<<pgrid, kFThreads, kPSmemBytes, (cudaStream_t)stream>>>(mh, ml, args);
     return check_launch("linear_f16x2 (pair)");
   }
 #define LAUNCH_F16(KB, LNV)                                                                                                \
