@@ -627,7 +627,9 @@ constexpr int kPTraceTiles = 32;
       p.trace[(((int64_t)blockIdx.x * 4 + (role)) * kPTraceTiles + (vt)) * 16 + (slot)] = clock64();             \
   } while (0)
 
-template <bool TRACE>
+// DIRECT: the epilogue stores straight from the 16x256b TMEM fragment (a quad of lanes owns one 32-byte sector of a row) instead
+// of transposing through shared memory
+template <bool TRACE, bool DIRECT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1)
 gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, GemmF16Args p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -739,7 +741,8 @@ gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid
     }
   } else if (warp < 12) {
     // ===================== A producers: this CTA's 128 rows, converted once per tile =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;" ::: "memory");
+    if constexpr (DIRECT) asm volatile("setmaxnreg.inc.sync.aligned.u32 176;" ::: "memory");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 184;" ::: "memory");
     const int t = threadIdx.x - 128;
     const int q = t & 15, rg = t >> 4;
     uint32_t soff[8];
@@ -814,8 +817,75 @@ gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid
     if (p.a_amax != nullptr) warp_amax_to_global(seen_max, p.a_amax);
   } else {
     // ===================== epilogue: this CTA's 128 accumulator rows (warp -> TMEM lane quarter) =====================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");
     const int quarter = warp & 3;
+    if constexpr (DIRECT) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 112;" ::: "memory");
+      // 16x256b fragments: lane (rq = lane / 4, c = lane % 4) holds columns 8 n + 2 c, + 1 of rows rq and rq + 8 of a 16-lane
+      // half; two loads (lanes 0-15, 16-31 of the quarter) give rows rq + 8 h, h < 4.  A store instruction then writes one full
+      // 32-byte sector in each of 8 rows: no staging tile, no shared-memory round trip in the warp's dependency chain.
+      const int rq = lane >> 2, c = lane & 3;
+      const uint32_t cs_l = smem_u32(bscale_s) + (uint32_t)(c * 8), bs_l = smem_u32(bias_s) + (uint32_t)(c * 8);
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int64_t it = 0; it < my_steps; ++it) {
+        const int64_t row0 = ((cluster_id + it * num_clusters) * 2 + cta_rank) * kFBlockM + quarter * 32;
+        const int rows_left = (int)((p.M - row0) < 32 ? (p.M - row0) : 32) - rq;        // row rq + 8 h exists iff 8 h < rows_left
+        float rs[4];
+        float* rowp[4];
+        for (int g = 0; g < groups; ++g) {
+          mbar_wait_backoff(&tmem_full_bar[acc], acc_phase, 32);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (warp == 12 && lane == 0) GASFM_PTRACE(2, it * groups + g, 0);
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            rs[h] = row_descale[it & (kFScaleSlots - 1)][quarter * 32 + rq + 8 * h];
+            rowp[h] = p.C + (row0 + rq + 8 * h) * p.ldc + g * kPN + 2 * c;
+          }
+          const uint32_t csg = cs_l + (uint32_t)g * (kPN * 4), bsg = bs_l + (uint32_t)g * (kPN * 4);
+          const uint32_t ta = tmem_base + (uint32_t)(acc * kPN) + ((uint32_t)(quarter * 32) << 16), tb = ta + (16u << 16);
+          uint32_t f0[32], f1[32];                      // [0,16): lanes 0-15 of the quarter, [16,32): lanes 16-31; two sets in flight
+#define GASFM_TMEM_LD16(R, O, ADDR)                                                                                            \
+          asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"    \
+                       : "=r"(R[O + 0]), "=r"(R[O + 1]), "=r"(R[O + 2]), "=r"(R[O + 3]), "=r"(R[O + 4]), "=r"(R[O + 5]),           \
+                         "=r"(R[O + 6]), "=r"(R[O + 7]), "=r"(R[O + 8]), "=r"(R[O + 9]), "=r"(R[O + 10]), "=r"(R[O + 11]),         \
+                         "=r"(R[O + 12]), "=r"(R[O + 13]), "=r"(R[O + 14]), "=r"(R[O + 15])                                        \
+                       : "r"(ADDR))
+#define GASFM_EPI_BLOCK(R, CB)                                                                                                 \
+          _Pragma("unroll") for (int n = 0; n < 4; ++n) {                                                                      \
+            float2 cs, bs;                                                                                                     \
+            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(cs.x), "=f"(cs.y) : "r"(csg + (uint32_t)(((CB) + 8 * n) * 4)) : "memory"); \
+            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(bs.x), "=f"(bs.y) : "r"(bsg + (uint32_t)(((CB) + 8 * n) * 4)) : "memory"); \
+            _Pragma("unroll") for (int h = 0; h < 4; ++h) {                                                                    \
+              if (8 * h < rows_left) {                                                                                         \
+                const float a0 = __uint_as_float(R[16 * (h >> 1) + 4 * n + 2 * (h & 1)]);                                      \
+                const float a1 = __uint_as_float(R[16 * (h >> 1) + 4 * n + 2 * (h & 1) + 1]);                                  \
+                asm volatile("st.global.v2.f32 [%0], {%1,%2};" ::"l"(rowp[h] + (CB) + 8 * n), "f"(fmaf(a0, rs[h] * cs.x, bs.x)),  \
+                             "f"(fmaf(a1, rs[h] * cs.y, bs.y)) : "memory");                                                  \
+              }                                                                                                                \
+            }                                                                                                                  \
+          }
+          GASFM_TMEM_LD16(f0, 0, ta); GASFM_TMEM_LD16(f0, 16, tb);
+#pragma unroll
+          for (int cb = 0; cb < kPN; cb += 64) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (warp == 12 && lane == 0) GASFM_PTRACE(2, it * groups + g, 2 + (cb >> 5));
+            GASFM_TMEM_LD16(f1, 0, ta + (uint32_t)(cb + 32)); GASFM_TMEM_LD16(f1, 16, tb + (uint32_t)(cb + 32));
+            GASFM_EPI_BLOCK(f0, cb)
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (warp == 12 && lane == 0) GASFM_PTRACE(2, it * groups + g, 3 + (cb >> 5));
+            if (cb + 64 < kPN) { GASFM_TMEM_LD16(f0, 0, ta + (uint32_t)(cb + 64)); GASFM_TMEM_LD16(f0, 16, tb + (uint32_t)(cb + 64)); }
+            GASFM_EPI_BLOCK(f1, cb + 32)
+          }
+#undef GASFM_TMEM_LD16
+#undef GASFM_EPI_BLOCK
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote_relaxed(&tmem_empty_bar[acc], 0);
+          if (warp == 12 && lane == 0) GASFM_PTRACE(2, it * groups + g, 1);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");
     const uint32_t stg = smem_u32(c_stage + (warp - 12) * 4096);   // [32 rows x 128 B], 16-byte chunk ^= row % 8
     const int pc = lane & 3, rsub = lane >> 2;
     // everything that does not change from chunk to chunk is computed once (the first version spent ~270 instructions per
@@ -898,6 +968,7 @@ gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid
         if (warp == 12 && lane == 0) GASFM_PTRACE(2, it * groups + g, 1);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+    }
     }
   }
   __syncthreads();
@@ -984,7 +1055,13 @@ static int linear_f16x2_impl(const float* A, int64_t lda, const void* B_hi, cons
     // the shipped block shape: CTA pairs on one cta_group::2 MMA stream, A converted once per tile for all groups
     const int64_t pair_tiles = (M + 2 * kFBlockM - 1) / (2 * kFBlockM);
     const int pgrid = (int)(pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2) * 2;
-    auto kernel = g_trace ? gemm_f16x2_pair_kernel<true> : gemm_f16x2_pair_kernel<false>;
+    // GASFM_GEMM_EPI=direct: epilogue stores straight from the 16x256b TMEM fragments (A/B switch).  Measured slower than the
+    // staged default (5.73 vs 5.44 ms at cfg3): a store instruction that touches 8 lines costs the L1 data pipe 8 wavefronts
+    // whether it carries 256 bytes or 1 KB, which eats what the missing staging round trip saves.
+    static int direct = -1;
+    if (direct < 0) { const char* env = getenv("GASFM_GEMM_EPI"); direct = (env && env[0] == 'd') ? 1 : 0; }
+    auto kernel = direct ? (g_trace ? gemm_f16x2_pair_kernel<true, true> : gemm_f16x2_pair_kernel<false, true>)
+                         : (g_trace ? gemm_f16x2_pair_kernel<true, false> : gemm_f16x2_pair_kernel<false, false>);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmemBytes);
     if (e != cudaSuccess) {
       set_error("linear_f16x2: cannot reserve %zu bytes of shared memory (%s)", kPSmemBytes, cudaGetErrorString(e));

@@ -45,6 +45,7 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         if self._before is None:
             model.zero_grad(set_to_none=True)       # gradients are (re)allocated inside the graph's pool
+        torch.cuda.empty_cache()                    # the warm-up's cached blocks cannot serve the graph's private pool
         if capture_lock is not None:
             capture_lock.acquire()
         try:
@@ -103,6 +104,7 @@ class StreamedStep:
         if self._before is None:
             model.zero_grad(set_to_none=True)                # gradients are (re)allocated inside the graph's pool
         self.scene.invalidate()
+        torch.cuda.empty_cache()                             # the warm-up's cached blocks cannot serve the graph's private pool
         self.graph = torch.cuda.CUDAGraph()
         with _index.deferred_validation() as pending:
             with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
