@@ -498,7 +498,6 @@ def measure_workload(cfg, args, dev, rank, world, exchange, scaling):
         # the pinned host scene is copied into the captured buffers, the graph replayed, predictions + loss + index status read back
         from gasfm_b200.graphs import StreamedStep
         ok, streamed = 1, None
-        holder.clear()
         torch.cuda.empty_cache()
         try:
             streamed = StreamedStep(model, scene_host, loss_fn, outputs=("Ps_norm", "pts3D"), device=dev,

@@ -60,6 +60,8 @@ SIGNATURES = {
     "gasfm_update_bwd_views": (_I, [_P, _L, _I, _P, _P, _I, _F, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
     "gasfm_x0_bwd_rowmax": (_I, [_P, _L, _I, _P, _P, _I, _F, _P, _P, _P, _P, _P]),
     "gasfm_linear_f16x2_ln": (_I, [_P, _L, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _P, _P]),
+    "gasfm_linear_f16x2_ln_y_supported": (_I, [_L, _I, _I, _L, _L]),
+    "gasfm_linear_f16x2_ln_y": (_I, [_P, _L, _P, _P, _F, _P, _P, _P, _L, _P, _P, _P, _P, _P, _L, _L, _I, _I, _I, _P, _P]),
     "gasfm_wgrad_f16x2_supported": (_I, [_L, _I, _I, _L, _L]),
     "gasfm_wgrad_f16x2_ws_bytes": (_SZ, [_I, _I]),
     "gasfm_wgrad_f16x2": (_I, [_P, _L, _P, _L, _P, _P, _L, _I, _I, _P, _P, _P, _P]),

@@ -49,6 +49,7 @@ struct GemmF16Args {
   // LN variant: the operand is relu(layer_norm(A) * gamma + beta), evaluated on the register-resident tile (A = x_raw is
   // read once, the normalised matrix never exists in memory); the row statistics are written out for backward
   const float* ln_gamma; const float* ln_beta; float ln_eps; float* ln_mean; float* ln_rstd;
+  float* ln_y; int64_t ldy;                   // optional (pair kernel): the normalised operand itself, for the weight gradients
   // CAT variant: A = [A_0 | A_1 | ..] (n_seg matrices of seg_k = 64 KB columns each, separate buffers), K = n_seg * seg_k.
   // The tile no longer fits the registers, so the operand producer makes two passes over it: row maxima first (one scale per
   // row across all segments), then scale + split K block by K block; the second pass and -- through an L2 prefetch issued one
@@ -627,9 +628,67 @@ constexpr int kPTraceTiles = 32;
       p.trace[(((int64_t)blockIdx.x * 4 + (role)) * kPTraceTiles + (vt)) * 16 + (slot)] = clock64();             \
   } while (0)
 
+// Drain of one 128 x 256 accumulator by one epilogue warp (its 32 rows), shared by the pair kernels.
+template <bool TRACE>
+__device__ __forceinline__ void pair_epilogue_drain(const GemmF16Args& p, uint32_t taddr0, uint32_t sts_base, uint32_t lds_v, uint32_t lds_w,
+                                                    uint32_t csg, uint32_t bsg, const float (&rs)[4], float* const (&rowp)[4],
+                                                    int rows_left, int vt, bool tracer) {
+    // 32-column chunks: TMEM -> registers (lane = row) -> swizzled staging tile -> registers (lane = 8 columns of 4 rows)
+    // -> descale by row and column, bias -> 256-bit stores.  The next chunk's TMEM read is issued as soon as the registers
+    // are free, and all read-back loads of a chunk are issued before the first result is used.
+    uint32_t r[32];
+#define GASFM_TMEM_LD32(ADDR)                                                                                                  \
+    asm volatile(                                                                                                          \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                          \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),      \
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),           \
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),          \
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                        \
+        : "r"(ADDR))
+#define GASFM_LDS4(V, ADDR) \
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"((V).x), "=f"((V).y), "=f"((V).z), "=f"((V).w) : "r"(ADDR) : "memory")
+    GASFM_TMEM_LD32(taddr0);
+#pragma unroll
+    for (int c0 = 0; c0 < kPN; c0 += 32) {
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      __syncwarp();                                  // the previous chunk's read-back is complete
+      if (tracer) GASFM_PTRACE(2, vt, 2 + (c0 >> 5));
+#pragma unroll
+      for (int k = 0; k < 8; ++k)                    // lane = row: raw accumulators into the swizzled staging tile
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sts_base ^ (uint32_t)(k << 4)), "r"(r[4 * k]), "r"(r[4 * k + 1]),
+                     "r"(r[4 * k + 2]), "r"(r[4 * k + 3]) : "memory");
+      __syncwarp();
+      if (c0 + 32 < kPN) GASFM_TMEM_LD32(taddr0 + (uint32_t)(c0 + 32));      // overlaps the read-back below
+      float4 v[4], w[4], cs0, cs1, bs0, bs1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        GASFM_LDS4(v[i], lds_v + (uint32_t)(i * 1024));
+        GASFM_LDS4(w[i], lds_w + (uint32_t)(i * 1024));
+      }
+      GASFM_LDS4(cs0, csg + (uint32_t)(c0 * 4)); GASFM_LDS4(cs1, csg + (uint32_t)(c0 * 4 + 16));
+      GASFM_LDS4(bs0, bsg + (uint32_t)(c0 * 4)); GASFM_LDS4(bs1, bsg + (uint32_t)(c0 * 4 + 16));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (8 * i < rows_left) {
+          const float f = rs[i];
+          asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(rowp[i] + c0), "f"(fmaf(v[i].x, f * cs0.x, bs0.x)),
+                       "f"(fmaf(v[i].y, f * cs0.y, bs0.y)), "f"(fmaf(v[i].z, f * cs0.z, bs0.z)), "f"(fmaf(v[i].w, f * cs0.w, bs0.w)),
+                       "f"(fmaf(w[i].x, f * cs1.x, bs1.x)), "f"(fmaf(w[i].y, f * cs1.y, bs1.y)), "f"(fmaf(w[i].z, f * cs1.z, bs1.z)),
+                       "f"(fmaf(w[i].w, f * cs1.w, bs1.w))
+                       : "memory");
+        }
+      }
+    }
+#undef GASFM_TMEM_LD32
+#undef GASFM_LDS4
+}
+
 // DIRECT: the epilogue stores straight from the 16x256b TMEM fragment (a quad of lanes owns one 32-byte sector of a row) instead
 // of transposing through shared memory
-template <bool TRACE, bool DIRECT>
+// LN: the operand is relu(layer_norm(A) * gamma + beta), evaluated once per tile on the register-resident rows (the producers of
+// this kernel are idle two thirds of the time: the normalisation is free, and the separate LayerNorm pass over [E, d] goes away)
+template <bool TRACE, bool DIRECT, bool LN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1)
 gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, GemmF16Args p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -642,6 +701,7 @@ gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float bias_s[kFMaxGroups * kPN], bscale_s[kFMaxGroups * kPN];
   __shared__ float row_descale[kFScaleSlots][kFBlockM];
+  __shared__ __align__(16) float ln_gamma_s[LN ? kPN : 4], ln_beta_s[LN ? kPN : 4];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
@@ -649,6 +709,9 @@ gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid
   const int64_t num_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
   const int64_t my_steps = cluster_id < num_pair_tiles ? (num_pair_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
   const int groups = p.groups;
+  if constexpr (LN) {
+    for (int j = threadIdx.x; j < kPN; j += kFThreads) { ln_gamma_s[j] = p.ln_gamma[j]; ln_beta_s[j] = p.ln_beta[j]; }
+  }
 
   if (threadIdx.x == 0) {
     for (int k = 0; k < kPKB; ++k) { mbar_init(&a_full[k], 256); mbar_init(&a_empty[k], 1); }
@@ -772,6 +835,46 @@ gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid
     for (int kb = 0; kb < kPKB; ++kb) load_block(0, kb, buf[kb]);
     float seen_max = 0.f;
     for (int64_t it = 0; it < my_steps; ++it) {
+      if constexpr (LN) {
+        // LayerNorm + ReLU in place on the register tile: two-pass mean / variance over the 256 columns of each row (16 lanes
+        // share a row), then y = max(0, (x - mean) rstd gamma + beta) -- the arithmetic of ln_relu_fwd_kernel
+        const int64_t row0 = ((cluster_id + it * num_clusters) * 2 + cta_rank) * kFBlockM;
+        const bool full = row0 + kFBlockM <= p.M;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t row = row0 + rg + 16 * i;
+          float sum = 0.f;
+#pragma unroll
+          for (int kb = 0; kb < kPKB; ++kb) sum += (buf[kb][i].x + buf[kb][i].y) + (buf[kb][i].z + buf[kb][i].w);
+#pragma unroll
+          for (int off = 1; off < 16; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+          const float mean = sum * (1.f / kPN);
+          float sq = 0.f;
+#pragma unroll
+          for (int kb = 0; kb < kPKB; ++kb) {
+            const float dx = buf[kb][i].x - mean, dy = buf[kb][i].y - mean, dz = buf[kb][i].z - mean, dw = buf[kb][i].w - mean;
+            sq = fmaf(dx, dx, sq); sq = fmaf(dy, dy, sq); sq = fmaf(dz, dz, sq); sq = fmaf(dw, dw, sq);
+          }
+#pragma unroll
+          for (int off = 1; off < 16; off <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+          const float rstd = 1.f / sqrtf(sq * (1.f / kPN) + p.ln_eps);
+          const bool live = full || row < p.M;              // rows past the end stay zero (they must not enter a_amax)
+#pragma unroll
+          for (int kb = 0; kb < kPKB; ++kb) {
+            const int kcol = kb * kFBlockK + q * 4;
+            const float4 g = *reinterpret_cast<const float4*>(&ln_gamma_s[kcol]);
+            const float4 b = *reinterpret_cast<const float4*>(&ln_beta_s[kcol]);
+            float4 y;
+            y.x = live ? fmaxf(fmaf((buf[kb][i].x - mean) * rstd, g.x, b.x), 0.f) : 0.f;
+            y.y = live ? fmaxf(fmaf((buf[kb][i].y - mean) * rstd, g.y, b.y), 0.f) : 0.f;
+            y.z = live ? fmaxf(fmaf((buf[kb][i].z - mean) * rstd, g.z, b.z), 0.f) : 0.f;
+            y.w = live ? fmaxf(fmaf((buf[kb][i].w - mean) * rstd, g.w, b.w), 0.f) : 0.f;
+            buf[kb][i] = y;
+            if (p.ln_y != nullptr && live) st_stream4(p.ln_y + row * p.ldy + kcol, y);
+          }
+          if (q == 0 && live) { p.ln_mean[row] = mean; p.ln_rstd[row] = rstd; }
+        }
+      }
       float scale[8];
       float* descale_slot = row_descale[it & (kFScaleSlots - 1)];
 #pragma unroll
@@ -913,55 +1016,8 @@ gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid
         }
         const uint32_t csg = cs_base + (uint32_t)g * (kPN * 4), bsg = bs_base + (uint32_t)g * (kPN * 4);
         const uint32_t taddr0 = tmem_base + (uint32_t)(acc * kPN) + ((uint32_t)(quarter * 32) << 16);
-        // 32-column chunks: TMEM -> registers (lane = row) -> swizzled staging tile -> registers (lane = 8 columns of 4 rows)
-        // -> descale by row and column, bias -> 256-bit stores.  The next chunk's TMEM read is issued as soon as the registers
-        // are free, and all read-back loads of a chunk are issued before the first result is used.
-        uint32_t r[32];
-#define GASFM_TMEM_LD32(ADDR)                                                                                                  \
-        asm volatile(                                                                                                          \
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                          \
-            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),      \
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),           \
-              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),          \
-              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                        \
-            : "r"(ADDR))
-#define GASFM_LDS4(V, ADDR) \
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"((V).x), "=f"((V).y), "=f"((V).z), "=f"((V).w) : "r"(ADDR) : "memory")
-        GASFM_TMEM_LD32(taddr0);
-#pragma unroll
-        for (int c0 = 0; c0 < kPN; c0 += 32) {
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          __syncwarp();                                  // the previous chunk's read-back is complete
-          if (warp == 12 && lane == 0) GASFM_PTRACE(2, it * groups + g, 2 + (c0 >> 5));
-#pragma unroll
-          for (int k = 0; k < 8; ++k)                    // lane = row: raw accumulators into the swizzled staging tile
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sts_base ^ (uint32_t)(k << 4)), "r"(r[4 * k]), "r"(r[4 * k + 1]),
-                         "r"(r[4 * k + 2]), "r"(r[4 * k + 3]) : "memory");
-          __syncwarp();
-          if (c0 + 32 < kPN) GASFM_TMEM_LD32(taddr0 + (uint32_t)(c0 + 32));      // overlaps the read-back below
-          float4 v[4], w[4], cs0, cs1, bs0, bs1;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            GASFM_LDS4(v[i], lds_v + (uint32_t)(i * 1024));
-            GASFM_LDS4(w[i], lds_w + (uint32_t)(i * 1024));
-          }
-          GASFM_LDS4(cs0, csg + (uint32_t)(c0 * 4)); GASFM_LDS4(cs1, csg + (uint32_t)(c0 * 4 + 16));
-          GASFM_LDS4(bs0, bsg + (uint32_t)(c0 * 4)); GASFM_LDS4(bs1, bsg + (uint32_t)(c0 * 4 + 16));
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (8 * i < rows_left) {
-              const float f = rs[i];
-              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(rowp[i] + c0), "f"(fmaf(v[i].x, f * cs0.x, bs0.x)),
-                           "f"(fmaf(v[i].y, f * cs0.y, bs0.y)), "f"(fmaf(v[i].z, f * cs0.z, bs0.z)), "f"(fmaf(v[i].w, f * cs0.w, bs0.w)),
-                           "f"(fmaf(w[i].x, f * cs1.x, bs1.x)), "f"(fmaf(w[i].y, f * cs1.y, bs1.y)), "f"(fmaf(w[i].z, f * cs1.z, bs1.z)),
-                           "f"(fmaf(w[i].w, f * cs1.w, bs1.w))
-                           : "memory");
-            }
-          }
-        }
-#undef GASFM_TMEM_LD32
-#undef GASFM_LDS4
+        pair_epilogue_drain<TRACE>(p, taddr0, sts_base, lds_v, lds_w, csg, bsg, rs, rowp, rows_left, (int)(it * groups + g),
+                                   warp == 12 && lane == 0);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive_remote_relaxed(&tmem_empty_bar[acc], 0);   // the leader's MMA thread owns the accumulator hand-back
@@ -973,6 +1029,264 @@ gemm_f16x2_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid
   }
   __syncthreads();
   cluster_sync();                            // neither CTA leaves (or frees TMEM) while the pair's MMAs / remote arrives are in flight
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// cta_group::2 form of the concatenated input gradient dX[M, 256] = [dY_0 | dY_1 | ..] Wcat^T with row maxima from upstream
+// (n_seg segments of 256 columns, K = 256 n_seg).  Same pair structure as gemm_f16x2_pair_kernel; the operand streams instead
+// of staying resident: a stage holds one K block of this CTA's 128 rows (fp16 hi | lo, written by the producers) and this CTA's
+// half of the weights' K block (TMA) -- 64 KB, so THREE stages fit where the cta_group::1 kernel has two of 96 KB.
+constexpr int kCStageBytes = kPSlotBytes + kPBStageBytes;       // A hi | A lo | B hi half | B lo half
+constexpr int kCStages = 3;
+constexpr size_t kCSmemBytes = (size_t)kCStages * kCStageBytes + 4 * 4096 + 1024;
+
+template <bool TRACE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1)
+gemm_f16x2_cat_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, GemmF16Args p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* c_stage = smem + (size_t)kCStages * kCStageBytes;
+  __shared__ uint64_t full_bar[kCStages], split_bar[kCStages], empty_bar[kCStages], peer_bar[kCStages];
+  __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float bias_s[kPN], bscale_s[kPN];
+  __shared__ float row_descale[kFScaleSlots][kFBlockM];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int64_t num_pair_tiles = (p.M + 2 * kFBlockM - 1) / (2 * kFBlockM);
+  const int64_t num_clusters = gridDim.x / 2, cluster_id = blockIdx.x / 2;
+  const int64_t my_steps = cluster_id < num_pair_tiles ? (num_pair_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
+  const int nkb = kPKB * p.n_seg;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kCStages; ++s) {
+      mbar_init(&full_bar[s], 1); mbar_init(&split_bar[s], 256); mbar_init(&empty_bar[s], 1); mbar_init(&peer_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int j = threadIdx.x; j < kPN; j += kFThreads) {
+    bias_s[j] = p.bias ? p.bias[j] : 0.f;
+    bscale_s[j] = p.b_scale[j];
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA: this CTA's 128 weight rows, K block by K block =====================
+      int stage = 0; uint32_t phase = 0;
+      const int b_row0 = (int)cta_rank * (kPN / 2);
+      for (int64_t it = 0; it < my_steps; ++it) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait_backoff(&empty_bar[stage], phase ^ 1, 32);
+          if (kb < 16) GASFM_PTRACE(3, it, kb);
+          uint8_t* st = smem + (size_t)stage * kCStageBytes + kPSlotBytes;
+          mbar_expect_tx(&full_bar[stage], kPBStageBytes);
+          tma_load_2d(st, &map_bhi, &full_bar[stage], kb * kFBlockK, b_row0);
+          tma_load_2d(st + kPBPlaneBytes, &map_blo, &full_bar[stage], kb * kFBlockK, b_row0);
+          if (++stage == kCStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      if (cta_rank != 0) {
+        // ===================== relay (peer CTA) =====================
+        for (int64_t it = 0; it < my_steps; ++it) {
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait_backoff(&full_bar[stage], phase, 20);
+            mbar_wait_backoff(&split_bar[stage], phase, 20);
+            mbar_arrive_remote(&peer_bar[stage], 0);
+            if (++stage == kCStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      } else {
+        // ===================== MMA issuer (leader CTA), M = 256 over the pair =====================
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(kPN >> 3) << 17) | ((uint32_t)((2 * kFBlockM) >> 4) << 24);
+        int acc = 0; uint32_t acc_phase = 0;
+        const uint32_t s_base = smem_u32(smem);
+        for (int64_t it = 0; it < my_steps; ++it) {
+          mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          GASFM_PTRACE(1, it, 0);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kPN);
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            mbar_wait(&split_bar[stage], phase);
+            mbar_wait(&peer_bar[stage], phase);
+            if (kb < 12) GASFM_PTRACE(1, it, 1 + kb);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = s_base + (uint32_t)stage * kCStageBytes, a_lo = a_hi + kFATileBytes;
+            const uint32_t b_hi = a_hi + kPSlotBytes, b_lo = b_hi + kPBPlaneBytes;
+#pragma unroll
+            for (int k = 0; k < kFBlockK / kFUmmaK; ++k) {
+              const uint32_t koff = k * kFUmmaK * 2;
+              umma_f16_pair(d_tmem, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, (kb == 0 && k == 0) ? 0u : 1u);
+              umma_f16_pair(d_tmem, make_desc(a_lo + koff), make_desc(b_hi + koff), idesc, 1u);
+              umma_f16_pair(d_tmem, make_desc(a_hi + koff), make_desc(b_lo + koff), idesc, 1u);
+            }
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == nkb - 1) umma_commit_pair(&tmem_full_bar[acc]);
+            if (++stage == kCStages) { stage = 0; phase ^= 1; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 12) {
+    // ===================== A producers: K blocks of this CTA's 128 rows stream through four register buffers =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;" ::: "memory");
+    const int t = threadIdx.x - 128;
+    const int q = t & 15, rg = t >> 4;
+    int stage = 0; uint32_t phase = 0;
+    uint32_t soff[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = rg + 16 * i;
+      soff[i] = (uint32_t)(row * 128 + ((((q >> 1) ^ (row & 7))) << 4) + ((q & 1) << 3));
+    }
+    const uint32_t smem_base = smem_u32(smem);
+    int64_t tr_it = 0; int tr_kb = 0;                            // (profiling only)
+    auto convert_block = [&](const float4 (&v)[8], const float (&scale)[8]) {
+      if (t == 0) mbar_wait_backoff(&empty_bar[stage], phase ^ 1, 32);        // one polling lane, the rest block on the named barrier
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (t == 0) { GASFM_PTRACE(0, tr_it, tr_kb); }
+      const uint32_t sb = smem_base + (uint32_t)stage * (uint32_t)kCStageBytes;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float s = scale[i];
+        const float x0 = v[i].x * s, x1 = v[i].y * s, x2 = v[i].z * s, x3 = v[i].w * s;
+        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+        const uint32_t addr = sb + soff[i];
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h01)),
+                     "r"(*reinterpret_cast<const uint32_t*>(&h23)) : "memory");
+        asm volatile("st.shared.v2.b32 [%0+%3], {%1, %2};" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&l01)),
+                     "r"(*reinterpret_cast<const uint32_t*>(&l23)), "n"(kFATileBytes) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&split_bar[stage]);
+      if (TRACE) { if (++tr_kb == nkb) { tr_kb = 0; ++tr_it; } }
+      if (++stage == kCStages) { stage = 0; phase ^= 1; }
+    };
+    auto load_kbg = [&](int64_t it, int kbg, float4 (&v)[8]) {
+      if (kbg >= nkb) { kbg -= nkb; ++it; }                     // the stream runs across tiles
+      const int seg = kbg / kPKB, kcol = (kbg % kPKB) * kFBlockK + q * 4;
+      const float* base = seg == 0 ? p.A_seg[0] : (seg == 1 ? p.A_seg[1] : (seg == 2 ? p.A_seg[2] : p.A_seg[3]));
+      const int64_t ld = seg == 0 ? p.lda_seg[0] : (seg == 1 ? p.lda_seg[1] : (seg == 2 ? p.lda_seg[2] : p.lda_seg[3]));
+      const int64_t row0 = ((cluster_id + it * num_clusters) * 2 + cta_rank) * kFBlockM;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t row = row0 + rg + 16 * i;
+        v[i] = (it < my_steps && row < p.M) ? ld_stream4(base + row * ld + kcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    float seg_seen[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 v0[8], v1[8], v2[8], v3[8];
+    // row scales of tile ``it`` from the upstream row maxima.  The device timeline of the first version showed the MMA stream
+    // idle for ~12 k cycles at the start of EVERY tile: these loads (cold, queued behind 96 KB of streaming operand loads) sat
+    // between two tiles.  Now the next tile's maxima are prefetched into L2 at the top of a tile and turned into scales before
+    // the tile's LAST conversion, while the MMA still has two staged K blocks to work on.
+    auto tile_scales = [&](int64_t it, float (&scale)[8]) {
+      const int64_t row0 = ((cluster_id + it * num_clusters) * 2 + cta_rank) * kFBlockM;
+      float* descale_slot = row_descale[it & (kFScaleSlots - 1)];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t row = row0 + rg + 16 * i;
+        float m = 0.f;
+#pragma unroll
+        for (int seg = 0; seg < 4; ++seg) {
+          if (seg < p.n_seg && it < my_steps && row < p.M) {
+            const float r = __ldg(p.rowmax_seg[seg] + row);
+            m = fmaxf(m, r);
+            seg_seen[seg] = fmaxf(seg_seen[seg], r);
+          }
+        }
+        float descale;
+        row_scale_from_amax(m, scale[i], descale);
+        if (q == 0) descale_slot[rg + 16 * i] = descale;
+      }
+    };
+    auto prefetch_rowmax = [&](int64_t it) {                    // 128 rows x 4 B = 4 lines per segment
+      const int64_t row = ((cluster_id + it * num_clusters) * 2 + cta_rank) * kFBlockM + (t & 3) * 32;
+      const int seg = t >> 2;
+      if (t < 16 && seg < p.n_seg && it < my_steps && row < p.M) {
+        const float* src = (seg == 0 ? p.rowmax_seg[0] : (seg == 1 ? p.rowmax_seg[1] : (seg == 2 ? p.rowmax_seg[2] : p.rowmax_seg[3]))) + row;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+      }
+    };
+    load_kbg(0, 0, v0); load_kbg(0, 1, v1); load_kbg(0, 2, v2);
+    float scale[8];
+    tile_scales(0, scale);
+    for (int64_t it = 0; it < my_steps; ++it) {
+      prefetch_rowmax(it + 1);
+      float scale_next[8];
+      for (int kbg = 0; kbg < nkb; kbg += 4) {                  // nkb % 4 == 0
+        load_kbg(it, kbg + 3, v3);
+        convert_block(v0, scale);
+        load_kbg(it, kbg + 4, v0);
+        convert_block(v1, scale);
+        load_kbg(it, kbg + 5, v1);
+        convert_block(v2, scale);
+        load_kbg(it, kbg + 6, v2);
+        if (kbg + 4 >= nkb) tile_scales(it + 1, scale_next);
+        convert_block(v3, scale);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) scale[i] = scale_next[i];
+    }
+    if (p.seg_amax != nullptr) {
+#pragma unroll
+      for (int seg = 0; seg < 4; ++seg)
+        if (seg < p.n_seg) warp_amax_to_global(seg_seen[seg], p.seg_amax + seg);
+    }
+  } else {
+    // ===================== epilogue: this CTA's 128 accumulator rows =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");
+    const int quarter = warp & 3;
+    const uint32_t stg = smem_u32(c_stage + (warp - 12) * 4096);
+    const int pc = lane & 3, rsub = lane >> 2;
+    const uint32_t sts_base = stg + (uint32_t)(lane * 128 + ((lane & 7) << 4));
+    const uint32_t lds_v = stg + (uint32_t)(rsub * 128 + (((2 * pc) ^ rsub) << 4)), lds_w = lds_v ^ 16u;
+    const uint32_t csg = smem_u32(bscale_s) + (uint32_t)(pc * 32), bsg = smem_u32(bias_s) + (uint32_t)(pc * 32);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int64_t it = 0; it < my_steps; ++it) {
+      const int64_t row0 = ((cluster_id + it * num_clusters) * 2 + cta_rank) * kFBlockM + quarter * 32;
+      const int rows_left = (int)((p.M - row0) < 32 ? (p.M - row0) : 32) - rsub;
+      float rs[4];
+      float* rowp[4];
+      mbar_wait_backoff(&tmem_full_bar[acc], acc_phase, 32);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (warp == 12 && lane == 0) GASFM_PTRACE(2, it, 0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        rs[i] = row_descale[it & (kFScaleSlots - 1)][quarter * 32 + 8 * i + rsub];
+        rowp[i] = p.C + (row0 + 8 * i + rsub) * p.ldc + 8 * pc;
+      }
+      const uint32_t taddr0 = tmem_base + (uint32_t)(acc * kPN) + ((uint32_t)(quarter * 32) << 16);
+      pair_epilogue_drain<TRACE>(p, taddr0, sts_base, lds_v, lds_w, csg, bsg, rs, rowp, rows_left, (int)it, warp == 12 && lane == 0);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote_relaxed(&tmem_empty_bar[acc], 0);
+      if (warp == 12 && lane == 0) GASFM_PTRACE(2, it, 1);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  __syncthreads();
+  cluster_sync();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -1024,7 +1338,7 @@ extern "C" int gasfm_linear_f16x2_supported(int64_t M, int N, int K, int64_t lda
 static int linear_f16x2_impl(const float* A, int64_t lda, const void* B_hi, const void* B_lo, const float* b_descale,
                             const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int groups, int accumulate,
                             float* a_amax, const float* ln_gamma, const float* ln_beta, float ln_eps, float* ln_mean,
-                            float* ln_rstd, void* stream) {
+                            float* ln_rstd, float* ln_y, int64_t ldy, void* stream) {
   GASFM_REQUIRE(gasfm_linear_f16x2_supported(M, N, K, lda, ldc), "linear_f16x2: unsupported shape M=%lld N=%d K=%d lda=%lld ldc=%lld",
                 (long long)M, N, K, (long long)lda, (long long)ldc);
   GASFM_REQUIRE(groups >= 1 && groups <= kFMaxGroups && ldc >= (int64_t)groups * N, "linear_f16x2: 1..%d groups, ldc >= groups * N", kFMaxGroups);
@@ -1051,7 +1365,11 @@ static int linear_f16x2_impl(const float* A, int64_t lda, const void* B_hi, cons
   args.A = A; args.lda = lda; args.b_scale = b_descale; args.bias = bias; args.C = C; args.ldc = ldc; args.M = M; args.N = N; args.K = K;
   args.groups = groups; args.tmem_cols = tmem_cols; args.accumulate = accumulate; args.debug = debug; args.a_amax = a_amax;
   args.ln_gamma = ln_gamma; args.ln_beta = ln_beta; args.ln_eps = ln_eps; args.ln_mean = ln_mean; args.ln_rstd = ln_rstd; args.trace = g_trace;
-  if (use_pair && !ln && !accumulate && N == kPN && K == kPKB * kFBlockK && ldc % 8 == 0 && (uintptr_t)C % 32 == 0 && debug == 0) {
+  const bool pair_ok = use_pair && !accumulate && N == kPN && K == kPKB * kFBlockK && ldc % 8 == 0 && (uintptr_t)C % 32 == 0 && debug == 0;
+  GASFM_REQUIRE(ln_y == nullptr || (ln && pair_ok && ldy >= K && ldy % 4 == 0 && (uintptr_t)ln_y % 16 == 0),
+                "linear_f16x2_ln: the normalised operand can only be written by the N = K = 256 kernel (see gasfm_linear_f16x2_ln_y_supported)");
+  args.ln_y = ln_y; args.ldy = ldy;
+  if (pair_ok) {
     // the shipped block shape: CTA pairs on one cta_group::2 MMA stream, A converted once per tile for all groups
     const int64_t pair_tiles = (M + 2 * kFBlockM - 1) / (2 * kFBlockM);
     const int pgrid = (int)(pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2) * 2;
@@ -1060,8 +1378,9 @@ static int linear_f16x2_impl(const float* A, int64_t lda, const void* B_hi, cons
     // whether it carries 256 bytes or 1 KB, which eats what the missing staging round trip saves.
     static int direct = -1;
     if (direct < 0) { const char* env = getenv("GASFM_GEMM_EPI"); direct = (env && env[0] == 'd') ? 1 : 0; }
-    auto kernel = direct ? (g_trace ? gemm_f16x2_pair_kernel<true, true> : gemm_f16x2_pair_kernel<false, true>)
-                         : (g_trace ? gemm_f16x2_pair_kernel<true, false> : gemm_f16x2_pair_kernel<false, false>);
+    auto kernel = ln ? gemm_f16x2_pair_kernel<false, false, true>
+                     : direct ? (g_trace ? gemm_f16x2_pair_kernel<true, true> : gemm_f16x2_pair_kernel<false, true>)
+                              : (g_trace ? gemm_f16x2_pair_kernel<true, false> : gemm_f16x2_pair_kernel<false, false>);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPSmemBytes);
     if (e != cudaSuccess) {
       set_error("linear_f16x2: cannot reserve %zu bytes of shared memory (%s)", kPSmemBytes, cudaGetErrorString(e));
@@ -1149,6 +1468,28 @@ static int linear_f16x2_cat_impl(const float* const* A, const int64_t* lda, cons
       args.rowmax_seg[i] = rowmax[i];
     }
   }
+  {
+    static int use_pair = -1;
+    if (use_pair < 0) { const char* env = getenv("GASFM_GEMM_PAIR"); use_pair = env ? atoi(env) : 1; }
+    if (use_pair && rowmax != nullptr && N == kPN && seg_k == kPKB * kFBlockK && ldc % 8 == 0 && (uintptr_t)C % 32 == 0 && args.debug == 0) {
+      // the block shape with row maxima at hand: CTA pairs on one cta_group::2 MMA stream, three 64 KB stages
+      bool lda_ok = true;
+      for (int i = 0; i < n_seg; ++i) lda_ok = lda_ok && lda[i] >= seg_k;
+      if (lda_ok) {
+        const int64_t pair_tiles = (M + 2 * kFBlockM - 1) / (2 * kFBlockM);
+        const int pgrid = (int)(pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2) * 2;
+        args.trace = g_trace;
+        auto kernel = g_trace ? gemm_f16x2_cat_pair_kernel<true> : gemm_f16x2_cat_pair_kernel<false>;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemBytes);
+        if (e != cudaSuccess) {
+          set_error("linear_f16x2_cat: cannot reserve %zu bytes of shared memory (%s)", kCSmemBytes, cudaGetErrorString(e));
+          return (int)e;
+        }
+        kernel<<<pgrid, kFThreads, kCSmemBytes, (cudaStream_t)stream>>>(mh, ml, args);
+        return check_launch("linear_f16x2_cat (pair)");
+      }
+    }
+  }
 #define LAUNCH_CAT(KB)                                                                                                          \
   do {                                                                                                                          \
     cudaError_t e = cudaFuncSetAttribute(gemm_f16x2_kernel<KB, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
@@ -1167,7 +1508,7 @@ extern "C" int gasfm_linear_f16x2(const float* A, int64_t lda, const void* B_hi,
                                   const float* bias, float* C, int64_t ldc, int64_t M, int N, int K, int groups, int accumulate,
                                   float* a_amax, void* stream) {
   return linear_f16x2_impl(A, lda, B_hi, B_lo, b_descale, bias, C, ldc, M, N, K, groups, accumulate, a_amax, nullptr, nullptr, 0.f,
-                           nullptr, nullptr, stream);
+                           nullptr, nullptr, nullptr, 0, stream);
 }
 
 extern "C" int gasfm_linear_f16x2_ln(const float* A, int64_t lda, const float* ln_gamma, const float* ln_beta, float ln_eps,
@@ -1176,5 +1517,19 @@ extern "C" int gasfm_linear_f16x2_ln(const float* A, int64_t lda, const float* l
                                      float* a_amax, void* stream) {
   GASFM_REQUIRE(ln_gamma != nullptr, "linear_f16x2_ln: gamma is required");
   return linear_f16x2_impl(A, lda, B_hi, B_lo, b_descale, bias, C, ldc, M, N, K, groups, 0, a_amax, ln_gamma, ln_beta, ln_eps,
-                           ln_mean, ln_rstd, stream);
+                           ln_mean, ln_rstd, nullptr, 0, stream);
+}
+
+extern "C" int gasfm_linear_f16x2_ln_y_supported(int64_t M, int N, int K, int64_t lda, int64_t ldc) {
+  const char* env = getenv("GASFM_GEMM_PAIR");
+  return (gasfm_linear_f16x2_supported(M, N, K, lda, ldc) && N == kPN && K == kPKB * kFBlockK && ldc % 8 == 0 && !(env && atoi(env) == 0)) ? 1 : 0;
+}
+
+extern "C" int gasfm_linear_f16x2_ln_y(const float* A, int64_t lda, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                                       float* ln_mean, float* ln_rstd, float* y, int64_t ldy, const void* B_hi, const void* B_lo,
+                                       const float* b_descale, const float* bias, float* C, int64_t ldc, int64_t M, int N, int K,
+                                       int groups, float* a_amax, void* stream) {
+  GASFM_REQUIRE(ln_gamma != nullptr && y != nullptr, "linear_f16x2_ln_y: gamma and y are required");
+  return linear_f16x2_impl(A, lda, B_hi, B_lo, b_descale, bias, C, ldc, M, N, K, groups, 0, a_amax, ln_gamma, ln_beta, ln_eps,
+                           ln_mean, ln_rstd, y, ldy, stream);
 }

@@ -104,15 +104,15 @@ class GraphAttnSfMNet(BaseNet):
         return SparseMat(x.values, x.indices, x.cam_per_pts, x.pts_per_cam, tuple(x.shape), _index=idx)
 
     def _wants_recompute(self, n_obs, device):
-        """Activation recompute policy.  A block keeps 4-5 [E, n_feat_proj] fp32 tensors for backward (x_raw, the three
-        grouped projections, and relu(LN(x_raw)) unless the GEMM normalises on the fly); with recompute only x_raw stays.  "auto": switch it on when the kept
+        """Activation recompute policy.  A block keeps five [E, n_feat_proj] fp32 tensors for backward (x_raw, the three
+        grouped projections and relu(LN(x_raw))); with recompute only x_raw stays.  "auto": switch it on when the kept
         activations of all blocks would take more than half of the device memory."""
         mode = ops.ACTIVATION_RECOMPUTE
         if mode in ("on", "off"):
             return mode == "on"
         if not torch.is_grad_enabled():
             return False
-        kept = (4.0 if ops.LN_FUSED else 5.0) * n_obs * self.n_feat_proj * 4 * len(self.equivariant_blocks)
+        kept = 5.0 * n_obs * self.n_feat_proj * 4 * len(self.equivariant_blocks)
         return kept > 0.5 * torch.cuda.get_device_properties(device).total_memory
 
     def forward(self, data):

@@ -457,9 +457,14 @@ def gemm_f16x2_groups(a, weights, biases, want_amax=False):
     return (c, amax) if want_amax else c
 
 
-def gemm_f16x2_groups_ln(x_raw, gamma, beta, eps, weights, biases):
+def gemm_f16x2_ln_y_supported(M, N, K, lda, ldc):
+    return bool(_lib.load().gasfm_linear_f16x2_ln_y_supported(int(M), int(N), int(K), int(lda), int(ldc)))
+
+
+def gemm_f16x2_groups_ln(x_raw, gamma, beta, eps, weights, biases, want_y=False):
     """gemm_f16x2_groups over relu(layer_norm(x_raw)) with the normalisation done inside the GEMM's operand producer:
-    x_raw is read once, the normalised matrix is never materialised.  -> (out [M, G*N], max|operand| [1], mean [M], rstd [M])."""
+    x_raw is read once.  -> (out [M, G*N], max|operand| [1], mean [M], rstd [M]) and, with ``want_y`` (N = K = 256 kernel
+    only, ``gemm_f16x2_ln_y_supported``), the normalised matrix itself as a by-product of the same pass."""
     x_raw, lda = _rows(x_raw)
     M, K = x_raw.shape
     G, N = len(weights), weights[0].shape[0]
@@ -471,6 +476,12 @@ def gemm_f16x2_groups_ln(x_raw, gamma, beta, eps, weights, biases):
     mean = torch.empty(M, dtype=torch.float32, device=dev)
     rstd = torch.empty(M, dtype=torch.float32, device=dev)
     with _lib.device_guard(dev):
+        if want_y:
+            y = torch.empty((M, K), dtype=torch.float32, device=dev)
+            _lib.call("gasfm_linear_f16x2_ln_y", _lib.ptr(x_raw), lda, _lib.ptr(gamma.contiguous()), _lib.ptr(beta.contiguous()),
+                      float(eps), _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(y), K, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(descale),
+                      _lib.ptr(bias), _lib.ptr(c), G * N, M, N, K, G, _lib.ptr(amax), _lib.stream_ptr())
+            return c, amax, mean, rstd, y
         _lib.call("gasfm_linear_f16x2_ln", _lib.ptr(x_raw), lda, _lib.ptr(gamma.contiguous()), _lib.ptr(beta.contiguous()), float(eps),
                   _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(descale), _lib.ptr(bias), _lib.ptr(c), G * N,
                   M, N, K, G, _lib.ptr(amax), _lib.stream_ptr())
@@ -723,10 +734,15 @@ class _LinearMulti(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------
 # one GASFM block's observation-level front end: relu(LN(x_raw)) -> lin_l (x2) + lin_proj, as ONE autograd node
 # ---------------------------------------------------------------------------------------------
-# LayerNorm + ReLU inside the projection GEMM's operand producer.  Measured on cfg2 (profiles/r02_fusion_ab.md): the forward
-# gets 0.2 ms faster (the GEMM slows down by about what the separate LN kernel cost), but backward then has to rebuild
-# relu(LN(x)) for the weight gradients, +1.5 ms per step -- so it is OFF by default and meant for forward-only use.
-LN_FUSED = os.environ.get("GASFM_LN_FUSED", "0") != "0"
+# LayerNorm + ReLU inside the projection GEMM's operand producer (default: wherever the CTA-pair kernel runs, N = K = 256).
+# That kernel converts the operand tile once for all three projections, so its producers have time to spare: the
+# normalisation costs 5 % of the GEMM and the separate LayerNorm pass over [E, d] disappears; relu(LN(x)) is written out from
+# the same registers only when backward needs it.  cfg3 at d = 256 (recompute): 570.9 -> 552 ms per step, and the step then
+# fits a second graph capture (end-to-end 579.9 eager -> 553.5 ms replayed); cfg2: no change (profiles/r02_fusion_ab.md).
+# "0": never; "force": also on the cta_group::1 kernel (other widths), where backward has to rebuild relu(LN(x)) separately.
+_LN_FUSED_MODE = os.environ.get("GASFM_LN_FUSED", "1")
+LN_FUSED = _LN_FUSED_MODE != "0"
+LN_FUSED_ANY_SHAPE = _LN_FUSED_MODE == "force"
 ACTIVATION_RECOMPUTE = os.environ.get("GASFM_RECOMPUTE", "auto")   # "on" | "off" | "auto" (decided per scene by the model)
 _recompute_now = False
 
@@ -748,6 +764,7 @@ class EdgeBlockContext:
 
     def __init__(self, recompute):
         self.recompute = bool(recompute)
+        self.ln_fused = False
         self.y = self.xl = None
         self.args = None
         self.rowmax = {}
@@ -789,7 +806,11 @@ class EdgeBlockContext:
             x_raw, _, _, gamma, beta, eps, weights, biases = self.args
             w2, b2 = [w.detach() for w in weights[:2]], [b.detach() for b in biases[:2]]
             with torch.no_grad():
-                if LN_FUSED:
+                if self.ln_fused and self.y is None and gemm_f16x2_ln_y_supported(x_raw.shape[0], self.n_out, x_raw.shape[1],
+                                                                                  x_raw.shape[1], 2 * self.n_out):
+                    # one pass over x_raw rebuilds the attention sources AND relu(LN(x_raw)) for the weight gradients
+                    self.xl, _, _, _, self.y = gemm_f16x2_groups_ln(x_raw, gamma, beta, eps, w2, b2, want_y=True)
+                elif self.ln_fused and self.y is None:
                     self.xl = gemm_f16x2_groups_ln(x_raw, gamma, beta, eps, w2, b2)[0]
                 else:
                     self.xl = gemm_f16x2_groups(self.get_y(), w2, b2)
@@ -824,11 +845,19 @@ class _EdgeBlockProject(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_raw, gamma, beta, eps, rc, *wb):
         weights, biases = wb[0::2], wb[1::2]
-        if LN_FUSED:
-            # LayerNorm + ReLU inside the GEMM's operand producer: x_raw is read once, relu(LN(x_raw)) never exists in memory
+        rc.ln_fused = LN_FUSED and (LN_FUSED_ANY_SHAPE or gemm_f16x2_ln_y_supported(
+            x_raw.shape[0], weights[0].shape[0], x_raw.shape[1], x_raw.shape[1], 3 * weights[0].shape[0]))
+        if rc.ln_fused:
+            # LayerNorm + ReLU inside the GEMM's operand producer: x_raw is read once; relu(LN(x_raw)) is written out only when
+            # backward will need it and it is not going to be recomputed (same pass, from the registers that hold it)
             x_raw, y = x_raw.contiguous(), None
             gamma, beta = gamma.contiguous(), beta.contiguous()
-            out, x_amax, mean, rstd = gemm_f16x2_groups_ln(x_raw, gamma, beta, eps, weights, biases)
+            M, K = x_raw.shape
+            keep_y = (not rc.recompute) and torch.is_grad_enabled() and gemm_f16x2_ln_y_supported(M, weights[0].shape[0], K, K, 3 * weights[0].shape[0])
+            if keep_y:
+                out, x_amax, mean, rstd, y = gemm_f16x2_groups_ln(x_raw, gamma, beta, eps, weights, biases, want_y=True)
+            else:
+                out, x_amax, mean, rstd = gemm_f16x2_groups_ln(x_raw, gamma, beta, eps, weights, biases)
         else:
             x_raw, y, mean, rstd, gamma, beta = _ln_relu_forward(x_raw, gamma, beta, eps)
             out, x_amax = gemm_f16x2_groups(y, weights, biases, want_amax=True)

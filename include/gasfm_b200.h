@@ -274,6 +274,14 @@ GASFM_API int gasfm_linear_f16x2_ln(const float* A, int64_t lda, const float* ln
                           float* ln_mean, float* ln_rstd, const void* B_hi, const void* B_lo,
                           const float* b_descale, const float* bias, float* C, int64_t ldc,
                           int64_t M, int N, int K, int groups, float* a_amax, void* stream);
+/* ... which also writes the normalised operand y[M, K] (row stride ldy) from the registers that hold it: the weight gradients of
+ * the same projections read it (dW = dY^T y), and a forward that keeps activations gets it without a separate LayerNorm pass.
+ * Only the N = K = 256 kernel (CTA pairs, cta_group::2) does this: ask gasfm_linear_f16x2_ln_y_supported first. */
+GASFM_API int gasfm_linear_f16x2_ln_y_supported(int64_t M, int N, int K, int64_t lda, int64_t ldc);
+GASFM_API int gasfm_linear_f16x2_ln_y(const float* A, int64_t lda, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                          float* ln_mean, float* ln_rstd, float* y, int64_t ldy, const void* B_hi, const void* B_lo,
+                          const float* b_descale, const float* bias, float* C, int64_t ldc,
+                          int64_t M, int N, int K, int groups, float* a_amax, void* stream);
 
 /* Weight gradient on the fp16 path: dW = dY^T X (+ db), each operand scaled by ONE power of two derived from its largest
  * magnitude (amax_dy[1], amax_x[1]: DEVICE scalars, as left behind by the GEMMs above that read the same matrices).

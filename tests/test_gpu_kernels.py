@@ -699,6 +699,12 @@ def test_gemm_f16x2_with_fused_layernorm_relu(M, K, N, G):
     y32 = ops.ln_relu(x, gamma, beta, 1e-5)
     ref32 = ops.gemm_f16x2_groups(y32, ws, bs) if G > 1 else ops.gemm_f16x2(y32, ws[0], bs[0])
     assert rel_err(out, ref32.double().cpu().numpy()) < FP32_TOL
+    # N = K = 256 (CTA-pair kernel): the normalised operand as a by-product of the same pass, projections bit-identical
+    assert ops.gemm_f16x2_ln_y_supported(M, N, K, K, G * N) == (N == 256 and K == 256)
+    if N == 256 and K == 256:
+        out2, amax2, mean2, rstd2, y_out = ops.gemm_f16x2_groups_ln(x, gamma, beta, 1e-5, ws, bs, want_y=True)
+        assert torch.equal(out2, out) and torch.equal(mean2, mean) and torch.equal(rstd2, rstd) and torch.equal(amax2, amax)
+        assert rel_err(y_out, y.cpu().numpy()) < 1e-5 and float(y_out.min()) >= 0.0
 
 
 @pytest.mark.parametrize("M,N,n_seg,seg_k", [(70001, 256, 3, 256), (1000, 256, 2, 256), (4099, 64, 3, 128), (129, 256, 4, 256), (300, 32, 1, 128)])

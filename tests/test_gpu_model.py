@@ -176,13 +176,14 @@ def test_cfg2_scale_model_matches_fp32_oracle():
     assert worst < GRAD_TOL, (key, worst)
 
 
-@pytest.mark.parametrize("ln_fused", [False, True])
-def test_activation_recompute_gives_identical_results(ln_fused, monkeypatch):
+@pytest.mark.parametrize("ln_fused,width", [(False, 128), (True, 128), (False, 256), (True, 256)])
+def test_activation_recompute_gives_identical_results(ln_fused, width, monkeypatch):
     """GASFM_RECOMPUTE: keeping only x_raw + LayerNorm statistics per block and rebuilding relu(LN(x)) and the projected
     attention sources in backward must not change a single bit of the outputs or gradients."""
     from gasfm_b200 import ops
     monkeypatch.setattr(ops, "LN_FUSED", ln_fused)          # LayerNorm + ReLU as its own kernel / inside the projection GEMM
-    conf = gasfm_conf(n_feat_proj=128, n_feat_view=128, n_feat_global=256, num_layers=3)
+    monkeypatch.setattr(ops, "LN_FUSED_ANY_SHAPE", ln_fused)   # (width 128: the cta_group::1 kernel; 256: the CTA-pair kernel)
+    conf = gasfm_conf(n_feat_proj=width, n_feat_view=128, n_feat_global=256, num_layers=3)
     torch.manual_seed(3)
     model = GraphAttnSfMNet(conf).to(DEV)
     idx, vals = gasfm_cpu.synthetic_observations(40, 4000, 30000, seed=3)
@@ -207,7 +208,7 @@ def test_activation_recompute_gives_identical_results(ln_fused, monkeypatch):
     for k, g in res["off"][2].items():
         assert torch.equal(g, res["on"][2][k]), k
     # activations held between forward and backward: each of the two fused blocks drops its three projections (and relu(LN(x)))
-    assert res["off"][3] - res["on"][3] > 2 * 2.5 * idx.shape[1] * 128 * 4
+    assert res["off"][3] - res["on"][3] > 2 * 2.5 * idx.shape[1] * width * 4
 
 
 def _mirrored_tracks(idx, vals, n):
