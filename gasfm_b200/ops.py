@@ -853,7 +853,8 @@ class _EdgeBlockProject(torch.autograd.Function):
             x_raw, y = x_raw.contiguous(), None
             gamma, beta = gamma.contiguous(), beta.contiguous()
             M, K = x_raw.shape
-            keep_y = (not rc.recompute) and torch.is_grad_enabled() and gemm_f16x2_ln_y_supported(M, weights[0].shape[0], K, K, 3 * weights[0].shape[0])
+            keep_y = ((not rc.recompute) and any(ctx.needs_input_grad) and       # (grad mode is always off inside Function.forward)
+                      gemm_f16x2_ln_y_supported(M, weights[0].shape[0], K, K, 3 * weights[0].shape[0]))
             if keep_y:
                 out, x_amax, mean, rstd, y = gemm_f16x2_groups_ln(x_raw, gamma, beta, eps, weights, biases, want_y=True)
             else:
