@@ -208,10 +208,16 @@ def kernel_roofline(cfg, peaks, peak_kind, forward_ms=None):
         f16 = ops.GEMM_KIND == "f16x2" and ops.gemm_f16x2_supported(E, HC, HC, HC, HC)
         gemm_ms = timed_batches(lambda: ops.gemm_tc(XL, W))
         if f16:
-            grp_ms = timed_batches(lambda: ops.gemm_f16x2_groups(XL, [W, W, W], [None, None, None]))
-            # write_frac: the bytes this kernel WRITES against the write half of the measured copy bandwidth -- a copy moves
-            # hbm_gbs / 2 in each direction, which is also the most one SM-side store stream was seen to sustain (~22 B/ns per SM)
-            res["gemm_f16x2 x3 groups (forward projections)"] = dict(
+            ln_fused = ops.LN_FUSED and ops.gemm_f16x2_ln_y_supported(E, HC, HC, HC, 3 * HC)
+            if ln_fused:
+                # as the model runs it: LayerNorm + ReLU inside the operand producer (x_raw in, three projections out)
+                gamma, beta = torch.rand(HC, device=dev) + 0.5, torch.randn(HC, device=dev) * 0.1
+                grp_ms = timed_batches(lambda: ops.gemm_f16x2_groups_ln(XL, gamma, beta, 1e-5, [W, W, W], [None, None, None]))
+            else:
+                grp_ms = timed_batches(lambda: ops.gemm_f16x2_groups(XL, [W, W, W], [None, None, None]))
+            # write_frac: the bytes this kernel WRITES against the write half of the measured copy bandwidth (a copy moves
+            # hbm_gbs / 2 in each direction)
+            res["gemm_f16x2 x3 groups (LayerNorm + ReLU + forward projections)" if ln_fused else "gemm_f16x2 x3 groups (forward projections)"] = dict(
                 bound="hbm", ms=grp_ms, work=4 * E * HC * 4, calls=n_blocks3, pipe_util=9 * flops / grp_ms / 1e9 / (2.0 * peak_tf32),
                 write_frac=3 * E * HC * 4 / grp_ms / 1e6 / (peak_gbs / 2))
             res["gemm_f16x2 (single projection)"] = dict(bound="hbm", ms=gemm_ms, work=io_bytes, calls=2,
