@@ -165,7 +165,7 @@ def timed_batches(fn, batches=5, per_batch=5, warmup=5):
 # ---------------------------------------------------------------------------------------------
 # roofline of the hot kernels, each timed alone
 # ---------------------------------------------------------------------------------------------
-def kernel_roofline(cfg, peaks, peak_kind, forward_ms=None):
+def kernel_roofline(cfg, peaks, peak_kind, forward_ms=None, recompute=False):
     """The hot kernels alone at the workload's shapes (E observations, width d = n_feat_proj), CUDA events.
 
     Edge-attention kernels, the scaled 2 x FP16 projections and the fp16 weight gradient are HBM-bound: achieved =
@@ -220,6 +220,12 @@ def kernel_roofline(cfg, peaks, peak_kind, forward_ms=None):
             res["gemm_f16x2 x3 groups (LayerNorm + ReLU + forward projections)" if ln_fused else "gemm_f16x2 x3 groups (forward projections)"] = dict(
                 bound="hbm", ms=grp_ms, work=4 * E * HC * 4, calls=n_blocks3, pipe_util=9 * flops / grp_ms / 1e9 / (2.0 * peak_tf32),
                 write_frac=3 * E * HC * 4 / grp_ms / 1e6 / (peak_gbs / 2))
+            if recompute and ln_fused:
+                # activation recompute: backward rebuilds the two attention sources and relu(LN(x)) in one more pass over x_raw
+                rc_ms = timed_batches(lambda: ops.gemm_f16x2_groups_ln(XL, gamma, beta, 1e-5, [W, W], [None, None], want_y=True))
+                res["gemm_f16x2 x2 groups + relu(LN(x)) (recompute in backward)"] = dict(
+                    bound="hbm", ms=rc_ms, work=4 * E * HC * 4, calls=n_blocks3, pipe_util=6 * flops / rc_ms / 1e9 / (2.0 * peak_tf32),
+                    write_frac=3 * E * HC * 4 / rc_ms / 1e6 / (peak_gbs / 2))
             res["gemm_f16x2 (single projection)"] = dict(bound="hbm", ms=gemm_ms, work=io_bytes, calls=2,
                                                          pipe_util=3 * flops / gemm_ms / 1e9 / (2.0 * peak_tf32),
                                                          write_frac=E * HC * 4 / gemm_ms / 1e6 / (peak_gbs / 2))
@@ -645,7 +651,7 @@ def run_ours(args):
             "clocks": r["clocks"], "roofline": None, "cpu_baseline": None, "parity": parity}
     if world == 1:
         if not args.no_roofline:
-            line["roofline"] = kernel_roofline(cfg, peaks, peak_kind, r["forward_ms"])
+            line["roofline"] = kernel_roofline(cfg, peaks, peak_kind, r["forward_ms"], recompute=r["recompute"])
             torch.cuda.empty_cache()
         if not args.no_cpu_baseline:
             line["cpu_baseline"], _, ref = cpu_baseline(cfg, repeats=1)

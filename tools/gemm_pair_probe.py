@@ -20,9 +20,10 @@ ws = [torch.randn(256, 256, device=dev) / 16 for _ in range(3)]
 bs = [torch.randn(256, device=dev) for _ in range(3)]
 gamma, beta = torch.rand(256, device=dev) + 0.5, torch.randn(256, device=dev) * 0.1
 if mode == "cat":
-    rm = x.abs().amax(dim=1)
+    dys = [x, torch.randn(E, 256, device=dev), torch.randn(E, 256, device=dev)]      # three different matrices, as in backward
+    rms = [d.abs().amax(dim=1) for d in dys]
     wcat = torch.cat(ws, dim=1)
-    fn = lambda: ops.gemm_f16x2_cat([x, x, x], wcat, rowmax=[rm, rm, rm])      # noqa: E731
+    fn = lambda: ops.gemm_f16x2_cat(dys, wcat, rowmax=rms)                    # noqa: E731
 elif mode == "ln":
     fn = lambda: ops.gemm_f16x2_groups_ln(x, gamma, beta, 1e-5, ws, bs)       # noqa: E731
 else:
