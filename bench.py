@@ -457,7 +457,10 @@ def measure_workload(cfg, args, dev, rank, world, exchange, scaling):
     n_eager = 3
     eager_ms = timed(lambda: step(scene_dev), n_eager, 1, sync_dist=sync)
     launches = (_lib.launch_count - l0) // (n_eager + 1)
-    recompute = bool(__import__("gasfm_b200.ops", fromlist=["ops"]).activation_recompute_enabled())
+    _ops = __import__("gasfm_b200.ops", fromlist=["ops"])
+    recompute = bool(_ops.activation_recompute_used())
+    recompute_blocks = list(_ops.last_recompute_plan)          # [blocks that recompute their activations, blocks]
+    peak_mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
 
     # the device-resident step is replayed as ONE CUDA graph (same kernels, no per-launch host overhead); sharded steps too:
     # their exchanges are peer-memory kernels, not NCCL calls
@@ -542,6 +545,7 @@ def measure_workload(cfg, args, dev, rank, world, exchange, scaling):
     return {"E": E_total, "n_total": n_total, "ms": ms, "value": E_total * n_gat / (ms / 1e3), "eager_ms": eager_ms,
             "forward_ms": fwd_ms, "e2e_ms": e2e_ms, "e2e_value": E_total * n_gat / (e2e_ms / 1e3), "h2d": int(h2d), "d2h": int(d2h),
             "launches": int(launches), "graphed": graphed, "clocks": clocks, "recompute": recompute,
+            "recompute_blocks": recompute_blocks, "peak_mem_gb": round(peak_mem_gb, 1),
             "e2e_graphed": e2e_graphed, "e2e_eager_ms": e2e_eager_ms}
 
 
@@ -643,7 +647,8 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wc,
             "forward_ms_per_scene": r["forward_ms"], "cuda_graph": r["graphed"], "eager_ms_per_step": r["eager_ms"],
-            "activation_recompute": r["recompute"], "exchange": exchange_kind, "exchange_kernels": exch,
+            "activation_recompute": r["recompute"], "recompute_blocks": r["recompute_blocks"], "peak_mem_gb_eager_step": r["peak_mem_gb"],
+            "exchange": exchange_kind, "exchange_kernels": exch,
             "e2e": {"value": r["e2e_value"], "unit": "edges/s", "ms_per_step": r["e2e_ms"],
                     "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                     "cuda_graph": r["e2e_graphed"], "eager_ms_per_step": r["e2e_eager_ms"]},

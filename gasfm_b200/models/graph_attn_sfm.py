@@ -103,22 +103,36 @@ class GraphAttnSfMNet(BaseNet):
         idx.shard = getattr(data, "shard", None) or getattr(x, "shard", None)     # track-sharded scene (gasfm_b200.dist)
         return SparseMat(x.values, x.indices, x.cam_per_pts, x.pts_per_cam, tuple(x.shape), _index=idx)
 
-    def _wants_recompute(self, n_obs, device):
-        """Activation recompute policy.  A block keeps five [E, n_feat_proj] fp32 tensors for backward (x_raw, the three
-        grouped projections and relu(LN(x_raw))); with recompute only x_raw stays.  "auto": switch it on when the kept
-        activations of all blocks would take more than half of the device memory."""
+    def _recompute_plan(self, n_obs, device):
+        """Activation recompute policy -> number of (leading) blocks that recompute.  A block keeps five [E, n_feat_proj] fp32
+        tensors for backward (x_raw, the three grouped projections and relu(LN(x_raw))); with recompute only x_raw stays.
+        "auto": nothing is recomputed while the kept activations of all blocks take less than half of the device memory;
+        beyond that the LAST blocks keep theirs as far as a conservative budget allows (their backward runs first and frees
+        them before the recomputed blocks need room): 80 % of the device minus what a fully recomputed step was measured to
+        hold at its peak -- 1.5 x_raw-sized tensors per block + 4 transient ones (cfg3 at d = 256: 101 GiB = 21.3 such tensors
+        for 12 blocks) -- at four tensors per kept block."""
+        n_blocks = len(self.equivariant_blocks)
         mode = ops.ACTIVATION_RECOMPUTE
-        if mode in ("on", "off"):
-            return mode == "on"
-        if not torch.is_grad_enabled():
-            return False
-        kept = 5.0 * n_obs * self.n_feat_proj * 4 * len(self.equivariant_blocks)
-        return kept > 0.5 * torch.cuda.get_device_properties(device).total_memory
+        if mode == "off" or (mode == "auto" and not torch.is_grad_enabled()):
+            return 0
+        unit = float(n_obs) * self.n_feat_proj * 4
+        total = torch.cuda.get_device_properties(device).total_memory
+        if mode == "auto" and 5.0 * unit * n_blocks <= 0.5 * total:
+            return 0
+        if ops.RECOMPUTE_KEEP != "auto":
+            keep = int(ops.RECOMPUTE_KEEP)
+        elif mode == "on":
+            keep = 0
+        else:
+            keep = int((0.8 * total - unit * (1.5 * n_blocks + 4.0)) // (4.0 * unit))
+        return n_blocks - max(0, min(n_blocks, keep))
 
     def forward(self, data):
         graph_structure = data.graph_wrappers
         observations = self._observations(data)
-        ops.set_activation_recompute(self._wants_recompute(observations.indices.shape[1], observations.values.device))
+        n_recompute = self._recompute_plan(observations.indices.shape[1], observations.values.device)
+        ops.last_recompute_plan = (n_recompute, len(self.equivariant_blocks))
+        ops.set_activation_recompute(n_recompute > 0, first_of_forward=True)
         projection_features = self.embed(observations)   # [m,n,2] -> [m,n,d_emb]
         if not self.use_norm_proj_update:
             # in-place ReLU aliasing of the reference (layers.py:982-984): without a norm layer, block 0
@@ -127,7 +141,8 @@ class GraphAttnSfMNet(BaseNet):
         skipconn = projection_features if self.add_skipconn_from_init_projfeat else None
         scenepoint_features = view_features = global_features = None
         stateful = self.stateful_global_features
-        for block in self.equivariant_blocks:
+        for i_block, block in enumerate(self.equivariant_blocks):
+            ops.set_activation_recompute(i_block < n_recompute)
             projection_features, scenepoint_features, view_features, global_features = block(
                 projection_features, graph_structure,
                 prev_scenepoint_features=scenepoint_features if stateful else None,

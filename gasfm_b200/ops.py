@@ -744,18 +744,30 @@ _LN_FUSED_MODE = os.environ.get("GASFM_LN_FUSED", "1")
 LN_FUSED = _LN_FUSED_MODE != "0"
 LN_FUSED_ANY_SHAPE = _LN_FUSED_MODE == "force"
 ACTIVATION_RECOMPUTE = os.environ.get("GASFM_RECOMPUTE", "auto")   # "on" | "off" | "auto" (decided per scene by the model)
+# "auto" keeps the activations of as many of the LAST blocks as fit (their backward runs first and frees them before the
+# recomputed blocks need room); GASFM_RECOMPUTE_KEEP=<k> fixes that number
+RECOMPUTE_KEEP = os.environ.get("GASFM_RECOMPUTE_KEEP", "auto")
 _recompute_now = False
+_recompute_any = False
+last_recompute_plan = (0, 0)      # (blocks recomputed, blocks) of the most recent forward with a policy decision
 
 
-def set_activation_recompute(flag):
-    """Forward passes issued while this is set keep only ``x_raw`` + LayerNorm statistics per block and rebuild
+def set_activation_recompute(flag, first_of_forward=False):
+    """Blocks whose forward is issued while this is set keep only ``x_raw`` + LayerNorm statistics and rebuild
     relu(LN(x_raw)) and the projected attention sources in backward (activation memory)."""
-    global _recompute_now
+    global _recompute_now, _recompute_any
     _recompute_now = bool(flag)
+    _recompute_any = bool(flag) if first_of_forward else (_recompute_any or bool(flag))
 
 
 def activation_recompute_enabled():
+    """Whether the block being issued recomputes its activations."""
     return _recompute_now
+
+
+def activation_recompute_used():
+    """Whether any block of the most recent forward pass recomputes its activations."""
+    return _recompute_any
 
 
 class EdgeBlockContext:

@@ -176,13 +176,15 @@ def test_cfg2_scale_model_matches_fp32_oracle():
     assert worst < GRAD_TOL, (key, worst)
 
 
-@pytest.mark.parametrize("ln_fused,width", [(False, 128), (True, 128), (False, 256), (True, 256)])
-def test_activation_recompute_gives_identical_results(ln_fused, width, monkeypatch):
+@pytest.mark.parametrize("ln_fused,width,keep", [(False, 128, "auto"), (True, 128, "auto"), (False, 256, "auto"), (True, 256, "auto"),
+                                                 (True, 256, "1")])
+def test_activation_recompute_gives_identical_results(ln_fused, width, keep, monkeypatch):
     """GASFM_RECOMPUTE: keeping only x_raw + LayerNorm statistics per block and rebuilding relu(LN(x)) and the projected
     attention sources in backward must not change a single bit of the outputs or gradients."""
     from gasfm_b200 import ops
     monkeypatch.setattr(ops, "LN_FUSED", ln_fused)          # LayerNorm + ReLU as its own kernel / inside the projection GEMM
     monkeypatch.setattr(ops, "LN_FUSED_ANY_SHAPE", ln_fused)   # (width 128: the cta_group::1 kernel; 256: the CTA-pair kernel)
+    monkeypatch.setattr(ops, "RECOMPUTE_KEEP", keep)           # "1": partial recompute, the last block keeps its activations
     conf = gasfm_conf(n_feat_proj=width, n_feat_view=128, n_feat_global=256, num_layers=3)
     torch.manual_seed(3)
     model = GraphAttnSfMNet(conf).to(DEV)
@@ -196,7 +198,7 @@ def test_activation_recompute_gives_identical_results(ln_fused, width, monkeypat
             model.zero_grad(set_to_none=True)
             torch.cuda.reset_peak_memory_stats()
             out = model(scene)
-            assert ops.activation_recompute_enabled() == (mode == "on")
+            assert ops.activation_recompute_used() == (mode == "on")
             kept = torch.cuda.memory_allocated()
             _loss(out).backward()
             res[mode] = (out["Ps_norm"].detach().clone(), out["pts3D"].detach().clone(),
@@ -208,7 +210,10 @@ def test_activation_recompute_gives_identical_results(ln_fused, width, monkeypat
     for k, g in res["off"][2].items():
         assert torch.equal(g, res["on"][2][k]), k
     # activations held between forward and backward: each of the two fused blocks drops its three projections (and relu(LN(x)))
-    assert res["off"][3] - res["on"][3] > 2 * 2.5 * idx.shape[1] * width * 4
+    n_rebuilt = 2 if keep == "auto" else 1
+    assert res["off"][3] - res["on"][3] > n_rebuilt * 2.5 * idx.shape[1] * width * 4
+    if keep != "auto":
+        assert ops.last_recompute_plan == (2, 3)
 
 
 def _mirrored_tracks(idx, vals, n):
