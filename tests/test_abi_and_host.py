@@ -54,6 +54,11 @@ def test_tensor_core_kernel_shape_predicates():
     assert lib.gasfm_wgrad_f16x2_supported(E, 256, 32, 256, 32) == 0
     assert lib.gasfm_wgrad_tf32x3_supported(E, 256, 32, 256, 32) == 1
     assert lib.gasfm_wgrad_small_supported(64, 64, 64, 64) == 1
+    # LayerNorm inside the GEMM with the normalised operand as a by-product: only the CTA-pair kernel (N = K = 256) writes it
+    assert lib.gasfm_linear_f16x2_ln_y_supported(E, 256, 256, 256, 768) == 1
+    assert lib.gasfm_linear_f16x2_ln_y_supported(E, 128, 128, 128, 384) == 0
+    assert lib.gasfm_linear_f16x2_ln_y_supported(E, 256, 192, 192, 768) == 0
+    assert lib.gasfm_update_bwd_views_ws_bytes(100, 256) > 0
     # workspace queries are pure host arithmetic too
     assert lib.gasfm_wgrad_f16x2_ws_bytes(256, 256) == (148 * 256 * 256 + 148 * 256) * 4
     assert lib.gasfm_col_sum_ws_bytes(100, 256) == 0 and lib.gasfm_col_sum_ws_bytes(50000, 256) == 195 * 256 * 4
