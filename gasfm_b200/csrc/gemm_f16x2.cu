@@ -1043,9 +1043,14 @@ constexpr int kCStageBytes = kPSlotBytes + kPBStageBytes;       // A hi | A lo |
 constexpr int kCStages = 3;
 constexpr size_t kCSmemBytes = (size_t)kCStages * kCStageBytes + 4 * 4096 + 1024;
 
-template <bool TRACE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFThreads, 1)
+// PWG: producer warpgroups (2, default: 8 rows per thread as in the other GEMMs; 4: 16 producer warps, 4 rows per thread,
+// GASFM_GEMM_CAT_PRODUCERS=16).  The timeline of the 8-warp form shows the operand producers setting the pace, but doubling them
+// does not help (6.42 vs 6.25 ms at cfg3): what they wait for is the operand loads and the shared-memory data pipe, not issue slots.
+template <bool TRACE, int PWG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * (PWG + 2), 1)
 gemm_f16x2_cat_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo, GemmF16Args p) {
+  constexpr int kThreads = 128 * (PWG + 2), kProducers = 128 * PWG, kRows = 16 / PWG, kRowStep = 8 * PWG;   // rows per thread / stride
+  constexpr int kEpiWarp0 = 4 * (PWG + 1);                     // first epilogue warp (a multiple of 4: warp % 4 = TMEM lane quarter)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* c_stage = smem + (size_t)kCStages * kCStageBytes;
@@ -1064,12 +1069,12 @@ gemm_f16x2_cat_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kCStages; ++s) {
-      mbar_init(&full_bar[s], 1); mbar_init(&split_bar[s], 256); mbar_init(&empty_bar[s], 1); mbar_init(&peer_bar[s], 1);
+      mbar_init(&full_bar[s], 1); mbar_init(&split_bar[s], kProducers); mbar_init(&empty_bar[s], 1); mbar_init(&peer_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int j = threadIdx.x; j < kPN; j += kFThreads) {
+  for (int j = threadIdx.x; j < kPN; j += kThreads) {
     bias_s[j] = p.bias ? p.bias[j] : 0.f;
     bscale_s[j] = p.b_scale[j];
   }
@@ -1084,7 +1089,10 @@ gemm_f16x2_cat_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+    // PWG == 4: launched with 80 registers per thread (768 threads); the redistribution must stay within that allocation:
+    // 128 x 24 + 512 x 88 + 128 x 96 = 60,416 <= 61,440 (asking for more makes the last setmaxnreg.inc wait forever)
+    if constexpr (PWG == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
     if (warp == 0 && lane == 0) {
       // ===================== TMA: this CTA's 128 weight rows, K block by K block =====================
       int stage = 0; uint32_t phase = 0;
@@ -1145,27 +1153,28 @@ gemm_f16x2_cat_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __
         }
       }
     }
-  } else if (warp < 12) {
+  } else if (warp < kEpiWarp0) {
     // ===================== A producers: K blocks of this CTA's 128 rows stream through four register buffers =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;" ::: "memory");
+    if constexpr (PWG == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;" ::: "memory");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 184;" ::: "memory");
     const int t = threadIdx.x - 128;
     const int q = t & 15, rg = t >> 4;
     int stage = 0; uint32_t phase = 0;
-    uint32_t soff[8];
+    uint32_t soff[kRows];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = rg + 16 * i;
+    for (int i = 0; i < kRows; ++i) {
+      const int row = rg + kRowStep * i;
       soff[i] = (uint32_t)(row * 128 + ((((q >> 1) ^ (row & 7))) << 4) + ((q & 1) << 3));
     }
     const uint32_t smem_base = smem_u32(smem);
     int64_t tr_it = 0; int tr_kb = 0;                            // (profiling only)
-    auto convert_block = [&](const float4 (&v)[8], const float (&scale)[8]) {
+    auto convert_block = [&](const float4 (&v)[kRows], const float (&scale)[kRows]) {
       if (t == 0) mbar_wait_backoff(&empty_bar[stage], phase ^ 1, 32);        // one polling lane, the rest block on the named barrier
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");
       if (t == 0) { GASFM_PTRACE(0, tr_it, tr_kb); }
       const uint32_t sb = smem_base + (uint32_t)stage * (uint32_t)kCStageBytes;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < kRows; ++i) {
         const float s = scale[i];
         const float x0 = v[i].x * s, x1 = v[i].y * s, x2 = v[i].z * s, x3 = v[i].w * s;
         const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
@@ -1182,30 +1191,30 @@ gemm_f16x2_cat_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __
       if (TRACE) { if (++tr_kb == nkb) { tr_kb = 0; ++tr_it; } }
       if (++stage == kCStages) { stage = 0; phase ^= 1; }
     };
-    auto load_kbg = [&](int64_t it, int kbg, float4 (&v)[8]) {
+    auto load_kbg = [&](int64_t it, int kbg, float4 (&v)[kRows]) {
       if (kbg >= nkb) { kbg -= nkb; ++it; }                     // the stream runs across tiles
       const int seg = kbg / kPKB, kcol = (kbg % kPKB) * kFBlockK + q * 4;
       const float* base = seg == 0 ? p.A_seg[0] : (seg == 1 ? p.A_seg[1] : (seg == 2 ? p.A_seg[2] : p.A_seg[3]));
       const int64_t ld = seg == 0 ? p.lda_seg[0] : (seg == 1 ? p.lda_seg[1] : (seg == 2 ? p.lda_seg[2] : p.lda_seg[3]));
       const int64_t row0 = ((cluster_id + it * num_clusters) * 2 + cta_rank) * kFBlockM;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t row = row0 + rg + 16 * i;
+      for (int i = 0; i < kRows; ++i) {
+        const int64_t row = row0 + rg + kRowStep * i;
         v[i] = (it < my_steps && row < p.M) ? ld_stream4(base + row * ld + kcol) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     float seg_seen[4] = {0.f, 0.f, 0.f, 0.f};
-    float4 v0[8], v1[8], v2[8], v3[8];
+    float4 v0[kRows], v1[kRows], v2[kRows], v3[kRows];
     // row scales of tile ``it`` from the upstream row maxima.  The device timeline of the first version showed the MMA stream
     // idle for ~12 k cycles at the start of EVERY tile: these loads (cold, queued behind 96 KB of streaming operand loads) sat
     // between two tiles.  Now the next tile's maxima are prefetched into L2 at the top of a tile and turned into scales before
     // the tile's LAST conversion, while the MMA still has two staged K blocks to work on.
-    auto tile_scales = [&](int64_t it, float (&scale)[8]) {
+    auto tile_scales = [&](int64_t it, float (&scale)[kRows]) {
       const int64_t row0 = ((cluster_id + it * num_clusters) * 2 + cta_rank) * kFBlockM;
       float* descale_slot = row_descale[it & (kFScaleSlots - 1)];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t row = row0 + rg + 16 * i;
+      for (int i = 0; i < kRows; ++i) {
+        const int64_t row = row0 + rg + kRowStep * i;
         float m = 0.f;
 #pragma unroll
         for (int seg = 0; seg < 4; ++seg) {
@@ -1217,7 +1226,7 @@ gemm_f16x2_cat_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __
         }
         float descale;
         row_scale_from_amax(m, scale[i], descale);
-        if (q == 0) descale_slot[rg + 16 * i] = descale;
+        if (q == 0) descale_slot[rg + kRowStep * i] = descale;
       }
     };
     auto prefetch_rowmax = [&](int64_t it) {                    // 128 rows x 4 B = 4 lines per segment
@@ -1229,11 +1238,11 @@ gemm_f16x2_cat_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __
       }
     };
     load_kbg(0, 0, v0); load_kbg(0, 1, v1); load_kbg(0, 2, v2);
-    float scale[8];
+    float scale[kRows];
     tile_scales(0, scale);
     for (int64_t it = 0; it < my_steps; ++it) {
       prefetch_rowmax(it + 1);
-      float scale_next[8];
+      float scale_next[kRows];
       for (int kbg = 0; kbg < nkb; kbg += 4) {                  // nkb % 4 == 0
         load_kbg(it, kbg + 3, v3);
         convert_block(v0, scale);
@@ -1246,7 +1255,7 @@ gemm_f16x2_cat_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __
         convert_block(v3, scale);
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) scale[i] = scale_next[i];
+      for (int i = 0; i < kRows; ++i) scale[i] = scale_next[i];
     }
     if (p.seg_amax != nullptr) {
 #pragma unroll
@@ -1255,9 +1264,10 @@ gemm_f16x2_cat_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __
     }
   } else {
     // ===================== epilogue: this CTA's 128 accumulator rows =====================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");
+    if constexpr (PWG == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;" ::: "memory");      // launched with 80
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");
     const int quarter = warp & 3;
-    const uint32_t stg = smem_u32(c_stage + (warp - 12) * 4096);
+    const uint32_t stg = smem_u32(c_stage + (warp - kEpiWarp0) * 4096);
     const int pc = lane & 3, rsub = lane >> 2;
     const uint32_t sts_base = stg + (uint32_t)(lane * 128 + ((lane & 7) << 4));
     const uint32_t lds_v = stg + (uint32_t)(rsub * 128 + (((2 * pc) ^ rsub) << 4)), lds_w = lds_v ^ 16u;
@@ -1270,18 +1280,18 @@ gemm_f16x2_cat_pair_kernel(const __grid_constant__ CUtensorMap map_bhi, const __
       float* rowp[4];
       mbar_wait_backoff(&tmem_full_bar[acc], acc_phase, 32);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (warp == 12 && lane == 0) GASFM_PTRACE(2, it, 0);
+      if (warp == kEpiWarp0 && lane == 0) GASFM_PTRACE(2, it, 0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         rs[i] = row_descale[it & (kFScaleSlots - 1)][quarter * 32 + 8 * i + rsub];
         rowp[i] = p.C + (row0 + 8 * i + rsub) * p.ldc + 8 * pc;
       }
       const uint32_t taddr0 = tmem_base + (uint32_t)(acc * kPN) + ((uint32_t)(quarter * 32) << 16);
-      pair_epilogue_drain<TRACE>(p, taddr0, sts_base, lds_v, lds_w, csg, bsg, rs, rowp, rows_left, (int)it, warp == 12 && lane == 0);
+      pair_epilogue_drain<TRACE>(p, taddr0, sts_base, lds_v, lds_w, csg, bsg, rs, rowp, rows_left, (int)it, warp == kEpiWarp0 && lane == 0);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive_remote_relaxed(&tmem_empty_bar[acc], 0);
-      if (warp == 12 && lane == 0) GASFM_PTRACE(2, it, 1);
+      if (warp == kEpiWarp0 && lane == 0) GASFM_PTRACE(2, it, 1);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -1479,13 +1489,17 @@ static int linear_f16x2_cat_impl(const float* const* A, const int64_t* lda, cons
         const int64_t pair_tiles = (M + 2 * kFBlockM - 1) / (2 * kFBlockM);
         const int pgrid = (int)(pair_tiles < kNumSMs / 2 ? pair_tiles : kNumSMs / 2) * 2;
         args.trace = g_trace;
-        auto kernel = g_trace ? gemm_f16x2_cat_pair_kernel<true> : gemm_f16x2_cat_pair_kernel<false>;
+        static int pwg = -1;                  // GASFM_GEMM_CAT_PRODUCERS=16: sixteen producer warps (A/B switch; default eight)
+        if (pwg < 0) { const char* env = getenv("GASFM_GEMM_CAT_PRODUCERS"); pwg = (env && atoi(env) == 16) ? 4 : 2; }
+        auto kernel = pwg == 4 ? (g_trace ? gemm_f16x2_cat_pair_kernel<true, 4> : gemm_f16x2_cat_pair_kernel<false, 4>)
+                               : (g_trace ? gemm_f16x2_cat_pair_kernel<true, 2> : gemm_f16x2_cat_pair_kernel<false, 2>);
+        const int threads = 128 * (pwg + 2);
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemBytes);
         if (e != cudaSuccess) {
           set_error("linear_f16x2_cat: cannot reserve %zu bytes of shared memory (%s)", kCSmemBytes, cudaGetErrorString(e));
           return (int)e;
         }
-        kernel<<<pgrid, kFThreads, kCSmemBytes, (cudaStream_t)stream>>>(mh, ml, args);
+        kernel<<<pgrid, threads, kCSmemBytes, (cudaStream_t)stream>>>(mh, ml, args);
         return check_launch("linear_f16x2_cat (pair)");
       }
     }
