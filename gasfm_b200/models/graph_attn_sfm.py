@@ -104,28 +104,9 @@ class GraphAttnSfMNet(BaseNet):
         return SparseMat(x.values, x.indices, x.cam_per_pts, x.pts_per_cam, tuple(x.shape), _index=idx)
 
     def _recompute_plan(self, n_obs, device):
-        """Activation recompute policy -> number of (leading) blocks that recompute.  A block keeps five [E, n_feat_proj] fp32
-        tensors for backward (x_raw, the three grouped projections and relu(LN(x_raw))); with recompute only x_raw stays.
-        "auto": nothing is recomputed while the kept activations of all blocks take less than half of the device memory;
-        beyond that the LAST blocks keep theirs as far as a conservative budget allows (their backward runs first and frees
-        them before the recomputed blocks need room): 80 % of the device minus what a fully recomputed step was measured to
-        hold at its peak -- 1.5 x_raw-sized tensors per block + 4 transient ones (cfg3 at d = 256: 101 GiB = 21.3 such tensors
-        for 12 blocks) -- at four tensors per kept block."""
-        n_blocks = len(self.equivariant_blocks)
-        mode = ops.ACTIVATION_RECOMPUTE
-        if mode == "off" or (mode == "auto" and not torch.is_grad_enabled()):
-            return 0
-        unit = float(n_obs) * self.n_feat_proj * 4
-        total = torch.cuda.get_device_properties(device).total_memory
-        if mode == "auto" and 5.0 * unit * n_blocks <= 0.5 * total:
-            return 0
-        if ops.RECOMPUTE_KEEP != "auto":
-            keep = int(ops.RECOMPUTE_KEEP)
-        elif mode == "on":
-            keep = 0
-        else:
-            keep = int((0.8 * total - unit * (1.5 * n_blocks + 4.0)) // (4.0 * unit))
-        return n_blocks - max(0, min(n_blocks, keep))
+        """Number of leading blocks that recompute their activations in backward (policy: ``ops.recompute_plan``)."""
+        return ops.recompute_plan(n_obs, self.n_feat_proj, len(self.equivariant_blocks),
+                                  torch.cuda.get_device_properties(device).total_memory, torch.is_grad_enabled())
 
     def forward(self, data):
         graph_structure = data.graph_wrappers

@@ -752,6 +752,31 @@ _recompute_any = False
 last_recompute_plan = (0, 0)      # (blocks recomputed, blocks) of the most recent forward with a policy decision
 
 
+def recompute_plan(n_obs, width, n_blocks, total_memory, grad_enabled=True, mode=None, keep=None):
+    """Activation recompute policy -> number of (leading) blocks that recompute (pure arithmetic, no device access).
+
+    A block keeps five [E, width] fp32 tensors for backward (x_raw, the three grouped projections and relu(LN(x_raw))); with
+    recompute only x_raw stays.  "auto": nothing is recomputed while the kept activations of all blocks take less than half of
+    the device memory; beyond that the LAST blocks keep theirs as far as a conservative budget allows (their backward runs
+    first and frees them before the recomputed blocks need room): 80 % of the device minus what a fully recomputed step was
+    measured to hold at its peak -- 1.5 x_raw-sized tensors per block + 4 transient ones (cfg3 at d = 256: 101 GiB = 21.3 such
+    tensors for 12 blocks) -- at four tensors per kept block.  "on": every block (unless ``keep`` says otherwise); "off": none."""
+    mode = ACTIVATION_RECOMPUTE if mode is None else mode
+    keep = RECOMPUTE_KEEP if keep is None else keep
+    if mode == "off" or (mode == "auto" and not grad_enabled):
+        return 0
+    unit = float(n_obs) * width * 4
+    if mode == "auto" and 5.0 * unit * n_blocks <= 0.5 * total_memory:
+        return 0
+    if keep != "auto":
+        kept = int(keep)
+    elif mode == "on":
+        kept = 0
+    else:
+        kept = int((0.8 * total_memory - unit * (1.5 * n_blocks + 4.0)) // (4.0 * unit))
+    return n_blocks - max(0, min(n_blocks, kept))
+
+
 def set_activation_recompute(flag, first_of_forward=False):
     """Blocks whose forward is issued while this is set keep only ``x_raw`` + LayerNorm statistics and rebuild
     relu(LN(x_raw)) and the projected attention sources in backward (activation memory)."""

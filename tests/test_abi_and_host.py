@@ -157,3 +157,19 @@ def test_module_tree_equals_live_reference_shipped_conf():
     assert list(a) == list(b)                                          # same names, same ORDER
     assert all(a[k].shape == b[k].shape for k in a)
     ours.load_state_dict(a, strict=True)
+
+
+def test_activation_recompute_plan():
+    """Which blocks recompute their [E, d] activations (pure host arithmetic): nothing while everything fits in half of the
+    device, otherwise the LAST blocks keep theirs as far as the budget allows; BASELINE.json configs[2] at d = 256 on a 180 GB
+    part as measured (1 GPU: 11 of 12 recompute; half the tracks per GPU: 3 of 12; a quarter: none)."""
+    from gasfm_b200 import ops
+    total = 191_500_000_000
+    E = 4_987_789
+    plan = lambda e, **kw: ops.recompute_plan(e, 256, 12, total, **{"mode": "auto", "keep": "auto", **kw})   # noqa: E731
+    assert plan(E) == 11 and plan(E // 2) == 3 and plan(E // 4) == 0 and plan(E // 8) == 0
+    assert plan(E, grad_enabled=False) == 0                       # inference keeps nothing anyway
+    assert plan(495_592) == 0                                     # cfg2
+    assert plan(E, mode="off") == 0 and plan(495_592, mode="on") == 12
+    assert plan(E, keep="3") == 9 and plan(495_592, mode="on", keep="1") == 11 and plan(E, keep="99") == 0
+    assert plan(3 * E) == 12                                      # nothing fits: every block recomputes
