@@ -41,6 +41,7 @@ struct WgradF16Args {
   const float* dY[kHMaxGroups]; int64_t lddy[kHMaxGroups]; const float* X; int64_t ldx;
   const float* amax_dy /* [n_groups] */; const float* amax_x;
   float* ws; float* ws_db; int64_t E; int Nout; int Kout; int m_tiles; int tmem_cols; int64_t rows_per_cta; int pass_stages;
+  int prefetch;                               // L2 prefetch distance in stages beyond the register stages (0 = off)
   int n_groups;                              // CTA b works on group b % n_groups, row range b / n_groups: the CTAs that read the
 };                                           // same rows of X are launched together, so X comes from HBM once and from L2 after
 
@@ -159,6 +160,20 @@ __global__ void __launch_bounds__(kHThreads, 1) wgrad_f16x2_kernel(WgradF16Args 
         for (int i = 0; i < RPT; ++i) {
           a[i] = ld_stream4(ba + (toff_a + (uint32_t)i * step_a));
           b[i] = ld_stream4(bb + (toff_b + (uint32_t)i * step_b));
+        }
+        // ncu (profiles/r02_wgrad_multi_cfg3_ncu_full.csv): 25 % of all samples are the first use of these loads -- two register
+        // stages are one stage period of lead, less than the HBM latency under load.  Optional experiment (off by default,
+        // GASFM_WGRAD_PREFETCH=<stages>): one lane per 128-byte line pulls the lines of a later stage into L2.  Measured SLOWER
+        // (three dW of a block at cfg2: 0.672 ms without, 0.703 at 2 stages, 0.720 at 4): the prefetches are extra requests on
+        // the same saturated path and do not shorten what the loads wait for.
+        if (p.prefetch > 0 && (col4 & 7) == 0 && e0 + (int64_t)(p.prefetch + 1) * kHRows <= row_end) {
+          const float* pa = ba + (int64_t)p.prefetch * kHRows * lddyg;
+          const float* pb = bb + (int64_t)p.prefetch * kHRows * p.ldx;
+#pragma unroll
+          for (int i = 0; i < RPT; ++i) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + (toff_a + (uint32_t)i * step_a)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + (toff_b + (uint32_t)i * step_b)));
+          }
         }
         return;
       }
@@ -377,6 +392,9 @@ static int wgrad_f16x2_launch(const float* const* dY, const int64_t* lddy, int n
   for (int g = 0; g < n_groups; ++g) { a.dY[g] = dY[g]; a.lddy[g] = lddy[g]; }
   a.X = X; a.ldx = ldx; a.amax_dy = amax_dy; a.amax_x = amax_x; a.ws = (float*)ws; a.ws_db = ws_db; a.E = E; a.Nout = Nout; a.Kout = Kout;
   a.m_tiles = m_tiles; a.tmem_cols = tmem_cols; a.rows_per_cta = rows_per_cta; a.pass_stages = pass_stages; a.n_groups = n_groups;
+  static int prefetch = -1;                   // GASFM_WGRAD_PREFETCH=<stages> (0 = off; A/B switch)
+  if (prefetch < 0) { const char* env = getenv("GASFM_WGRAD_PREFETCH"); prefetch = env ? atoi(env) : 0; }
+  a.prefetch = prefetch;
   cudaStream_t st = (cudaStream_t)stream;
   bool full = Nout == 256 && Kout == 256 && ldx < (1 << 24);
   for (int g = 0; g < n_groups; ++g) full = full && lddy[g] < (1 << 24);
