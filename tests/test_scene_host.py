@@ -42,3 +42,21 @@ def test_to_keeps_the_aliases_and_invalidate_drops_cached_structure():
     setattr(moved.graph_wrappers["view2global"], _PLAN_ATTR, object())
     moved.invalidate()
     assert not hasattr(moved.x, _INDEX_ATTR) and not hasattr(moved.graph_wrappers["view2global"], _PLAN_ATTR)
+
+
+def test_deferred_index_validation_bookkeeping():
+    """The streamed step builds the observation index inside a captured graph, so the status word cannot be read back during
+    the build: the context collects what to check later; the status bits map to the same errors as the immediate check."""
+    from gasfm_b200 import index
+    assert index._DeferredValidation.active is None
+    with index.deferred_validation() as outer:
+        assert index._DeferredValidation.active is outer
+        with index.deferred_validation() as inner:
+            assert index._DeferredValidation.active is inner
+        assert index._DeferredValidation.active is outer and outer.entries == []
+    assert index._DeferredValidation.active is None
+    index.raise_for_status(0, 3, 4)
+    with pytest.raises(ValueError, match="out of range"):
+        index.raise_for_status(1, 3, 4)
+    with pytest.raises(ValueError, match="row-major sorted"):
+        index.raise_for_status(2, 3, 4)
